@@ -1,0 +1,102 @@
+/*
+ * sd_b200.h -- C ABI of the B200-native string-decomposition DP (libsd_b200.so).
+ *
+ * The reference (ablab/stringdecomposer v1.1.2) has no FFI: its boundary is the process CLI of the `dp`
+ * binary that stringdecomposer/main.py:194 spawns.  The entry points below are what a binding for that
+ * path would need; each cites the reference code it replaces (paths relative to
+ * stringdecomposer/src/main.cpp).  Plain C types only, caller-owned inputs, library-owned outputs that
+ * are released with sd_free(), integer status codes (0 = ok), no exceptions cross the boundary.
+ * A handle may be used from one host thread at a time.  There is no CPU fallback: sd_create() fails
+ * with SD_ERR_NO_DEVICE when no CUDA device is usable.
+ */
+#ifndef SD_B200_H
+#define SD_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sd_handle sd_handle;
+
+enum {
+    SD_OK = 0,
+    SD_ERR_ARG = 1,          /* bad argument (NULL, negative size, symbol outside ACGTN, ...) */
+    SD_ERR_NO_DEVICE = 2,    /* no usable CUDA device / CUDA runtime error at start-up */
+    SD_ERR_UNSUPPORTED = 3,  /* outside the supported domain (monomer set too large for this build, scores reaching
+                                the reference's INF sentinel, ed_thr pre-filter) */
+    SD_ERR_CUDA = 4,         /* CUDA failure while running */
+    SD_ERR_INTERNAL = 5,
+    SD_ERR_INPUT = 255       /* illegal FASTA symbol: the reference exits with status 255 (main.cpp:333-336) */
+};
+
+/* One monomer alignment of a segment -- MonomerAlignment (main.cpp:37-49) with the monomer kept as a DP-row
+ * index: rows 0..M-1 are the forward monomers in input order, rows M..2M-1 their reverse complements in the
+ * same order (add_reverse_complement, main.cpp:364-371).  start/end are segment-relative read positions
+ * (main.cpp:225,254,259), score is the `identity` field the raw TSV prints (main.cpp:225,255,279). */
+typedef struct { int32_t row, start, end, score; } sd_record;
+
+typedef struct {
+    double sweep_ms, traceback_ms;      /* CUDA-event time of the kernels, max over devices, accumulated */
+    double h2d_ms, d2h_ms;
+    int64_t h2d_bytes, d2h_bytes;
+    int64_t cells;                      /* cell updates computed: sum over segments n_seg * sum of row lengths */
+    int64_t segments, columns;
+    int64_t launches;                   /* kernels launched */
+    int32_t n_devices;
+    int32_t packed;                     /* 1: s16x2 sweep, 0: s32 sweep (last call) */
+    int32_t C, T, NS, NT;               /* launch geometry of the last call */
+} sd_stats;
+
+/* Replaces the MonomersAligner constructor (main.cpp:59-65) + add_reverse_complement (main.cpp:364-371).
+ * monomers: the forward monomers as upper-case ACGTN text, concatenated; monomer j is
+ * monomers[offsets[j] .. offsets[j+1]).  device_ids may be NULL (n_devices = 0 -> device 0; n_devices = -1 ->
+ * all visible devices). */
+int sd_create(const char *monomers, const int64_t *offsets, int32_t n_monomers,
+              int32_t ins, int32_t del, int32_t mismatch, int32_t match,
+              const int32_t *device_ids, int32_t n_devices, sd_handle **out);
+
+/* Replaces the per-segment calls of AlignPartClassicDP (main.cpp:151-270) that AlignReadsSet issues under OpenMP
+ * (main.cpp:87-102).  segments: ACGTN text of all segments back to back, segment s = [offsets[s], offsets[s+1]).
+ * On success *records holds the alignments of all segments in segment order, each segment's in read order,
+ * and (*rec_offsets)[s .. s+1] delimits segment s (n_segments+1 entries).  Release both with sd_free(). */
+int sd_decompose(sd_handle *h, const char *segments, const int64_t *offsets, int64_t n_segments,
+                 sd_record **records, int64_t **rec_offsets);
+
+/* The same call split in three so that the kernels can be timed with inputs resident in HBM:
+ * sd_stage copies the segments to the device(s), sd_run_staged runs sweep + traceback (may be repeated),
+ * sd_fetch_staged returns the records.  Only valid when the batch fits one wave per device. */
+int sd_stage(sd_handle *h, const char *segments, const int64_t *offsets, int64_t n_segments);
+int sd_run_staged(sd_handle *h, double *kernel_ms);
+int sd_fetch_staged(sd_handle *h, sd_record **records, int64_t **rec_offsets);
+
+/* Replaces AlignReadsSet's segmentation (main.cpp:70-81).  Returns the number of segments of a read of
+ * read_len symbols; fills offs/lens (capacity cap) when they are not NULL.  Negative on bad arguments. */
+int64_t sd_segment_read(int64_t read_len, int32_t part_size, int32_t overlap, int64_t *offs, int32_t *lens, int64_t cap);
+
+/* Replaces PostProcessing (main.cpp:287-302) on read-relative records.  Returns the number kept (<= n). */
+int64_t sd_postprocess(const sd_record *in, int64_t n, sd_record *out);
+
+/* Replaces main() of the `dp` binary (main.cpp:374-402) after argument parsing: load_fasta of both files
+ * (main.cpp:314-346), reverse complements, segmentation, DP, overlap resolution, SaveBatch (main.cpp:272-285).
+ * The raw TSV goes to out_fd, the reference's diagnostics to err_fd.  Returns the process exit status the
+ * reference would produce (0, or 255 for an illegal symbol) or an SD_ERR_* code. */
+int sd_run_files(const char *reads_path, const char *monomers_path, int32_t threads, int32_t part_size,
+                 int32_t overlap, int32_t ins, int32_t del, int32_t mismatch, int32_t match, int32_t ed_thr,
+                 int out_fd, int err_fd);
+
+int sd_get_stats(sd_handle *h, sd_stats *out);
+void sd_reset_stats(sd_handle *h);
+const char *sd_last_error(sd_handle *h);       /* h may be NULL: error of the last failed sd_create/sd_run_files */
+void sd_free(void *p);
+void sd_destroy(sd_handle *h);
+int sd_device_count(void);
+const char *sd_version(void);
+
+/* Measures the integer-pipe issue rate (lane-ops per second) the roofline is quoted against: streams of
+ * independent VIADDMNMX.S16x2 (ALU pipe) and IMAD (FMA pipe) instructions on every SM of `device`. */
+int sd_int_peak(int32_t device, double *alu_lane_ops_per_s, double *alu_fma_lane_ops_per_s, double *sm_clock_mhz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,233 @@
+// api.cpp -- the C ABI declared in include/sd_b200.h.
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <unistd.h>
+
+#include "../../include/sd_b200.h"
+#include "pipeline.h"
+
+using namespace sdb;
+
+#ifdef SD_EMULATOR_BUILD
+static const bool kEmu = true;      // libsd_emu.so: CPU test-suite only
+#else
+static const bool kEmu = false;     // libsd_b200.so: CUDA only, no fallback
+#endif
+
+struct sd_handle {
+    std::unique_ptr<Engine> eng;
+    std::string err;
+    int n_devices = 0;
+};
+
+static std::string g_err;
+static std::mutex g_mu;
+static void set_global_error(const std::string &e) { std::lock_guard<std::mutex> l(g_mu); g_err = e; }
+
+#ifndef SD_EMULATOR_BUILD
+namespace sdb { Backend *make_emu_backend() { return nullptr; } }
+int cuda_device_count();
+int cuda_int_peak(int device, double *alu, double *both, double *mhz, std::string &err);
+#else
+namespace sdb { Backend *make_cuda_backend(int, std::string &err) { err = "emulator build"; return nullptr; } }
+static int cuda_device_count() { return 1; }
+static int cuda_int_peak(int, double *, double *, double *, std::string &err) { err = "emulator build has no device"; return SD_ERR_NO_DEVICE; }
+#endif
+
+static int make_backends(const int32_t *ids, int32_t n, std::vector<std::unique_ptr<Backend>> &out, std::string &err)
+{
+    if (kEmu) { out.emplace_back(make_emu_backend()); return SD_OK; }
+    std::vector<int> dev;
+    const int avail = cuda_device_count();
+    if (avail <= 0) { err = "no CUDA device is visible: libsd_b200 has no CPU path"; return SD_ERR_NO_DEVICE; }
+    if (n == 0) dev.push_back(0);
+    else if (n < 0) for (int d = 0; d < avail; ++d) dev.push_back(d);
+    else for (int i = 0; i < n; ++i) dev.push_back(ids ? ids[i] : i);
+    for (int d : dev) {
+        if (d < 0 || d >= avail) { err = "device id out of range"; return SD_ERR_ARG; }
+        Backend *b = make_cuda_backend(d, err);
+        if (!b) return SD_ERR_NO_DEVICE;
+        out.emplace_back(b);
+    }
+    return SD_OK;
+}
+
+static int to_batch(const char *segments, const int64_t *offsets, int64_t n, Batch &b, std::string &err)
+{
+    if (n < 0 || (n > 0 && (!segments || !offsets))) { err = "bad segment arguments"; return SD_ERR_ARG; }
+    b.off.assign((size_t)n + 1, 0);
+    const int64_t base = n ? offsets[0] : 0;
+    for (int64_t s = 0; s <= n && n; ++s) {
+        b.off[(size_t)s] = offsets[s] - base;
+        if (s && offsets[s] <= offsets[s - 1]) { err = "segments must be non-empty and offsets increasing"; return SD_ERR_ARG; }
+    }
+    const int64_t total = n ? offsets[n] - base : 0;
+    b.bases.resize((size_t)total);
+    for (int64_t x = 0; x < total; ++x) {
+        int c = base_code(segments[base + x]);
+        if (c < 0) { err = "segment contains a symbol outside ACGTN"; return SD_ERR_INPUT; }
+        b.bases[(size_t)x] = (uint8_t)c;
+    }
+    return SD_OK;
+}
+
+static int export_result(const BatchResult &res, sd_record **records, int64_t **rec_offsets)
+{
+    static_assert(sizeof(sd_record) == sizeof(Record), "record layout");
+    sd_record *r = (sd_record *)malloc(sizeof(sd_record) * std::max<size_t>(res.recs.size(), 1));
+    int64_t *o = (int64_t *)malloc(sizeof(int64_t) * res.rec_off.size());
+    if (!r || !o) { free(r); free(o); return SD_ERR_INTERNAL; }
+    if (!res.recs.empty()) memcpy(r, res.recs.data(), sizeof(sd_record) * res.recs.size());
+    memcpy(o, res.rec_off.data(), sizeof(int64_t) * res.rec_off.size());
+    *records = r; *rec_offsets = o;
+    return SD_OK;
+}
+
+extern "C" {
+
+int sd_create(const char *monomers, const int64_t *offsets, int32_t n_monomers, int32_t ins, int32_t del,
+              int32_t mismatch, int32_t match, const int32_t *device_ids, int32_t n_devices, sd_handle **out)
+{
+    if (!out) return SD_ERR_ARG;
+    *out = nullptr;
+    if (!monomers || !offsets || n_monomers <= 0) { set_global_error("bad monomer arguments"); return SD_ERR_ARG; }
+    std::vector<std::string> fwd;
+    for (int j = 0; j < n_monomers; ++j) {
+        if (offsets[j + 1] <= offsets[j]) { set_global_error("monomers must be non-empty"); return SD_ERR_ARG; }
+        fwd.emplace_back(monomers + offsets[j], (size_t)(offsets[j + 1] - offsets[j]));
+    }
+    std::string err;
+    std::vector<std::unique_ptr<Backend>> devs;
+    int st = make_backends(device_ids, n_devices, devs, err);
+    if (st) { set_global_error(err); return st; }
+    try {
+        std::unique_ptr<sd_handle> h(new sd_handle);
+        h->n_devices = (int)devs.size();
+        Scoring sc; sc.ins = ins; sc.del = del; sc.mismatch = mismatch; sc.match = match;
+        h->eng.reset(new Engine(fwd, sc, std::move(devs)));
+        *out = h.release();
+    } catch (PlanError &e) { set_global_error(e.msg); return SD_ERR_ARG; }
+    return SD_OK;
+}
+
+int sd_decompose(sd_handle *h, const char *segments, const int64_t *offsets, int64_t n_segments,
+                 sd_record **records, int64_t **rec_offsets)
+{
+    if (!h || !records || !rec_offsets) return SD_ERR_ARG;
+    Batch b;
+    int st = to_batch(segments, offsets, n_segments, b, h->err);
+    if (st) return st;
+    BatchResult res;
+    try { h->eng->decompose(b, res); }
+    catch (PlanError &e) { h->err = e.msg; return e.msg.find("CUDA") != std::string::npos ? SD_ERR_CUDA : SD_ERR_UNSUPPORTED; }
+    catch (std::exception &e) { h->err = e.what(); return SD_ERR_INTERNAL; }
+    return export_result(res, records, rec_offsets);
+}
+
+int sd_stage(sd_handle *h, const char *segments, const int64_t *offsets, int64_t n_segments)
+{
+    if (!h) return SD_ERR_ARG;
+    Batch b;
+    int st = to_batch(segments, offsets, n_segments, b, h->err);
+    if (st) return st;
+    try { h->eng->stage(b); }
+    catch (PlanError &e) { h->err = e.msg; return e.msg.find("CUDA") != std::string::npos ? SD_ERR_CUDA : SD_ERR_UNSUPPORTED; }
+    return SD_OK;
+}
+
+int sd_run_staged(sd_handle *h, double *kernel_ms)
+{
+    if (!h) return SD_ERR_ARG;
+    try { double ms = h->eng->run_staged(); if (kernel_ms) *kernel_ms = ms; }
+    catch (PlanError &e) { h->err = e.msg; return SD_ERR_CUDA; }
+    return SD_OK;
+}
+
+int sd_fetch_staged(sd_handle *h, sd_record **records, int64_t **rec_offsets)
+{
+    if (!h || !records || !rec_offsets) return SD_ERR_ARG;
+    BatchResult res;
+    try { h->eng->fetch_staged(res); }
+    catch (PlanError &e) { h->err = e.msg; return SD_ERR_CUDA; }
+    return export_result(res, records, rec_offsets);
+}
+
+int64_t sd_segment_read(int64_t read_len, int32_t part_size, int32_t overlap, int64_t *offs, int32_t *lens, int64_t cap)
+{
+    if (read_len < 0) return -1;
+    std::vector<std::pair<int, int>> v;
+    int64_t n = segment_read(read_len, part_size, overlap, &v);
+    if (n < 0) return n;
+    if (offs && lens) for (int64_t i = 0; i < n && i < cap; ++i) { offs[i] = v[(size_t)i].first; lens[i] = v[(size_t)i].second; }
+    return n;
+}
+
+int64_t sd_postprocess(const sd_record *in, int64_t n, sd_record *out)
+{
+    if (n < 0 || (n && (!in || !out))) return -1;
+    std::vector<Record> a((size_t)n), b;
+    if (n) memcpy(a.data(), in, sizeof(Record) * (size_t)n);
+    postprocess(a, b);
+    if (!b.empty()) memcpy(out, b.data(), sizeof(Record) * b.size());
+    return (int64_t)b.size();
+}
+
+int sd_run_files(const char *reads_path, const char *monomers_path, int32_t threads, int32_t part_size, int32_t overlap,
+                 int32_t ins, int32_t del, int32_t mismatch, int32_t match, int32_t ed_thr, int out_fd, int err_fd)
+{
+    if (!reads_path || !monomers_path) return SD_ERR_ARG;
+    std::string err;
+    std::vector<std::unique_ptr<Backend>> devs;
+    int32_t ndev = 0;
+    if (const char *e = getenv("SD_DEVICES")) ndev = (strcmp(e, "all") == 0) ? -1 : atoi(e);
+    int st = make_backends(nullptr, ndev, devs, err);
+    if (st) {
+        set_global_error(err);
+        std::string m = "ERROR: " + err + "\n";
+        if (::write(err_fd, m.data(), m.size()) < 0) {}
+        return st;
+    }
+    Scoring sc; sc.ins = ins; sc.del = del; sc.mismatch = mismatch; sc.match = match;
+    st = run_files(reads_path, monomers_path, threads, part_size, overlap, sc, ed_thr, std::move(devs), out_fd, err_fd, err);
+    if (!err.empty()) set_global_error(err);
+    return st;
+}
+
+int sd_get_stats(sd_handle *h, sd_stats *o)
+{
+    if (!h || !o) return SD_ERR_ARG;
+    const EngineStats &s = h->eng->stats;
+    memset(o, 0, sizeof *o);
+    o->sweep_ms = s.sweep_ms; o->traceback_ms = s.traceback_ms; o->h2d_ms = s.h2d_ms; o->d2h_ms = s.d2h_ms;
+    o->h2d_bytes = s.h2d_bytes; o->d2h_bytes = s.d2h_bytes; o->cells = s.cells; o->segments = s.segments;
+    o->columns = s.columns; o->launches = s.launches; o->n_devices = h->n_devices;
+    o->packed = s.g.packed; o->C = s.g.C; o->T = s.g.T; o->NS = s.g.NS; o->NT = s.g.NT;
+    return SD_OK;
+}
+
+void sd_reset_stats(sd_handle *h) { if (h) { Geometry g = h->eng->stats.g; h->eng->stats = EngineStats(); h->eng->stats.g = g; } }
+
+const char *sd_last_error(sd_handle *h)
+{
+    if (h) return h->err.c_str();
+    std::lock_guard<std::mutex> l(g_mu);
+    static thread_local std::string copy;
+    copy = g_err;
+    return copy.c_str();
+}
+
+void sd_free(void *p) { free(p); }
+void sd_destroy(sd_handle *h) { delete h; }
+int sd_device_count(void) { return kEmu ? 0 : cuda_device_count(); }
+const char *sd_version(void) { return kEmu ? "stringdecomposer_b200 0.1 (host emulator, tests only)" : "stringdecomposer_b200 0.1 (sm_100a)"; }
+
+int sd_int_peak(int32_t device, double *alu, double *both, double *mhz)
+{
+    std::string err;
+    int st = cuda_int_peak(device, alu, both, mhz, err);
+    if (st) set_global_error(err);
+    return st;
+}
+
+} // extern "C"

@@ -1,0 +1,92 @@
+// common.h -- host-side types shared by the planner, the pipeline, the CUDA backend and the test emulator.
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "sweep_core.cuh"
+
+namespace sdb {
+
+struct Scoring { int ins = -1, del = -1, mismatch = -1, match = 1; };   // main.cpp:380 defaults
+
+// Symbol codes: A C G T N -> 0..4 (N is a fifth symbol that matches itself, main.cpp:190,330).
+inline int base_code(char c)
+{
+    switch (c) { case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'T': return 3; case 'N': return 4; default: return -1; }
+}
+
+// DP rows: forward monomers in input order, then the reverse complement of each (main.cpp:364-371).
+struct MonomerSet {
+    int M = 0;                       // forward monomers; rows = 2M
+    std::vector<uint8_t> rows;       // symbol codes of all 2M rows, concatenated
+    std::vector<int> row_off;        // 2M+1 offsets into rows
+    int Lmax = 0, Lmin = 0;
+    int nrows() const { return 2 * M; }
+    int rowlen(int r) const { return row_off[r + 1] - row_off[r]; }
+};
+
+// Everything a backend needs that depends only on (monomers, scoring, launch geometry).
+struct Plan {
+    Geometry g{};
+    Scoring sc;
+    int deadz = 0;                       // "minus infinity" in tag-3 form
+    int nsl = 0;                         // slot lanes per segment = nslots*T
+    std::vector<uint32_t> prof;          // [5 symbols][C/4][nsl][4] profile words 4*s'' (pad cells: very negative)
+    std::vector<int> slot_len;           // row length of each slot
+    std::vector<int> slot_endadd;        // (L-1)*del of each slot
+    size_t smem_bytes(int seg_stride) const;
+};
+
+// A batch of segments to decompose (symbol codes, concatenated).
+struct Batch {
+    std::vector<uint8_t> bases;          // all segments back to back
+    std::vector<int64_t> off;            // nseg+1
+    int nseg() const { return (int)off.size() - 1; }
+    int len(int s) const { return (int)(off[s + 1] - off[s]); }
+};
+
+struct BatchResult {
+    std::vector<Record> recs;            // per segment in read order (already reversed), positions segment-relative
+    std::vector<int64_t> rec_off;        // nseg+1
+};
+
+struct PlanError { std::string msg; };
+
+// plan.cpp
+void build_monomer_set(const std::vector<std::string> &forward, MonomerSet &ms);     // throws PlanError
+// nseg_hint/n_hint steer the geometry heuristic (few long segments -> more lanes per slot).
+Plan make_plan(const MonomerSet &ms, const Scoring &sc, int max_seg_len, int64_t nseg_hint);  // throws PlanError
+bool packed_range_ok(const MonomerSet &ms, const Scoring &sc, int *deadz, int *pad_s);
+bool geometry_compiled(int packed, int C, int T);
+// CTA bookkeeping shared by backend and emulator
+struct CtaLayout {
+    std::vector<int> cta_nmax;           // longest segment of each CTA
+    std::vector<int64_t> cta_code_off;   // word offset of each CTA's backpointer block (+1 sentinel)
+    std::vector<int64_t> seg_j_off;      // offset of each segment's J/argJ arrays (n+1 entries each) (+1 sentinel)
+    std::vector<int64_t> seg_rec_off;    // scratch record offset of each segment (cap = n) (+1 sentinel)
+};
+CtaLayout make_cta_layout(const Plan &p, const Batch &b, int seg_begin, int seg_end);
+
+// Backend interface.  configure() binds a plan; stage() copies a range of segments to the device;
+// execute() runs sweep + traceback with inputs and outputs resident; fetch() brings the records back.
+class Backend {
+public:
+    virtual ~Backend() {}
+    virtual const char *name() const = 0;
+    virtual void configure(const Plan &p, const MonomerSet &ms) = 0;
+    virtual int64_t wave_bytes(const Batch &b, int seg_begin, int seg_end) const = 0;   // device bytes stage() would need
+    virtual int64_t wave_budget() const = 0;                                            // bytes one wave may use
+    virtual void stage(const Batch &b, int seg_begin, int seg_end) = 0;
+    virtual void execute() = 0;
+    virtual void fetch(BatchResult &out) = 0;       // appends to out.recs / out.rec_off (out.rec_off starts as {0})
+    double sweep_ms = 0, traceback_ms = 0, h2d_ms = 0, d2h_ms = 0;     // accumulated since reset_stats()
+    int64_t h2d_bytes = 0, d2h_bytes = 0, launches = 0;
+    void reset_stats() { sweep_ms = traceback_ms = h2d_ms = d2h_ms = 0; h2d_bytes = d2h_bytes = launches = 0; }
+};
+
+Backend *make_cuda_backend(int device_id, std::string &err);    // sweep_kernels.cu (product)
+Backend *make_emu_backend();                                    // emu.cpp (CPU test-suite only; absent from libsd_b200.so)
+
+} // namespace sdb

@@ -1,0 +1,41 @@
+// dp_main.cpp -- drop-in replacement for the reference's `dp` binary (stringdecomposer/src/main.cpp:374-402):
+// same argv, same raw TSV on stdout, same diagnostics on stderr, same exit status.  stringdecomposer/main.py:194
+// spawns it as  dp <reads> <monomers> <threads> <part-size> <overlap> <ins> <del> <mismatch> <match> <ed_thr>.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+#include "../../include/sd_b200.h"
+
+static int to_int(const char *s)   // std::stoi as used at main.cpp:382-400: throws on garbage -> abort (status 134)
+{
+    if (!s) throw std::logic_error("basic_string: construction from null is not valid");
+    size_t pos = 0;
+    return std::stoi(std::string(s), &pos);
+}
+
+int main(int argc, char **argv)
+{
+    if (argc < 5) {                                                                           // main.cpp:375-379
+        fputs("Failed to process. Number of arguments < 5\n", stdout);
+        fputs("./decompose <reads> <monomers> <threads> <part-size> <overlap> [<ins-score> <del-score> <mismatch-score> <match-score>]\n", stdout);
+        return -1;
+    }
+    int ins = -1, del = -1, mismatch = -1, match = 1;
+    // Scores are read only when argc == 10 and ed_thr only when argc == 11 (main.cpp:381-391); main.py always sends
+    // 10 user arguments, so through main.py the reference ignores -s.  SD_HONOR_SCORING=1 opts into parsing the
+    // scores in the 11-argument form as well.
+    const bool honor = getenv("SD_HONOR_SCORING") && atoi(getenv("SD_HONOR_SCORING"));
+    if (argc == 10 || (argc == 11 && honor)) {
+        ins = to_int(argv[6]); del = to_int(argv[7]); mismatch = to_int(argv[8]); match = to_int(argv[9]);
+    }
+    int ed_thr = -1;
+    if (argc == 11) ed_thr = to_int(argv[10]);
+    const int threads = to_int(argv[3]);
+    const int part = to_int(argv[4]);
+    const int overlap = to_int(argv[5]);       // argc == 5: argv[5] is NULL -> logic_error, as in the reference
+    int st = sd_run_files(argv[1], argv[2], threads, part, overlap, ins, del, mismatch, match, ed_thr, 1, 2);
+    return st;
+}

@@ -1,0 +1,347 @@
+// pipeline.cpp -- host driver around the device sweep: FASTA ingest, segmentation, per-device scheduling,
+// overlap resolution and the raw TSV writer.  Reference behaviour restated from stringdecomposer/src/main.cpp
+// (line numbers cited per function); the data structures and control flow are this project's own.
+#include <algorithm>
+#include <cstring>
+#include <fstream>
+#include <thread>
+#include <unistd.h>
+
+#include "pipeline.h"
+
+namespace sdb {
+
+// ---------------------------------------------------------------------------------------------
+// FASTA: name = first whitespace-delimited token of the header (main.cpp:321-325); sequence lines are
+// appended verbatim (main.cpp:327) -- the toupper in Seq's constructor only ever sees "" (main.cpp:29,325),
+// so lower case and '\r' are illegal symbols; alphabet check and messages main.cpp:330-344.
+// ---------------------------------------------------------------------------------------------
+int load_fasta(const std::string &path, FastaSet &out, std::string &diag)
+{
+    out.names.clear(); out.seqs.clear();
+    std::ifstream f(path, std::ios::in | std::ios::binary);
+    std::string line;
+    while (std::getline(f, line)) {
+        if (!line.empty() && line[0] == '>') {
+            size_t a = 1;
+            auto ws = [](char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\n' || c == '\v' || c == '\f'; };
+            while (a < line.size() && ws(line[a])) ++a;
+            size_t b = a;
+            while (b < line.size() && !ws(line[b])) ++b;
+            out.names.emplace_back(line.substr(a, b - a));
+            out.seqs.emplace_back();
+        } else if (!out.seqs.empty()) {
+            out.seqs.back() += line;
+        }
+    }
+    bool has_n = false;
+    for (size_t i = 0; i < out.seqs.size(); ++i)
+        for (char c : out.seqs[i]) {
+            if (base_code(c) < 0) {
+                diag += "ERROR: Sequence " + out.names[i] + " contains undefined symbol (not ACGT): " + std::string(1, c) + "\n";
+                return 255;
+            }
+            if (c == 'N') has_n = true;
+        }
+    if (has_n) diag += "WARNING: sequences in " + path + " contain N symbol. It will be counted as a separate symbol in scoring!\n";
+    return 0;
+}
+
+// main.cpp:73-79.  The test at :74 is evaluated in size_t (int operands converted), as written there.
+int64_t segment_read(int64_t read_len, int part_size, int overlap, std::vector<std::pair<int, int>> *out)
+{
+    if (part_size <= 0) return -1;
+    int64_t cnt = 0;
+    const size_t len = (size_t)read_len;
+    for (size_t i = 0; i < len; i += (size_t)part_size) {
+        bool keep = ((size_t)(int)len - i >= (size_t)overlap) || (len < (size_t)overlap);
+        if (!keep) continue;
+        int rest = (int)(len - i), want = part_size + overlap;
+        int take = std::min(want, rest);
+        if (take < 0) take = rest;
+        if (out) out->emplace_back((int)i, take);
+        ++cnt;
+    }
+    return cnt;
+}
+
+// main.cpp:287-302
+void postprocess(const std::vector<Record> &in, std::vector<Record> &out)
+{
+    out.clear();
+    size_t i = 0; const size_t n = in.size();
+    while (i < n) {
+        for (size_t j = i + 1; j < std::min(i + 7, n); ++j) {
+            if ((in[i].end - in[j].start) * 2 > (in[j].end - in[j].start)) {
+                out.push_back(in[i]);
+                i = j + 1;
+                break;
+            }
+        }
+        if (i < n) out.push_back(in[i]);
+        ++i;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+Engine::Engine(const std::vector<std::string> &forward_monomers, const Scoring &sc, std::vector<std::unique_ptr<Backend>> devs)
+    : sc_(sc), devs_(std::move(devs))
+{
+    build_monomer_set(forward_monomers, ms_);
+    if (devs_.empty()) throw PlanError{"no device backend"};
+}
+
+void Engine::plan_for(const Batch &b)
+{
+    int maxlen = 0;
+    for (int s = 0; s < b.nseg(); ++s) maxlen = std::max(maxlen, b.len(s));
+    const int64_t per_dev = (b.nseg() + ndev() - 1) / ndev();
+    // re-plan only when the shape changes enough to matter (geometry depends on segment count and length)
+    if (have_plan_ && maxlen <= plan_maxlen_ && maxlen * 2 > plan_maxlen_ && per_dev == plan_nseg_) return;
+    plan_ = make_plan(ms_, sc_, maxlen, per_dev);
+    plan_maxlen_ = maxlen; plan_nseg_ = per_dev; have_plan_ = true;
+    for (auto &d : devs_) d->configure(plan_, ms_);
+    stats.g = plan_.g;
+}
+
+// contiguous, column-balanced ranges, one per device (segments are independent, no collective)
+void Engine::split(const Batch &b, std::vector<int> &bounds) const
+{
+    const int nd = ndev(), nseg = b.nseg();
+    bounds.assign(nd + 1, nseg);
+    bounds[0] = 0;
+    const int64_t total = b.off[nseg] - b.off[0];
+    int s = 0;
+    for (int d = 1; d < nd; ++d) {
+        const int64_t target = b.off[0] + total * d / nd;
+        while (s < nseg && b.off[s] < target) ++s;
+        int cut = s / plan_.g.NS * plan_.g.NS;           // keep CTAs whole
+        bounds[d] = std::max(bounds[d - 1], std::min(cut, nseg));
+    }
+}
+
+void Engine::decompose(const Batch &b, BatchResult &out)
+{
+    out.recs.clear(); out.rec_off.assign(1, 0);
+    if (b.nseg() == 0) return;
+    for (int s = 0; s < b.nseg(); ++s) if (b.len(s) <= 0) throw PlanError{"empty segment"};
+    plan_for(b);
+    std::vector<int> bounds; split(b, bounds);
+    const int nd = ndev();
+    std::vector<BatchResult> part(nd);
+    std::vector<std::string> errs(nd);
+    auto work = [&](int d) {
+        try {
+            Backend &dev = *devs_[d];
+            dev.reset_stats();
+            part[d].rec_off.assign(1, 0);
+            int s0 = bounds[d];
+            const int s_end = bounds[d + 1];
+            const int64_t budget = dev.wave_budget();
+            while (s0 < s_end) {
+                // largest wave that fits the budget: grow geometrically, then shrink by bisection
+                int lo = std::min(s_end, s0 + plan_.g.NS), hi = s_end;
+                if (dev.wave_bytes(b, s0, hi) > budget) {
+                    while (hi - lo > plan_.g.NS) {
+                        int mid = lo + (hi - lo) / 2 / plan_.g.NS * plan_.g.NS;
+                        if (mid <= lo) break;
+                        if (dev.wave_bytes(b, s0, mid) <= budget) lo = mid; else hi = mid;
+                    }
+                    hi = lo;
+                }
+                dev.stage(b, s0, hi);
+                dev.execute();
+                dev.fetch(part[d]);
+                s0 = hi;
+            }
+        } catch (PlanError &e) { errs[d] = e.msg.empty() ? "error" : e.msg; }
+        catch (std::exception &e) { errs[d] = e.what(); }
+    };
+    if (nd == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int d = 0; d < nd; ++d) th.emplace_back(work, d);
+        for (auto &t : th) t.join();
+    }
+    for (int d = 0; d < nd; ++d) if (!errs[d].empty()) throw PlanError{errs[d]};
+    double sw = 0, tb = 0, h2d = 0, d2h = 0;
+    for (int d = 0; d < nd; ++d) {
+        const int64_t base = (int64_t)out.recs.size();
+        out.recs.insert(out.recs.end(), part[d].recs.begin(), part[d].recs.end());
+        for (size_t x = 1; x < part[d].rec_off.size(); ++x) out.rec_off.push_back(base + part[d].rec_off[x]);
+        sw = std::max(sw, devs_[d]->sweep_ms); tb = std::max(tb, devs_[d]->traceback_ms);
+        h2d = std::max(h2d, devs_[d]->h2d_ms); d2h = std::max(d2h, devs_[d]->d2h_ms);
+        stats.h2d_bytes += devs_[d]->h2d_bytes; stats.d2h_bytes += devs_[d]->d2h_bytes; stats.launches += devs_[d]->launches;
+    }
+    stats.sweep_ms += sw; stats.traceback_ms += tb; stats.h2d_ms += h2d; stats.d2h_ms += d2h;
+    const int64_t cols = b.off[b.nseg()] - b.off[0];
+    stats.columns += cols; stats.segments += b.nseg(); stats.cells += cols * (int64_t)ms_.rows.size();
+}
+
+void Engine::stage(const Batch &b)
+{
+    if (b.nseg() == 0) throw PlanError{"nothing to stage"};
+    staged_ = b;
+    plan_for(staged_);
+    split(staged_, staged_bounds_);
+    for (int d = 0; d < ndev(); ++d) {
+        if (staged_bounds_[d] == staged_bounds_[d + 1]) continue;
+        if (devs_[d]->wave_bytes(staged_, staged_bounds_[d], staged_bounds_[d + 1]) > devs_[d]->wave_budget())
+            throw PlanError{"staged batch does not fit one wave on the device"};
+    }
+    auto work = [&](int d) { if (staged_bounds_[d] < staged_bounds_[d + 1]) devs_[d]->stage(staged_, staged_bounds_[d], staged_bounds_[d + 1]); };
+    std::vector<std::thread> th;
+    for (int d = 0; d < ndev(); ++d) th.emplace_back(work, d);
+    for (auto &t : th) t.join();
+}
+
+double Engine::run_staged()
+{
+    if (staged_.nseg() == 0) throw PlanError{"nothing staged"};
+    std::vector<std::string> errs(ndev());
+    auto work = [&](int d) {
+        try {
+            devs_[d]->reset_stats();
+            if (staged_bounds_[d] < staged_bounds_[d + 1]) devs_[d]->execute();
+        } catch (PlanError &e) { errs[d] = e.msg; }
+    };
+    std::vector<std::thread> th;
+    for (int d = 0; d < ndev(); ++d) th.emplace_back(work, d);
+    for (auto &t : th) t.join();
+    for (auto &e : errs) if (!e.empty()) throw PlanError{e};
+    double ms = 0, sw = 0, tb = 0;
+    for (auto &d : devs_) { ms = std::max(ms, d->sweep_ms + d->traceback_ms); sw = std::max(sw, d->sweep_ms); tb = std::max(tb, d->traceback_ms); stats.launches += d->launches; }
+    stats.sweep_ms += sw; stats.traceback_ms += tb;
+    const int64_t cols = staged_.off[staged_.nseg()] - staged_.off[0];
+    stats.columns += cols; stats.segments += staged_.nseg(); stats.cells += cols * (int64_t)ms_.rows.size();
+    return ms;
+}
+
+void Engine::fetch_staged(BatchResult &out)
+{
+    out.recs.clear(); out.rec_off.assign(1, 0);
+    for (int d = 0; d < ndev(); ++d) {
+        if (staged_bounds_[d] == staged_bounds_[d + 1]) continue;
+        devs_[d]->fetch(out);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct FdWriter {
+    int fd; std::string buf;
+    explicit FdWriter(int f) : fd(f) { buf.reserve(1 << 20); }
+    void flush() { size_t o = 0; while (o < buf.size()) { ssize_t w = ::write(fd, buf.data() + o, buf.size() - o); if (w <= 0) break; o += (size_t)w; } buf.clear(); }
+    void add(const std::string &s) { buf += s; if (buf.size() > (1 << 20)) flush(); }
+    void add_int(long v) { char t[24]; int n = 0; bool neg = v < 0; unsigned long u = neg ? 0ul - (unsigned long)v : (unsigned long)v;
+        do { t[n++] = (char)('0' + u % 10); u /= 10; } while (u); if (neg) t[n++] = '-'; while (n) buf.push_back(t[--n]); }
+    ~FdWriter() { flush(); }
+};
+
+} // namespace
+
+int run_files(const std::string &reads_path, const std::string &monomers_path, int threads, int part_size, int overlap,
+              const Scoring &sc, int ed_thr, std::vector<std::unique_ptr<Backend>> devs, int out_fd, int err_fd,
+              std::string &error)
+{
+    (void)threads;     // OpenMP width in the reference (main.cpp:85,88); the output does not depend on it
+    FdWriter err(err_fd);
+    err.add("Scores: insertion=" + std::to_string(sc.ins) + " deletion=" + std::to_string(sc.del) + " mismatch=" +
+            std::to_string(sc.mismatch) + " match=" + std::to_string(sc.match) + "\n");                  // main.cpp:393
+    err.flush();
+    FastaSet reads, mons;
+    std::string diag;
+    int st = load_fasta(reads_path, reads, diag);
+    err.add(diag); err.flush(); diag.clear();
+    if (st) return st;
+    st = load_fasta(monomers_path, mons, diag);
+    err.add(diag); err.flush();
+    if (st) return st;
+    if (ed_thr > -1) {
+        // FilterMonomersForRead (main.cpp:135-149) re-orders the rows per segment; running the unfiltered DP
+        // instead would silently change the output, so refuse.
+        error = "the --ed_thr monomer pre-filter is not implemented in this build (ed_thr must be -1)";
+        err.add("ERROR: " + error + "\n");
+        return 3;
+    }
+    if (part_size <= 0) { error = "part-size must be positive"; err.add("ERROR: " + error + "\n"); return 1; }
+
+    // segmentation of all reads, in read order (main.cpp:70-81)
+    std::vector<int64_t> first(reads.seqs.size() + 1, 0);
+    std::vector<std::pair<int, int>> segs;       // (offset in read, length)
+    std::vector<int> seg_read;
+    for (size_t p = 0; p < reads.seqs.size(); ++p) {
+        first[p] = (int64_t)segs.size();
+        size_t before = segs.size();
+        segment_read((int64_t)reads.seqs[p].size(), part_size, overlap, &segs);
+        for (size_t s = before; s < segs.size(); ++s) seg_read.push_back((int)p);
+    }
+    first[reads.seqs.size()] = (int64_t)segs.size();
+    err.add("Prepared reads\n"); err.flush();                                                                    // main.cpp:82
+    if (segs.empty()) return 0;
+    if (mons.seqs.empty()) { error = "no monomers"; err.add("ERROR: " + error + "\n"); return 1; }
+
+    BatchResult res;
+    try {
+        Engine eng(mons.seqs, sc, std::move(devs));
+        Batch b;
+        b.off.reserve(segs.size() + 1); b.off.push_back(0);
+        size_t total = 0;
+        for (auto &s : segs) total += (size_t)s.second;
+        b.bases.resize(total);
+        size_t o = 0;
+        for (size_t s = 0; s < segs.size(); ++s) {
+            const std::string &r = reads.seqs[seg_read[s]];
+            for (int x = 0; x < segs[s].second; ++x) b.bases[o + x] = (uint8_t)base_code(r[segs[s].first + x]);
+            o += (size_t)segs[s].second; b.off.push_back((int64_t)o);
+        }
+        eng.decompose(b, res);
+        if (getenv("SD_VERBOSE")) {
+            const EngineStats &s = eng.stats;
+            char line[512];
+            snprintf(line, sizeof line, "[sd_b200] devices=%d geometry packed=%d C=%d T=%d NS=%d NT=%d segments=%ld cells=%ld sweep=%.3f ms traceback=%.3f ms -> %.1f GCUPS (kernels)\n",
+                     eng.ndev(), s.g.packed, s.g.C, s.g.T, s.g.NS, s.g.NT, (long)s.segments, (long)s.cells, s.sweep_ms, s.traceback_ms,
+                     s.cells / ((s.sweep_ms + s.traceback_ms) * 1e6 + 1e-9));
+            err.add(line);
+        }
+    } catch (PlanError &e) {
+        error = e.msg;
+        err.add("ERROR: " + error + "\n");
+        return 3;
+    }
+
+    // per read: add segment offsets (main.cpp:110), PostProcessing (:116), SaveBatch (:117, :272-285)
+    FdWriter outw(out_fd);
+    std::vector<Record> all, kept;
+    const int M = (int)mons.seqs.size();
+    for (size_t p = 0; p < reads.seqs.size(); ++p) {
+        all.clear();
+        for (int64_t s = first[p]; s < first[p + 1]; ++s)
+            for (int64_t x = res.rec_off[s]; x < res.rec_off[s + 1]; ++x) {
+                Record r = res.recs[x];
+                r.start += segs[s].first; r.end += segs[s].first;
+                all.push_back(r);
+            }
+        if (all.empty()) continue;     // the reference dereferences batch[0] of an empty vector here (UB)
+        err.add(std::to_string((p + 1) * 100 / reads.seqs.size()) + "%: Aligned " + reads.names[p] + "\n");   // main.cpp:115
+        postprocess(all, kept);
+        int prev_end = 0;
+        for (const Record &r : kept) {
+            outw.add(reads.names[p]); outw.buf.push_back('\t');
+            outw.add(mons.names[r.row < M ? r.row : r.row - M]);
+            if (r.row >= M) outw.buf.push_back('\'');
+            outw.buf.push_back('\t'); outw.add_int(r.start);
+            outw.buf.push_back('\t'); outw.add_int(r.end);
+            outw.buf.push_back('\t'); outw.add_int(r.score); outw.buf += ".000000";      // to_string(float), main.cpp:279
+            outw.buf.push_back('\t'); outw.add_int(r.start - prev_end);
+            outw.buf.push_back('\t'); outw.add_int(r.end - r.start);
+            outw.buf.push_back('\n');
+            prev_end = r.end;
+            if (outw.buf.size() > (1 << 20)) outw.flush();
+        }
+    }
+    return 0;
+}
+
+} // namespace sdb

@@ -1,0 +1,195 @@
+// plan.cpp -- DP-row construction, score-range analysis (s16x2 vs s32), launch geometry, profile table.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "common.h"
+
+namespace sdb {
+
+// Rows = forward monomers in input order followed by the reverse complement of each, in the same order.
+// Restates add_reverse_complement / reverse_complement (main.cpp:348-371): this order is the arg-max
+// tie-break order of the whole DP (main.cpp:212, :230-236).
+void build_monomer_set(const std::vector<std::string> &forward, MonomerSet &ms)
+{
+    ms.M = (int)forward.size();
+    ms.rows.clear(); ms.row_off.assign(1, 0);
+    ms.Lmax = 0; ms.Lmin = 1 << 30;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (const std::string &m : forward) {
+            int L = (int)m.size();
+            if (L == 0) throw PlanError{"empty monomer sequence (the reference indexes seq[0] of it, main.cpp:173)"};
+            for (int x = 0; x < L; ++x) {
+                int c = base_code(pass == 0 ? m[x] : m[L - 1 - x]);
+                if (c < 0) throw PlanError{"monomer contains a symbol outside ACGTN"};
+                if (pass == 1 && c < 4) c = 3 - c;            // A<->T, C<->G, N stays N (main.cpp:350)
+                ms.rows.push_back((uint8_t)c);
+            }
+            ms.row_off.push_back((int)ms.rows.size());
+            ms.Lmax = std::max(ms.Lmax, L); ms.Lmin = std::min(ms.Lmin, L);
+        }
+    }
+    if (ms.M == 0) { ms.Lmax = ms.Lmin = 0; }
+}
+
+// Range proof for the packed s16x2 representation (DESIGN.md "score range").  With D=-del>=0, I=-ins>=0:
+//   live relative cells  rel in [min(s''min,0), D*(Lmax+1) + I + max(smax,0)]          (s'' = s + I + D)
+//   column shift         |delta| <= D*(Lmax+1) + I + max(|smax|,|smin|) + 1
+//   pad/dead level       s''pad = -(relmax + |s''min| + 2)
+// Every intermediate of lane_pass1/2 is (value +- 4*delta +- small), so 16 bits suffice when
+//   4*(|s''pad| + relmax + 2*dmax) + 64 <= 32767.
+// The host emulator traps any 16-bit overflow, which is how the tests keep this proof honest.
+bool packed_range_ok(const MonomerSet &ms, const Scoring &sc, int *deadz, int *pad_s)
+{
+    if (sc.ins > 0 || sc.del > 0) return false;
+    const int64_t D = -(int64_t)sc.del, I = -(int64_t)sc.ins;
+    const int64_t smax = std::max(sc.match, sc.mismatch), smin = std::min(sc.match, sc.mismatch);
+    const int64_t s2max = smax + I + D, s2min = smin + I + D;
+    const int64_t L = std::max(ms.Lmax, 2);
+    const int64_t relmax = D * (L + 2) + I + std::max<int64_t>(smax, 0) + 2 * std::max(std::llabs(s2min), std::llabs(s2max)) + 4;
+    const int64_t dmax = D * (L + 1) + I + std::max(std::llabs(smax), std::llabs(smin)) + 1;
+    const int64_t pad = relmax + std::llabs(s2min) + 2;
+    if (4 * (pad + relmax + 2 * dmax) + 64 > 32767) return false;
+    if (deadz) *deadz = (int)(-4 * pad + 3);
+    if (pad_s) *pad_s = (int)(-pad);
+    return true;
+}
+
+// Kernel instantiations compiled into the library (sweep_kernels.cu instantiates exactly this table).
+static const int kC[] = {8, 16, 24, 32, 48};
+static const int kT[] = {1, 2, 4, 8, 16, 32};
+bool geometry_compiled(int packed, int C, int T)
+{
+    (void)packed;
+    bool c = false, t = false;
+    for (int x : kC) c |= (x == C);
+    for (int x : kT) t |= (x == T);
+    return c && t;
+}
+
+static const size_t kSmemLimit = 200 * 1024;
+
+size_t Plan::smem_bytes(int seg_stride) const
+{
+    return prof.size() * 4 + (size_t)g.NS * (size_t)seg_stride + 3 * (size_t)g.NS * 4 + 64;
+}
+
+// Cost model (cycles of one SMSP) used to pick (C, T, NS); constants from tools/int_peak*.cu runs.
+// One warp needs warp_col issue cycles per column and cannot go faster than lat_col (dependent chain +
+// shuffles + the key exchange); w warps resident on an SMSP advance one column each in max(w*warp_col, lat_col).
+static double geometry_cost(int C, int T, int NS, int NT, int64_t nseg, int nmax)
+{
+    const int lg = (T > 1) ? __builtin_ctz((unsigned)T) : 0;
+    const double per_cell = (T == 1) ? 8.0 : 9.6;
+    const double warp_col = C * per_cell + 120.0 + (T > 1 ? 56.0 * (1 + lg) : 0.0);
+    const double lat_col = C * 8.0 + 220.0 + 60.0 * lg;
+    const int64_t nctas = (nseg + NS - 1) / NS;
+    const double wps = (double)nctas * (NT / 32) / (148.0 * 4.0);
+    const double cap = 8.0;
+    const double waves = std::max(1.0, std::ceil(wps / cap));
+    const double w_res = std::max(1.0, wps / waves);
+    return (double)nmax * waves * std::max(w_res * warp_col, lat_col);
+}
+
+Plan make_plan(const MonomerSet &ms, const Scoring &sc, int max_seg_len, int64_t nseg_hint)
+{
+    Plan p;
+    p.sc = sc;
+    if (ms.M <= 0) throw PlanError{"no monomers"};
+    if (ms.nrows() > SD_KEY_ROWS) throw PlanError{"more than 2048 monomers are not supported by this build"};
+    // The reference guards every candidate with '> INF' (INF=-1000000, main.cpp:156,191-201); those guards are
+    // no-ops only while every true score stays above INF.  Refuse instead of diverging silently.
+    {
+        int64_t a = std::max(std::abs(sc.ins), std::abs(sc.mismatch));
+        int64_t lo = (int64_t)max_seg_len * a + 2ll * ms.Lmax * std::abs(sc.del) + 2ll * std::abs(sc.mismatch) + std::abs(sc.match);
+        int64_t hi = ((int64_t)max_seg_len + ms.Lmax) * std::max({std::abs(sc.match), std::abs(sc.mismatch), std::abs(sc.ins), std::abs(sc.del)});
+        if (lo >= 999000) throw PlanError{"scores can reach the reference's INF sentinel (-1000000): outside the supported domain"};
+        if (hi >= (1 << 23)) throw PlanError{"scores exceed the exact float range of the reference's output"};
+    }
+    int pad_s = 0;
+    int packed = packed_range_ok(ms, sc, &p.deadz, &pad_s) ? 1 : 0;
+    if (const char *e = getenv("SD_FORCE_S32")) if (atoi(e)) packed = 0;
+    if (!packed) { pad_s = -(1 << 26); p.deadz = 4 * pad_s + 3; }
+
+    const int nslots = packed ? ms.M : 2 * ms.M;
+    int bestC = 0, bestT = 0, bestNS = 0, bestNT = 0; double best = 1e300;
+    int fC = 0, fT = 0, fNS = 0;
+    if (const char *e = getenv("SD_GEOM")) sscanf(e, "%d,%d,%d", &fC, &fT, &fNS);
+    for (int C : kC) for (int T : kT) {
+        if (fC && (C != fC || T != fT)) continue;
+        if (C * T < ms.Lmax) continue;
+        int ls = nslots * T;                        // lanes per segment
+        if (ls > 1024) continue;
+        size_t prof_bytes = (size_t)5 * C * ls * 4;
+        for (int NS = 1; NS <= 16; ++NS) {
+            if (fNS && NS != fNS) continue;
+            int lanes = NS * ls;
+            if (lanes > 1024) break;
+            int NT = (lanes + 31) / 32 * 32;
+            size_t smem = prof_bytes + (size_t)NS * ((size_t)max_seg_len + 64) + 256;
+            if (smem > kSmemLimit) continue;
+            double util = (double)lanes / NT;
+            double cost = geometry_cost(C, T, NS, NT, std::max<int64_t>(nseg_hint, 1), std::max(max_seg_len, 1)) / util;
+            cost *= 1.0 + 0.02 * (NS - 1);            // mild preference for independent CTAs
+            if (cost < best) { best = cost; bestC = C; bestT = T; bestNS = NS; bestNT = NT; }
+        }
+    }
+    if (!bestC) throw PlanError{"monomer set does not fit one CTA (rows*lanes > 1024 threads or profile > shared memory); "
+                                "the cluster sweep for large monomer sets is not built yet"};
+    Geometry &g = p.g;
+    g.packed = packed; g.C = bestC; g.T = bestT; g.nslots = nslots; g.M = ms.M; g.NS = bestNS; g.NT = bestNT;
+    const int cpw = packed ? 8 : 16;
+    g.CW = (g.C + cpw - 1) / cpw;
+    p.nsl = nslots * g.T;
+
+    // profile words: prof[sym][q][sl][e] = 4*s''(sym, row cell k) with k = t*C + 4q + e; pad cells get 4*pad_s.
+    const int C = g.C, T = g.T, SL = C * T;
+    p.prof.assign((size_t)5 * (C / 4) * p.nsl * 4, 0u);
+    p.slot_len.resize(nslots); p.slot_endadd.resize(nslots);
+    const int shift = -sc.ins - sc.del;
+    for (int slot = 0; slot < nslots; ++slot) {
+        const int L = ms.rowlen(slot);              // packed: forward row `slot`, its RC row M+slot has the same length
+        p.slot_len[slot] = L;
+        p.slot_endadd[slot] = (L - 1) * sc.del;
+        const int lead = (L == 1) ? SL - 1 : 0;     // length-1 rows sit in the last cell of their slot
+        for (int sym = 0; sym < 5; ++sym)
+            for (int pos = 0; pos < SL; ++pos) {
+                int k = pos - lead;
+                int lo = pad_s, hi = pad_s;
+                if (k >= 0 && k < L) {
+                    lo = (ms.rows[ms.row_off[slot] + k] == sym ? sc.match : sc.mismatch) + shift;
+                    if (packed) hi = (ms.rows[ms.row_off[ms.M + slot] + k] == sym ? sc.match : sc.mismatch) + shift;
+                }
+                uint32_t w = packed ? (((uint32_t)(4 * lo) & 0xffffu) | ((uint32_t)(4 * hi) << 16)) : (uint32_t)(4 * lo);
+                int t = pos / C, kk = pos % C, q = kk / 4, e = kk % 4;
+                int sl = slot * T + t;
+                p.prof[(((size_t)sym * (C / 4) + q) * p.nsl + sl) * 4 + e] = w;
+            }
+    }
+    return p;
+}
+
+CtaLayout make_cta_layout(const Plan &p, const Batch &b, int seg_begin, int seg_end)
+{
+    CtaLayout l;
+    const Geometry &g = p.g;
+    const int nseg = seg_end - seg_begin;
+    const int nctas = (nseg + g.NS - 1) / g.NS;
+    l.cta_nmax.assign(nctas, 0);
+    l.cta_code_off.assign(nctas + 1, 0);
+    l.seg_j_off.assign(nseg + 1, 0);
+    l.seg_rec_off.assign(nseg + 1, 0);
+    for (int s = 0; s < nseg; ++s) {
+        int n = b.len(seg_begin + s);
+        l.cta_nmax[s / g.NS] = std::max(l.cta_nmax[s / g.NS], n);
+        l.seg_j_off[s + 1] = l.seg_j_off[s] + n + 1;
+        l.seg_rec_off[s + 1] = l.seg_rec_off[s] + n;
+    }
+    for (int c = 0; c < nctas; ++c)
+        l.cta_code_off[c + 1] = l.cta_code_off[c] + (int64_t)l.cta_nmax[c] * g.NT * g.CW;
+    return l;
+}
+
+} // namespace sdb
