@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py -- DP GCUPS of the string-decomposition sweep on the BASELINE.json config-2 workload.
+
+One "step" = one pass of the hot path (forward sweep + traceback kernels) over one batch: the synthetic 2 Mb
+cenX-like DXZ1 HOR array cut into 400 segments (part 5000, overlap 500) against the 12 DXZ1 monomers and their
+reverse complements.  `value` is measured with the segments already resident in HBM (CUDA events on the library's
+stream); `e2e` goes through the public C ABI (sd_decompose) with host buffers, H2D and D2H inside the timed region.
+N > 1: one process per GPU (torchrun), every rank decomposes its own 2 Mb array (weak scaling, no collective on the
+data path -- segments are independent); torch.distributed is used for the barrier and the max over ranks.
+
+--impl reference times the unmodified reference binary (oracle/_ref/dp, built from /root/reference by
+oracle/Makefile) on the same workload with -t <host cores>.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PART, OVERLAP = 5000, 500
+SCORING = (-1, -1, -1, 1)
+METRIC = "dp_gcups"
+UNIT = "GCUPS"
+# integer-pipe instructions the sweep issues per useful DP cell in the packed s16x2 kernel:
+# per register (2 cells): 2 VIADDMNMX + VIADD.16x2 + 0.5 VIMNMX3 + VIMNMX + LOP3 (ALU pipe), 2 IMAD (FMA pipe) = 7.5 -> 3.75
+OPS_PER_CELL = 3.75
+SURVEY_OPS_PER_CELL = 5.5      # SURVEY.md section 8d planning figure for s16x2
+
+
+def dist_setup(n_gpus):
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if ws > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
+    return ws, rank, local
+
+
+def barrier_sync(ws):
+    import torch
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    if ws > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+
+
+def max_over_ranks(x, ws):
+    if ws == 1:
+        return x
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device="cuda" if torch.cuda.is_available() else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(x, ws):
+    if ws == 1:
+        return x
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device="cuda" if torch.cuda.is_available() else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.proc, self.lines = gpu, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [x for x in sm if x > 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload(rank):
+    from stringdecomposer_b200 import synth
+    from stringdecomposer_b200.hostpipe import segment_reads
+    rnames, reads, mnames, mons = synth.config2(seed=2 + rank)
+    segs, where = segment_reads(reads, PART, OVERLAP)
+    return rnames, reads, mnames, mons, segs
+
+
+def cells_of(segs, mons):
+    return sum(len(s) for s in segs) * 2 * sum(len(m) for m in mons)
+
+
+def headline_cells(reads, mons):
+    # north_star: "read bp x total monomer bp" (fwd + RC rows)
+    return sum(len(r) for r in reads) * 2 * sum(len(m) for m in mons)
+
+
+def run_reference_arm(args, ws, rank):
+    """The reference's own CPU implementation (oracle/_ref/dp) on the same workload, all host cores."""
+    if rank != 0:
+        return
+    from stringdecomposer_b200 import synth
+    ref = os.path.join(ROOT, "oracle", "_ref", "dp")
+    kind = "reference"
+    if not os.path.exists(ref):
+        ref = os.path.join(ROOT, "oracle", "_build", "oracle_dp")
+        kind = "port"
+    if not os.path.exists(ref):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "port"], check=False)
+    cores = os.cpu_count() or 1
+    rnames, reads, mnames, mons = synth.config2(seed=2)
+    with tempfile.TemporaryDirectory() as td:
+        rp, mp = os.path.join(td, "reads.fa"), os.path.join(td, "monomers.fa")
+        synth.write_fasta(rp, rnames, reads)
+        synth.write_fasta(mp, mnames, mons)
+        cmd = [ref, rp, mp, str(cores), str(PART), str(OVERLAP)]
+        times = []
+        for it in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            with open(os.path.join(td, "out.tsv"), "wb") as out:
+                subprocess.run(cmd, stdout=out, stderr=subprocess.DEVNULL, check=True)
+            dt = time.perf_counter() - t0
+            if it >= args.warmup:
+                times.append(dt)
+    T = sum(times)
+    cells = headline_cells(reads, mons) * len(times)
+    val = cells / T / 1e9
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * T / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "config": {"workload": "config2: synthetic 2 Mb cenX-like DXZ1 HOR array, 12 monomers (+RC), part 5000 overlap 500",
+                       "segments": 400, "scoring": "-1,-1,-1,1"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": "full config-2 contig (2,000,000 bp) per step, dp -t %d, wall time of the process" % cores},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "decomposed_mbp_per_s": sum(len(r) for r in reads) * len(times) / T / 1e6, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--geom", default=None, help="override launch geometry C,T,NS (exploration)")
+    args = ap.parse_args()
+    if args.geom:
+        os.environ["SD_GEOM"] = args.geom
+    ws, rank, local = dist_setup(args.gpus)
+    if args.impl == "reference":
+        run_reference_arm(args, ws, rank)
+        return
+
+    import torch
+    from stringdecomposer_b200 import Decomposer, int_peak
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local)
+    rnames, reads, mnames, mons, segs = workload(rank)
+    blob = "".join(segs).encode()
+    off = np.zeros(len(segs) + 1, dtype=np.int64)
+    np.cumsum([len(s) for s in segs], out=off[1:])
+    packed = (blob, off)
+    dec = Decomposer(mons, *SCORING, devices=[local])
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+
+    # ---- value: inputs resident in HBM, kernels only ------------------------------------------------
+    dec.stage(packed)
+    for _ in range(args.warmup):
+        dec.run_staged()
+    sampler = ClockSampler(local)
+    barrier_sync(ws)
+    sampler.start()
+    dec.reset_stats()
+    dev_ms = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        dev_ms += dec.run_staged()            # CUDA events around sweep + traceback on the library's stream
+    barrier_sync(ws)
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    st = dec.stats()
+    dev_ms = max_over_ranks(dev_ms, ws)
+    recs, roff = dec.fetch_staged()
+    cells_hl = sum_over_ranks(float(headline_cells(reads, mons)), ws)
+    cells_act = sum_over_ranks(float(cells_of(segs, mons)), ws)
+    value = cells_hl * args.steps / (dev_ms * 1e-3) / 1e9
+    sweep_ms = st["sweep_ms"] / args.steps
+    tb_ms = st["traceback_ms"] / args.steps
+
+    # ---- e2e: host buffers through sd_decompose, H2D + D2H inside the timed region -----------------
+    for _ in range(args.warmup):
+        dec.decompose(packed)
+    dec.reset_stats()
+    barrier_sync(ws)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r2, o2 = dec.decompose(packed)
+    barrier_sync(ws)
+    e2e_s = max_over_ranks(time.perf_counter() - t0, ws)
+    st2 = dec.stats()
+    e2e_val = cells_hl * args.steps / e2e_s / 1e9
+    same = bool(len(r2) == len(recs) and (r2 == recs).all() and (o2 == roff).all())
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel (sweep): integer issue rate --------------------------------
+        alu, both, mhz = int_peak(local)
+        cells_rank = float(cells_of(segs, mons))
+        ach = cells_rank / (sweep_ms * 1e-3) * OPS_PER_CELL / 1e12
+        peak = both / 1e12
+        codes_bytes = cells_rank * 0.25
+        roof = {"bound": "int", "achieved": ach, "peak": peak, "unit": "Tlane-op/s", "frac": ach / peak, "traffic": None,
+                "peak_source": "sd_int_peak: VIADDMNMX.S16x2 + IMAD streams on all SMs, this run (ALU pipe alone %.2f)" % (alu / 1e12),
+                "ops_per_cell": OPS_PER_CELL, "kernel": "sweep_kernel", "kernel_ms": sweep_ms, "traceback_ms": tb_ms,
+                "frac_at_survey_5.5_ops_per_cell_vs_alu_peak": cells_rank / (sweep_ms * 1e-3) * SURVEY_OPS_PER_CELL / alu,
+                "hbm": {"achieved_gbs": (codes_bytes + sum(len(s) for s in segs) * 9.0) / (sweep_ms * 1e-3) / 1e9,
+                        "peak_gbs": _hbm_peak(), "note": "2-bit backpointers, 0.25 B/cell; not the limiter"}}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "s16x2" if st["packed"] else "s32", "data": "synthetic",
+                "config": {"workload": "config2: synthetic 2 Mb cenX-like DXZ1 HOR array per GPU, 12 monomers (+RC), part 5000 overlap 500",
+                           "segments_per_gpu": len(segs), "scoring": "-1,-1,-1,1", "l2": "256 MiB memset between timed steps; "
+                           "the 2.5 GB backpointer stream exceeds L2 by itself",
+                           "geometry": {k: st[k] for k in ("C", "T", "NS", "NT")}},
+                "cells_actual_gcups": cells_act * args.steps / (dev_ms * 1e-3) / 1e9,
+                "decomposed_mbp_per_s": sum_len(reads) * ws * args.steps / (dev_ms * 1e-3) / 1e6,
+                "wall_ms_per_step": 1e3 * wall / args.steps,
+                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": st2["h2d_bytes"] // args.steps,
+                        "d2h_bytes_per_step": st2["d2h_bytes"] // args.steps, "ms_per_step": 1e3 * e2e_s / args.steps,
+                        "matches_resident_run": same},
+                "gpu_launches": int(st["launches"]), "clocks": clocks, "roofline": roof}
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(reads, rnames, mnames, mons)
+        print(json.dumps(line))
+    if ws > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def sum_len(reads):
+    return sum(len(r) for r in reads)
+
+
+def _hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)["hbm_gbs"]
+    except Exception:
+        return 6650.0
+
+
+def cpu_baseline(reads, rnames, mnames, mons):
+    """Reference binary (or the oracle port) on a bounded sample of the same workload, all host cores."""
+    from stringdecomposer_b200 import synth
+    ref = os.path.join(ROOT, "oracle", "_ref", "dp")
+    kind = "reference"
+    if not os.path.exists(ref):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "port"], check=False)
+        ref, kind = os.path.join(ROOT, "oracle", "_build", "oracle_dp"), "port"
+    if not os.path.exists(ref):
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": "oracle not built"}
+    cores = os.cpu_count() or 1
+    sample = reads[0][:1_000_000]
+    with tempfile.TemporaryDirectory() as td:
+        rp, mp = os.path.join(td, "reads.fa"), os.path.join(td, "monomers.fa")
+        synth.write_fasta(rp, rnames[:1], [sample])
+        synth.write_fasta(mp, mnames, mons)
+        t0 = time.perf_counter()
+        with open(os.path.join(td, "out.tsv"), "wb") as out:
+            subprocess.run([ref, rp, mp, str(cores), str(PART), str(OVERLAP)], stdout=out, stderr=subprocess.DEVNULL, check=True)
+        dt = time.perf_counter() - t0
+    cells = len(sample) * 2 * sum(len(m) for m in mons)
+    return {"value": cells / dt / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": "first 1,000,000 bp of the config-2 contig (200 segments), dp -t %d, process wall time %.2f s" % (cores, dt)}
+
+
+if __name__ == "__main__":
+    main()

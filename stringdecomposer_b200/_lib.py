@@ -1,0 +1,218 @@
+"""ctypes binding of include/sd_b200.h (the C ABI of libsd_b200.so)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+RECORD_DTYPE = np.dtype([("row", "<i4"), ("start", "<i4"), ("end", "<i4"), ("score", "<i4")])
+
+
+class SdError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__("sd_b200 status %d: %s" % (status, msg))
+        self.status = status
+
+
+class _Stats(C.Structure):
+    _fields_ = [("sweep_ms", C.c_double), ("traceback_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("cells", C.c_int64), ("segments", C.c_int64),
+                ("columns", C.c_int64), ("launches", C.c_int64), ("n_devices", C.c_int32), ("packed", C.c_int32),
+                ("C", C.c_int32), ("T", C.c_int32), ("NS", C.c_int32), ("NT", C.c_int32)]
+
+
+# every symbol include/sd_b200.h declares (tests/test_abi.py checks the header against this list)
+SYMBOLS = ["sd_create", "sd_decompose", "sd_stage", "sd_run_staged", "sd_fetch_staged", "sd_segment_read",
+           "sd_postprocess", "sd_run_files", "sd_get_stats", "sd_reset_stats", "sd_last_error", "sd_free",
+           "sd_destroy", "sd_device_count", "sd_version", "sd_int_peak"]
+
+_libs = {}
+
+
+def library_path(flavour="cuda"):
+    """Path of the in-tree shared library.  ``flavour="emu"`` is the host emulator used by the CPU tests only."""
+    name = {"cuda": "libsd_b200.so", "emu": "libsd_emu.so"}[flavour]
+    return os.path.join(_HERE, name)
+
+
+def load_library(flavour="cuda"):
+    if flavour in _libs:
+        return _libs[flavour]
+    path = library_path(flavour)
+    if not os.path.exists(path):
+        raise SdError(2, "%s is not built (run `python -c 'import __graft_entry__ as g; g.build()'` or "
+                         "`make -C stringdecomposer_b200/csrc`); there is no fallback path" % path)
+    lib = C.CDLL(path)
+    p = C.c_void_p
+    lib.sd_create.argtypes = [C.c_char_p, C.POINTER(C.c_int64), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                              C.POINTER(C.c_int32), C.c_int32, C.POINTER(p)]
+    lib.sd_create.restype = C.c_int
+    lib.sd_decompose.argtypes = [p, C.c_char_p, C.POINTER(C.c_int64), C.c_int64, C.POINTER(p), C.POINTER(p)]
+    lib.sd_decompose.restype = C.c_int
+    lib.sd_stage.argtypes = [p, C.c_char_p, C.POINTER(C.c_int64), C.c_int64]
+    lib.sd_stage.restype = C.c_int
+    lib.sd_run_staged.argtypes = [p, C.POINTER(C.c_double)]
+    lib.sd_run_staged.restype = C.c_int
+    lib.sd_fetch_staged.argtypes = [p, C.POINTER(p), C.POINTER(p)]
+    lib.sd_fetch_staged.restype = C.c_int
+    lib.sd_segment_read.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.c_int64]
+    lib.sd_segment_read.restype = C.c_int64
+    lib.sd_postprocess.argtypes = [p, C.c_int64, p]
+    lib.sd_postprocess.restype = C.c_int64
+    lib.sd_run_files.argtypes = [C.c_char_p, C.c_char_p] + [C.c_int32] * 8 + [C.c_int, C.c_int]
+    lib.sd_run_files.restype = C.c_int
+    lib.sd_get_stats.argtypes = [p, C.POINTER(_Stats)]
+    lib.sd_get_stats.restype = C.c_int
+    lib.sd_reset_stats.argtypes = [p]
+    lib.sd_reset_stats.restype = None
+    lib.sd_last_error.argtypes = [p]
+    lib.sd_last_error.restype = C.c_char_p
+    lib.sd_free.argtypes = [p]
+    lib.sd_free.restype = None
+    lib.sd_destroy.argtypes = [p]
+    lib.sd_destroy.restype = None
+    lib.sd_device_count.restype = C.c_int
+    lib.sd_version.restype = C.c_char_p
+    lib.sd_int_peak.argtypes = [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.sd_int_peak.restype = C.c_int
+    _libs[flavour] = lib
+    return lib
+
+
+def device_count(flavour="cuda"):
+    return int(load_library(flavour).sd_device_count())
+
+
+def _pack(seqs):
+    """list of str/bytes -> (bytes blob, int64 offsets)"""
+    bs = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]
+    off = np.zeros(len(bs) + 1, dtype=np.int64)
+    if bs:
+        np.cumsum([len(b) for b in bs], out=off[1:])
+    return b"".join(bs), off
+
+
+class Decomposer:
+    """Mirror of the reference's MonomersAligner (main.cpp:56-66): monomers + scoring bound once, then
+    batches of read segments are decomposed.  ``devices``: None -> GPU 0, "all" -> every visible GPU, or a list."""
+
+    def __init__(self, monomers, ins=-1, dele=-1, mismatch=-1, match=1, devices=None, flavour="cuda"):
+        self._lib = load_library(flavour)
+        self._h = C.c_void_p()
+        blob, off = _pack(monomers)
+        if devices is None:
+            ids, n = None, 0
+        elif devices == "all":
+            ids, n = None, -1
+        else:
+            arr = (C.c_int32 * len(devices))(*devices)
+            ids, n = arr, len(devices)
+        st = self._lib.sd_create(blob, off.ctypes.data_as(C.POINTER(C.c_int64)), len(monomers), ins, dele, mismatch, match,
+                                 ids, n, C.byref(self._h))
+        if st:
+            raise SdError(st, (self._lib.sd_last_error(None) or b"").decode())
+        self.n_monomers = len(monomers)
+
+    def close(self):
+        if self._h:
+            self._lib.sd_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _err(self, st):
+        raise SdError(st, (self._lib.sd_last_error(self._h) or b"").decode())
+
+    def _take(self, recs, offs, nseg):
+        o = np.ctypeslib.as_array(C.cast(offs, C.POINTER(C.c_int64)), shape=(nseg + 1,)).copy()
+        n = int(o[-1])
+        if n:
+            r = np.frombuffer((C.c_char * (n * RECORD_DTYPE.itemsize)).from_address(recs.value), dtype=RECORD_DTYPE).copy()
+        else:
+            r = np.zeros(0, dtype=RECORD_DTYPE)
+        self._lib.sd_free(recs)
+        self._lib.sd_free(offs)
+        return r, o
+
+    def decompose(self, segments):
+        """segments: list of ACGTN strings, or (blob, offsets).  Returns (records, rec_offsets)."""
+        blob, off = segments if isinstance(segments, tuple) else _pack(segments)
+        nseg = len(off) - 1
+        recs, offs = C.c_void_p(), C.c_void_p()
+        st = self._lib.sd_decompose(self._h, blob, off.ctypes.data_as(C.POINTER(C.c_int64)), nseg, C.byref(recs), C.byref(offs))
+        if st:
+            self._err(st)
+        return self._take(recs, offs, nseg)
+
+    def stage(self, segments):
+        blob, off = segments if isinstance(segments, tuple) else _pack(segments)
+        self._staged = len(off) - 1
+        st = self._lib.sd_stage(self._h, blob, off.ctypes.data_as(C.POINTER(C.c_int64)), self._staged)
+        if st:
+            self._err(st)
+
+    def run_staged(self):
+        ms = C.c_double()
+        st = self._lib.sd_run_staged(self._h, C.byref(ms))
+        if st:
+            self._err(st)
+        return ms.value
+
+    def fetch_staged(self):
+        recs, offs = C.c_void_p(), C.c_void_p()
+        st = self._lib.sd_fetch_staged(self._h, C.byref(recs), C.byref(offs))
+        if st:
+            self._err(st)
+        return self._take(recs, offs, self._staged)
+
+    def stats(self):
+        s = _Stats()
+        self._lib.sd_get_stats(self._h, C.byref(s))
+        return {k: getattr(s, k) for k, _ in _Stats._fields_}
+
+    def reset_stats(self):
+        self._lib.sd_reset_stats(self._h)
+
+
+def segment_read(read_len, part_size, overlap, flavour="cuda"):
+    """AlignReadsSet segmentation (main.cpp:70-81): list of (offset, length)."""
+    lib = load_library(flavour)
+    n = lib.sd_segment_read(read_len, part_size, overlap, None, None, 0)
+    if n < 0:
+        raise SdError(1, "bad segmentation arguments")
+    offs = np.zeros(max(n, 1), dtype=np.int64)
+    lens = np.zeros(max(n, 1), dtype=np.int32)
+    lib.sd_segment_read(read_len, part_size, overlap, offs.ctypes.data_as(C.POINTER(C.c_int64)),
+                        lens.ctypes.data_as(C.POINTER(C.c_int32)), n)
+    return [(int(offs[i]), int(lens[i])) for i in range(n)]
+
+
+def postprocess(records, flavour="cuda"):
+    """PostProcessing (main.cpp:287-302) on a structured array of read-relative records."""
+    lib = load_library(flavour)
+    rin = np.ascontiguousarray(records, dtype=RECORD_DTYPE)
+    out = np.zeros(len(rin), dtype=RECORD_DTYPE)
+    n = lib.sd_postprocess(rin.ctypes.data, len(rin), out.ctypes.data)
+    return out[:n]
+
+
+def run_files(reads_path, monomers_path, threads=1, part_size=5000, overlap=500, scoring=(-1, -1, -1, 1), ed_thr=-1,
+              out_fd=1, err_fd=2, flavour="cuda"):
+    lib = load_library(flavour)
+    return lib.sd_run_files(str(reads_path).encode(), str(monomers_path).encode(), threads, part_size, overlap,
+                            scoring[0], scoring[1], scoring[2], scoring[3], ed_thr, out_fd, err_fd)
+
+
+def int_peak(device=0):
+    """Measured integer-pipe issue rates (lane-ops/s): (ALU pipe only, ALU+FMA pipes, implied SM clock MHz)."""
+    lib = load_library("cuda")
+    a, b, m = C.c_double(), C.c_double(), C.c_double()
+    st = lib.sd_int_peak(device, C.byref(a), C.byref(b), C.byref(m))
+    if st:
+        raise SdError(st, (lib.sd_last_error(None) or b"").decode())
+    return a.value, b.value, m.value

@@ -61,7 +61,7 @@ void emu_cta(const Plan &p, const Batch &b, int seg_first, int nseg_cta, int nma
             bool kill_first = (t == 0), kill_last = (t == T - 1 && L == 1);
             uint32_t adj_first = (i == 0 && t == 0 && L > 1) ? P::splat(4 * p.sc.del) : 0u;
             uint32_t adj_last = (i == 0 && t == T - 1 && L == 1) ? P::splat(4 * p.sc.del) : 0u;
-            ColumnConsts cc = make_column_consts<P>(i == 0 ? 0 : delta[seg_local]);
+            ColumnConsts cc = make_column_consts<P>(i == 0 ? 0 : delta[seg_local], 0u);
             E[tid] = lane_pass1<P, C>(X[tid], prevZ[tid], prof4, cc, deadz, kill_first, kill_last, adj_first, adj_last);
         }
         // inclusive prefix max inside each slot (Kogge-Stone on the device), then exclusive carry

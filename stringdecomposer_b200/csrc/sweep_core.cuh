@@ -107,11 +107,14 @@ struct Scalar32 {
 struct ColumnConsts {
     uint32_t addc_dg;   // splat(-2 - 4*delta): tag-3 form -> diag candidate (tag 1) in this column's base
     uint32_t addc_up;   // splat(-1 - 4*delta): tag-3 form -> insertion candidate (tag 2)
+    uint32_t jump0;     // the jump operand: 0 relative to the column base.  Passed as an opaque run-time zero so
+                        // that ptxas keeps it in one register instead of materialising a packed zero per cell.
 };
 
-template <class P> SD_HD ColumnConsts make_column_consts(int delta)
+template <class P> SD_HD ColumnConsts make_column_consts(int delta, uint32_t zero)
 {
     ColumnConsts c;
+    c.jump0 = zero;
     c.addc_dg = P::splat(-2 - 4 * delta);
     c.addc_up = P::splat(-1 - 4 * delta);
     return c;
@@ -135,7 +138,7 @@ SD_HD uint32_t lane_pass1(uint32_t (&X)[C], uint32_t prevZ, const uint32_t *prof
         uint32_t s4 = prof4[kk];
         if (kk == 0) s4 = P::add(s4, adj_first);
         if (kk == C - 1) s4 = P::add(s4, adj_last);
-        uint32_t m1 = P::addmax(prev, cc.addc_dg, 0u);     // max(diag', jump'=0)
+        uint32_t m1 = P::addmax(prev, cc.addc_dg, cc.jump0);     // max(diag', jump'=0)
         uint32_t m1s = P::add(m1, s4);
         uint32_t up = X[kk];
         prev = up;

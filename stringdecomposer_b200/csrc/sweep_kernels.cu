@@ -1,0 +1,478 @@
+// sweep_kernels.cu -- sm_100a kernels of the string-decomposition DP and the CUDA backend that drives them.
+//
+//   sweep_kernel<P,C,T>   column-synchronous forward sweep.  A CTA owns NS segments; every DP row pair (Packed16:
+//                         forward monomer + reverse complement in the two s16 halves of a register) or row (Scalar32)
+//                         is a slot of T lanes x C cells held in registers.  Per column: pass 1 (chain-free
+//                         candidates, DPX VIADDMNMX), prefix-max scan of the deletion chain across the T lanes
+//                         (warp shuffles), pass 2 (chain + 2-bit backpointers), per-segment max/argmax of the row
+//                         ends through shared-memory atomicMax on a (score,row) key, one barrier.
+//   traceback_kernel      walks the 2-bit backpointers (sweep_core.cuh: traceback_segment).
+//   gather_kernel         compacts + reverses the per-segment records into one dense array for the D2H copy.
+//   int_peak_kernel       integer-pipe issue-rate probe the roofline is quoted against.
+//
+// Reference semantics: stringdecomposer/src/main.cpp:151-270 (AlignPartClassicDP); see sweep_core.cuh.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <climits>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.h"
+
+namespace sdb {
+
+#define SD_CUDA(x)                                                                                              \
+    do {                                                                                                        \
+        cudaError_t e_ = (x);                                                                                   \
+        if (e_ != cudaSuccess) throw PlanError{std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " +  \
+                                               __FILE__ + ":" + std::to_string(__LINE__)};                      \
+    } while (0)
+
+struct SweepArgs {
+    const uint4 *prof; int prof_u4;
+    const uint8_t *bases; const int64_t *seg_off;      // seg_off indexed by global segment id
+    int seg_begin, nseg;                                // this launch covers segments [seg_begin, seg_begin+nseg)
+    const int *cta_nmax; const int64_t *cta_code_off; const int64_t *seg_j_off;
+    uint32_t *codes; int *jcol; int *arow;
+    const int *slot_len; const int *slot_endadd;
+    int nslots, M, NS, NT, CW, nsl;
+    int ins, del, deadz;
+    int seg_stride;
+    uint32_t zero;          // always 0 (see ColumnConsts::jump0)
+};
+
+template <class P, int C, int T>
+__global__ void sweep_kernel(const SweepArgs a)
+{
+    extern __shared__ uint4 smem_u4[];
+    uint4 *sprof = smem_u4;
+    int *skey = reinterpret_cast<int *>(sprof + a.prof_u4);             // [3][NS]
+    uint8_t *schar = reinterpret_cast<uint8_t *>(skey + 3 * a.NS + ((4 - (3 * a.NS) % 4) % 4));
+
+    const int tid = threadIdx.x, cta = blockIdx.x;
+    const int NS = a.NS, NT = a.NT;
+    const int ginst = tid / T, t = tid % T;
+    int seg_local = ginst / a.nslots;
+    const int slot = ginst % a.nslots;
+    const int first = cta * NS;                                         // first segment (local to this launch)
+    const bool active = seg_local < NS && first + seg_local < a.nseg;
+    if (seg_local >= NS) seg_local = 0;
+    const int nmax = a.cta_nmax[cta];
+    int n_seg = 0;
+    if (active) n_seg = (int)(a.seg_off[a.seg_begin + first + seg_local + 1] - a.seg_off[a.seg_begin + first + seg_local]);
+
+    // stage profile, segment symbols and keys
+    for (int x = tid; x < a.prof_u4; x += NT) sprof[x] = a.prof[x];
+    for (int s = 0; s < NS; ++s) {
+        int n = 0; const uint8_t *src = nullptr;
+        if (first + s < a.nseg) {
+            const int64_t o = a.seg_off[a.seg_begin + first + s];
+            n = (int)(a.seg_off[a.seg_begin + first + s + 1] - o);
+            src = a.bases + o;
+        }
+        for (int x = tid; x < a.seg_stride; x += NT) schar[s * a.seg_stride + x] = (x < n) ? src[x] : (uint8_t)0;
+    }
+    for (int x = tid; x < 3 * NS; x += NT) skey[x] = INT_MIN;
+    __syncthreads();
+
+    const int sl = slot * T + t;
+    const int L = a.slot_len[slot];
+    const int endadd = a.slot_endadd[slot];
+    const uint32_t deadz = P::splat(a.deadz);
+    const bool kill_first = (t == 0), kill_last = (t == T - 1 && L == 1);
+    const bool j_writer = active && slot == 0 && t == 0;
+    int *jdst = a.jcol + (active ? a.seg_j_off[first + seg_local] : 0);
+    int *adst = a.arow + (active ? a.seg_j_off[first + seg_local] : 0);
+    uint32_t *cdst = a.codes + a.cta_code_off[cta] + (size_t)tid * a.CW;
+    const size_t cstride = (size_t)NT * a.CW;
+    const uint8_t *mychar = schar + seg_local * a.seg_stride;
+
+    uint32_t X[C];
+#pragma unroll
+    for (int kk = 0; kk < C; ++kk) X[kk] = deadz;
+
+    int bprev = a.ins;            // column base B[0] = ins (row-0 rule, main.cpp:180)
+    int delta = 0;
+    int kcur = 0, knext = 1, kclr = 2;    // key buffers: read / accumulate / clear
+    for (int i = 0;; ++i) {
+        if (i >= 1) {
+            const int key = skey[kcur * NS + seg_local];
+            const int vmax = key_value(key);
+            if (j_writer && i <= n_seg) { jdst[i] = vmax + bprev + (i - 1) * a.ins; adst[i] = key_row(key); }
+            delta = vmax + a.del;
+            bprev += delta;
+        }
+        if (i == nmax) break;
+        if (tid < NS) skey[kclr * NS + tid] = INT_MIN;
+
+        const int sym = mychar[i];
+        const uint4 *pp = sprof + (size_t)sym * (C / 4) * a.nsl + sl;
+        uint32_t pw[C];
+#pragma unroll
+        for (int q = 0; q < C / 4; ++q) {
+            const uint4 v = pp[(size_t)q * a.nsl];
+            pw[4 * q] = v.x; pw[4 * q + 1] = v.y; pw[4 * q + 2] = v.z; pw[4 * q + 3] = v.w;
+        }
+        uint32_t prevZ = deadz;
+        if (T > 1) { prevZ = __shfl_up_sync(0xffffffffu, X[C - 1], 1, T); if (t == 0) prevZ = deadz; }
+        uint32_t adj_first = 0u, adj_last = 0u;
+        if (i == 0) {
+            if (t == 0 && L > 1) adj_first = P::splat(4 * a.del);
+            if (t == T - 1 && L == 1) adj_last = P::splat(4 * a.del);
+        }
+        const ColumnConsts cc = make_column_consts<P>(delta, a.zero);
+        uint32_t E = lane_pass1<P, C>(X, prevZ, pw, cc, deadz, kill_first, kill_last, adj_first, adj_last);
+
+        uint32_t carry = deadz;
+        if (T > 1) {
+            uint32_t incl = E;
+#pragma unroll
+            for (int d = 1; d < T; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d, T);
+                if (t >= d) incl = P::max2(incl, o);
+            }
+            carry = __shfl_up_sync(0xffffffffu, incl, 1, T);
+            if (t == 0) carry = deadz;
+        }
+        uint32_t cw[(C + P::CELLS_PER_WORD - 1) / P::CELLS_PER_WORD];
+        lane_pass2<P, C>(X, carry, cw);
+
+        if (active && i < n_seg) {
+            uint32_t *d = cdst + (size_t)i * cstride;
+            constexpr int NW = (C + P::CELLS_PER_WORD - 1) / P::CELLS_PER_WORD;
+            if (NW == 2) *reinterpret_cast<uint2 *>(d) = make_uint2(cw[0], cw[1]);
+            else if (NW == 4) *reinterpret_cast<uint4 *>(d) = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+            else {
+#pragma unroll
+                for (int w = 0; w < NW; ++w) d[w] = cw[w];
+            }
+        }
+        if (t == T - 1 && active) {
+            const uint32_t z = X[C - 1];
+            int key = make_key(P::lo(z), endadd, slot);
+            if (P::ROWS == 2) key = max(key, make_key(P::hi(z), endadd, a.M + slot));
+            atomicMax(&skey[knext * NS + seg_local], key);
+        }
+        __syncthreads();
+        const int tmp = kcur; kcur = knext; knext = kclr; kclr = tmp;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct TbArgs {
+    Geometry g;
+    const uint32_t *codes; const int64_t *cta_code_off;
+    const int *jcol; const int *arow; const int64_t *seg_j_off;
+    const uint8_t *bases; const int64_t *seg_off; int seg_begin, nseg;
+    const uint8_t *rows; const int *row_off;
+    int ins, del, mismatch, match;
+    Record *scratch; const int64_t *seg_rec_off; int *counts;
+};
+
+__global__ void traceback_kernel(const TbArgs a)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= a.nseg) return;
+    const Geometry g = a.g;
+    const int cta = s / g.NS, seg_local = s % g.NS;
+    const int64_t o = a.seg_off[a.seg_begin + s];
+    const int n = (int)(a.seg_off[a.seg_begin + s + 1] - o);
+    const uint32_t *cbase = a.codes + a.cta_code_off[cta];
+    const size_t cstride = (size_t)g.NT * g.CW;
+    auto code_at = [&](int i, int row, int rowlen, int k) { return fetch_code(cbase + (size_t)i * cstride, g, seg_local, row, rowlen, k); };
+    a.counts[s] = traceback_segment(n, a.jcol + a.seg_j_off[s], a.arow + a.seg_j_off[s], a.bases + o, a.rows, a.row_off,
+                                    a.ins, a.del, a.mismatch, a.match, code_at, a.scratch + a.seg_rec_off[s], n);
+}
+
+// dense[out_off[s] + x] = scratch[seg_rec_off[s] + cnt-1-x]   (reversal of main.cpp:268)
+__global__ void gather_kernel(const Record *scratch, const int64_t *seg_rec_off, const int *counts, const int64_t *out_off,
+                              Record *dense, int nseg)
+{
+    const int s = blockIdx.x;
+    if (s >= nseg) return;
+    const int c = counts[s];
+    const Record *src = scratch + seg_rec_off[s];
+    Record *dst = dense + out_off[s];
+    for (int x = threadIdx.x; x < c; x += blockDim.x) dst[x] = src[c - 1 - x];
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int MODE> __global__ void int_peak_kernel(unsigned *out, unsigned seed)
+{
+    unsigned r[8];
+    const unsigned b = seed * 3u + threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = threadIdx.x * 17u + j * 1315423911u + seed;
+    for (int it = 0; it < 2048; ++it) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const unsigned nb = r[(j + 1) & 7];
+            if (MODE == 0) r[j] = __viaddmax_s16x2(r[j], b, nb);                       // ALU pipe only
+            else { r[j] = __viaddmax_s16x2(r[j], b, nb); r[j] = r[j] * b + nb; }       // ALU + FMA(IMAD) pipes
+        }
+    }
+    unsigned acc = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc ^= r[j];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+template <class P, int C> static const void *kern_t(int T)
+{
+    switch (T) {
+    case 1: return (const void *)sweep_kernel<P, C, 1>; case 2: return (const void *)sweep_kernel<P, C, 2>;
+    case 4: return (const void *)sweep_kernel<P, C, 4>; case 8: return (const void *)sweep_kernel<P, C, 8>;
+    case 16: return (const void *)sweep_kernel<P, C, 16>; case 32: return (const void *)sweep_kernel<P, C, 32>;
+    }
+    return nullptr;
+}
+template <class P> static const void *kern(int C, int T)
+{
+    switch (C) {
+    case 8: return kern_t<P, 8>(T); case 16: return kern_t<P, 16>(T); case 24: return kern_t<P, 24>(T);
+    case 32: return kern_t<P, 32>(T); case 48: return kern_t<P, 48>(T);
+    }
+    return nullptr;
+}
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr; size_t cap = 0;
+    void need(size_t bytes)
+    {
+        if (bytes <= cap) return;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        SD_CUDA(cudaMalloc(&p, want));
+        cap = want;
+    }
+    template <class U> U *as() { return reinterpret_cast<U *>(p); }
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+
+class CudaBackend : public Backend {
+public:
+    explicit CudaBackend(int dev) : dev_(dev)
+    {
+        SD_CUDA(cudaSetDevice(dev_));
+        SD_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+        for (auto &e : ev_) SD_CUDA(cudaEventCreate(&e));
+        SD_CUDA(cudaGetDeviceProperties(&prop_, dev_));
+        if (prop_.major < 10) throw PlanError{"CUDA device is not sm_100 class: this library carries sm_100a code only"};
+    }
+    ~CudaBackend() override
+    {
+        cudaSetDevice(dev_);
+        for (auto &e : ev_) cudaEventDestroy(e);
+        cudaStreamDestroy(st_);
+    }
+    const char *name() const override { return "cuda"; }
+
+    void configure(const Plan &p, const MonomerSet &ms) override
+    {
+        SD_CUDA(cudaSetDevice(dev_));
+        plan_ = p; ms_ = ms;
+        const Geometry &g = p.g;
+        kernel_ = g.packed ? kern<Packed16>(g.C, g.T) : kern<Scalar32>(g.C, g.T);
+        if (!kernel_) throw PlanError{"no sweep kernel compiled for this geometry"};
+        cudaFuncAttributes fa;
+        SD_CUDA(cudaFuncGetAttributes(&fa, kernel_));
+        if ((int64_t)fa.numRegs * g.NT > 65536) throw PlanError{"sweep geometry exceeds the register file (regs*threads > 64K)"};
+        d_prof_.need(p.prof.size() * 4);
+        SD_CUDA(cudaMemcpyAsync(d_prof_.p, p.prof.data(), p.prof.size() * 4, cudaMemcpyHostToDevice, st_));
+        d_slotlen_.need(p.slot_len.size() * 4); d_slotend_.need(p.slot_endadd.size() * 4);
+        SD_CUDA(cudaMemcpyAsync(d_slotlen_.p, p.slot_len.data(), p.slot_len.size() * 4, cudaMemcpyHostToDevice, st_));
+        SD_CUDA(cudaMemcpyAsync(d_slotend_.p, p.slot_endadd.data(), p.slot_endadd.size() * 4, cudaMemcpyHostToDevice, st_));
+        d_rows_.need(ms.rows.size()); d_rowoff_.need(ms.row_off.size() * 4);
+        SD_CUDA(cudaMemcpyAsync(d_rows_.p, ms.rows.data(), ms.rows.size(), cudaMemcpyHostToDevice, st_));
+        SD_CUDA(cudaMemcpyAsync(d_rowoff_.p, ms.row_off.data(), ms.row_off.size() * 4, cudaMemcpyHostToDevice, st_));
+        SD_CUDA(cudaStreamSynchronize(st_));
+    }
+
+    int64_t wave_bytes(const Batch &b, int s0, int s1) const override
+    {
+        CtaLayout l = make_cta_layout(plan_, b, s0, s1);
+        return l.cta_code_off.back() * 4 + l.seg_j_off.back() * 8 + l.seg_rec_off.back() * 32 + (b.off[s1] - b.off[s0]);
+    }
+    int64_t wave_budget() const override
+    {
+        if (const char *e = getenv("SD_WAVE_BYTES")) return atoll(e);
+        size_t fr = 0, tot = 0;
+        cudaSetDevice(dev_);
+        if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) return (int64_t)8 << 30;
+        int64_t pool = (int64_t)(d_codes_.cap + d_scratch_.cap + d_dense_.cap);
+        return std::min<int64_t>((int64_t)((fr + pool) * 0.85), (int64_t)96 << 30);
+    }
+
+    void stage(const Batch &b, int s0, int s1) override
+    {
+        SD_CUDA(cudaSetDevice(dev_));
+        const Geometry &g = plan_.g;
+        s0_ = s0; s1_ = s1; nseg_ = s1 - s0;
+        lay_ = make_cta_layout(plan_, b, s0, s1);
+        nmax_ = 0;
+        for (int v : lay_.cta_nmax) nmax_ = std::max(nmax_, v);
+        // inputs: bases of [s0,s1) and their offsets rebased to the staged buffer
+        const int64_t base = b.off[s0];
+        const size_t nb = (size_t)(b.off[s1] - base);
+        hoff_.resize((size_t)nseg_ + 1);
+        for (int s = 0; s <= nseg_; ++s) hoff_[s] = b.off[s0 + s] - base;
+        d_bases_.need(nb + 16); d_segoff_.need(hoff_.size() * 8);
+        d_ctanmax_.need(lay_.cta_nmax.size() * 4); d_ctacode_.need(lay_.cta_code_off.size() * 8);
+        d_segj_.need(lay_.seg_j_off.size() * 8); d_segrec_.need(lay_.seg_rec_off.size() * 8);
+        d_codes_.need((size_t)lay_.cta_code_off.back() * 4 + 16);
+        d_jcol_.need((size_t)lay_.seg_j_off.back() * 4 + 16); d_arow_.need((size_t)lay_.seg_j_off.back() * 4 + 16);
+        d_scratch_.need((size_t)lay_.seg_rec_off.back() * sizeof(Record) + 16);
+        d_counts_.need((size_t)nseg_ * 4 + 16); d_outoff_.need(((size_t)nseg_ + 1) * 8);
+        SD_CUDA(cudaEventRecord(ev_[0], st_));
+        SD_CUDA(cudaMemcpyAsync(d_bases_.p, b.bases.data() + base, nb, cudaMemcpyHostToDevice, st_));
+        SD_CUDA(cudaMemcpyAsync(d_segoff_.p, hoff_.data(), hoff_.size() * 8, cudaMemcpyHostToDevice, st_));
+        SD_CUDA(cudaMemcpyAsync(d_ctanmax_.p, lay_.cta_nmax.data(), lay_.cta_nmax.size() * 4, cudaMemcpyHostToDevice, st_));
+        SD_CUDA(cudaMemcpyAsync(d_ctacode_.p, lay_.cta_code_off.data(), lay_.cta_code_off.size() * 8, cudaMemcpyHostToDevice, st_));
+        SD_CUDA(cudaMemcpyAsync(d_segj_.p, lay_.seg_j_off.data(), lay_.seg_j_off.size() * 8, cudaMemcpyHostToDevice, st_));
+        SD_CUDA(cudaMemcpyAsync(d_segrec_.p, lay_.seg_rec_off.data(), lay_.seg_rec_off.size() * 8, cudaMemcpyHostToDevice, st_));
+        SD_CUDA(cudaEventRecord(ev_[1], st_));
+        SD_CUDA(cudaStreamSynchronize(st_));
+        float ms = 0; SD_CUDA(cudaEventElapsedTime(&ms, ev_[0], ev_[1]));
+        h2d_ms += ms;
+        h2d_bytes += (int64_t)(nb + hoff_.size() * 8 + lay_.cta_nmax.size() * 4 + lay_.cta_code_off.size() * 8 + lay_.seg_j_off.size() * 16);
+        (void)g;
+    }
+
+    void execute() override
+    {
+        SD_CUDA(cudaSetDevice(dev_));
+        const Geometry &g = plan_.g;
+        SweepArgs a;
+        a.prof = d_prof_.as<uint4>(); a.prof_u4 = (int)(plan_.prof.size() / 4);
+        a.bases = d_bases_.as<uint8_t>(); a.seg_off = d_segoff_.as<int64_t>();
+        a.seg_begin = 0; a.nseg = nseg_;
+        a.cta_nmax = d_ctanmax_.as<int>(); a.cta_code_off = d_ctacode_.as<int64_t>(); a.seg_j_off = d_segj_.as<int64_t>();
+        a.codes = d_codes_.as<uint32_t>(); a.jcol = d_jcol_.as<int>(); a.arow = d_arow_.as<int>();
+        a.slot_len = d_slotlen_.as<int>(); a.slot_endadd = d_slotend_.as<int>();
+        a.nslots = g.nslots; a.M = g.M; a.NS = g.NS; a.NT = g.NT; a.CW = g.CW; a.nsl = plan_.nsl;
+        a.ins = plan_.sc.ins; a.del = plan_.sc.del; a.deadz = plan_.deadz;
+        a.seg_stride = (nmax_ + 16) / 16 * 16; a.zero = 0u;
+        const size_t smem = plan_.prof.size() * 4 + ((size_t)3 * g.NS + 4) * 4 + (size_t)g.NS * a.seg_stride;
+        if (smem > (size_t)prop_.sharedMemPerBlockOptin) throw PlanError{"sweep geometry needs more shared memory than the SM has"};
+        SD_CUDA(cudaFuncSetAttribute(kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int nctas = (int)lay_.cta_nmax.size();
+        void *args[] = {(void *)&a};
+        SD_CUDA(cudaEventRecord(ev_[0], st_));
+        SD_CUDA(cudaLaunchKernel(kernel_, dim3(nctas), dim3(g.NT), args, smem, st_));
+        SD_CUDA(cudaEventRecord(ev_[1], st_));
+        TbArgs t;
+        t.g = g; t.codes = a.codes; t.cta_code_off = a.cta_code_off; t.jcol = a.jcol; t.arow = a.arow; t.seg_j_off = a.seg_j_off;
+        t.bases = a.bases; t.seg_off = a.seg_off; t.seg_begin = 0; t.nseg = nseg_;
+        t.rows = d_rows_.as<uint8_t>(); t.row_off = d_rowoff_.as<int>();
+        t.ins = plan_.sc.ins; t.del = plan_.sc.del; t.mismatch = plan_.sc.mismatch; t.match = plan_.sc.match;
+        t.scratch = d_scratch_.as<Record>(); t.seg_rec_off = d_segrec_.as<int64_t>(); t.counts = d_counts_.as<int>();
+        traceback_kernel<<<(nseg_ + 31) / 32, 32, 0, st_>>>(t);
+        SD_CUDA(cudaGetLastError());
+        SD_CUDA(cudaEventRecord(ev_[2], st_));
+        SD_CUDA(cudaStreamSynchronize(st_));
+        float ms = 0;
+        SD_CUDA(cudaEventElapsedTime(&ms, ev_[0], ev_[1])); sweep_ms += ms;
+        SD_CUDA(cudaEventElapsedTime(&ms, ev_[1], ev_[2])); traceback_ms += ms;
+        launches += 2;
+    }
+
+    void fetch(BatchResult &out) override
+    {
+        SD_CUDA(cudaSetDevice(dev_));
+        hcnt_.resize((size_t)nseg_);
+        SD_CUDA(cudaEventRecord(ev_[0], st_));
+        SD_CUDA(cudaMemcpyAsync(hcnt_.data(), d_counts_.p, (size_t)nseg_ * 4, cudaMemcpyDeviceToHost, st_));
+        SD_CUDA(cudaStreamSynchronize(st_));
+        houtoff_.assign((size_t)nseg_ + 1, 0);
+        for (int s = 0; s < nseg_; ++s) {
+            if (hcnt_[s] < 0) throw PlanError{"traceback overflowed its record buffer (internal error)"};
+            houtoff_[s + 1] = houtoff_[s] + hcnt_[s];
+        }
+        const int64_t total = houtoff_[nseg_];
+        d_dense_.need((size_t)total * sizeof(Record) + 16);
+        SD_CUDA(cudaMemcpyAsync(d_outoff_.p, houtoff_.data(), houtoff_.size() * 8, cudaMemcpyHostToDevice, st_));
+        gather_kernel<<<nseg_, 64, 0, st_>>>(d_scratch_.as<Record>(), d_segrec_.as<int64_t>(), d_counts_.as<int>(),
+                                             d_outoff_.as<int64_t>(), d_dense_.as<Record>(), nseg_);
+        SD_CUDA(cudaGetLastError());
+        const size_t base = out.recs.size();
+        out.recs.resize(base + (size_t)total);
+        if (total) SD_CUDA(cudaMemcpyAsync(out.recs.data() + base, d_dense_.p, (size_t)total * sizeof(Record), cudaMemcpyDeviceToHost, st_));
+        SD_CUDA(cudaEventRecord(ev_[1], st_));
+        SD_CUDA(cudaStreamSynchronize(st_));
+        float ms = 0; SD_CUDA(cudaEventElapsedTime(&ms, ev_[0], ev_[1]));
+        d2h_ms += ms; d2h_bytes += (int64_t)nseg_ * 4 + total * (int64_t)sizeof(Record);
+        launches += 1;
+        for (int s = 0; s < nseg_; ++s) out.rec_off.push_back((int64_t)base + houtoff_[s + 1]);
+    }
+
+private:
+    int dev_;
+    cudaStream_t st_{};
+    cudaEvent_t ev_[3]{};
+    cudaDeviceProp prop_{};
+    Plan plan_; MonomerSet ms_;
+    const void *kernel_ = nullptr;
+    CtaLayout lay_;
+    int s0_ = 0, s1_ = 0, nseg_ = 0, nmax_ = 0;
+    std::vector<int64_t> hoff_, houtoff_;
+    std::vector<int> hcnt_;
+    DevBuf d_prof_, d_slotlen_, d_slotend_, d_rows_, d_rowoff_;
+    DevBuf d_bases_, d_segoff_, d_ctanmax_, d_ctacode_, d_segj_, d_segrec_;
+    DevBuf d_codes_, d_jcol_, d_arow_, d_scratch_, d_counts_, d_outoff_, d_dense_;
+};
+
+} // namespace
+
+Backend *make_cuda_backend(int device_id, std::string &err)
+{
+    try { return new CudaBackend(device_id); }
+    catch (PlanError &e) { err = e.msg; return nullptr; }
+}
+
+} // namespace sdb
+
+int cuda_device_count()
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int cuda_int_peak(int device, double *alu, double *both, double *mhz, std::string &err)
+{
+    using namespace sdb;
+    try {
+        SD_CUDA(cudaSetDevice(device));
+        cudaDeviceProp p; SD_CUDA(cudaGetDeviceProperties(&p, device));
+        const int nblk = p.multiProcessorCount * 2, nthr = 512;
+        unsigned *d; SD_CUDA(cudaMalloc(&d, (size_t)nblk * nthr * 4));
+        cudaEvent_t e0, e1; SD_CUDA(cudaEventCreate(&e0)); SD_CUDA(cudaEventCreate(&e1));
+        double res[2] = {0, 0};
+        for (int mode = 0; mode < 2; ++mode) {
+            float best = 1e30f;
+            for (int rep = 0; rep < 5; ++rep) {
+                SD_CUDA(cudaEventRecord(e0));
+                if (mode == 0) int_peak_kernel<0><<<nblk, nthr>>>(d, 1234u); else int_peak_kernel<1><<<nblk, nthr>>>(d, 1234u);
+                SD_CUDA(cudaEventRecord(e1));
+                SD_CUDA(cudaEventSynchronize(e1));
+                float ms; SD_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+                if (rep > 0) best = std::min(best, ms);
+            }
+            const double ops = (double)nblk * nthr * 2048.0 * 8.0 * (mode == 0 ? 1.0 : 2.0);
+            res[mode] = ops / (best * 1e-3);
+        }
+        if (alu) *alu = res[0];
+        if (both) *both = res[1];
+        if (mhz) *mhz = res[0] / ((double)p.multiProcessorCount * 64.0) / 1e6;     // ALU pipe: 64 lanes/clk/SM (measured)
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    } catch (PlanError &e) { err = e.msg; return 4; }
+    return 0;
+}
