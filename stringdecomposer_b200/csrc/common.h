@@ -33,7 +33,8 @@ struct Plan {
     Scoring sc;
     int deadz = 0;                       // "minus infinity" in tag-3 form
     int nsl = 0;                         // slot lanes per segment = nslots*T
-    std::vector<uint32_t> prof;          // [5 symbols][C/4][nsl][4] profile words 4*s'' (pad cells: very negative)
+    int qp = 0;                          // uint4 per lane row of the profile: C/4 padded to an odd count (bank-conflict-free LDS.128)
+    std::vector<uint32_t> prof;          // [5 symbols][nsl][qp][4] profile words 4*s''-1 (pad cells: very negative)
     std::vector<int> slot_len;           // row length of each slot
     std::vector<int> slot_endadd;        // (L-1)*del of each slot
     size_t smem_bytes(int seg_stride) const;

@@ -16,94 +16,114 @@ namespace {
 
 template <class P, int C, int T>
 void emu_cta(const Plan &p, const Batch &b, int seg_first, int nseg_cta, int nmax,
-             uint32_t *codes, int *const *jcol, int *const *arow)
+             uint32_t *codes, JR *const *jr)
 {
     const Geometry &g = p.g;
     const int NT = g.NT, NS = g.NS;
-    std::vector<uint32_t> Xall((size_t)NT * C, (uint32_t)P::splat(p.deadz));
-    std::vector<uint32_t> E(NT), incl(NT), carry(NT), prevZ(NT);
-    std::vector<int> Bprev(NS, p.sc.ins), delta(NS, 0);
-    std::vector<int> key(NS, INT_MIN), keynext(NS, INT_MIN);
-    const uint32_t deadz = P::splat(p.deadz);
+    constexpr int SPW = 32 / T;
+    const uint32_t deadu = P::splat(p.deadz - 1);
+    std::vector<uint32_t> Xall((size_t)NT * C, deadu), PWall((size_t)NT * C, 0u);
+    std::vector<uint32_t> E(NT), carry(NT), prevU(NT);
+    std::vector<int> bref(NS, p.sc.ins), jump0(NS, 0);
+    std::vector<int> key(NS, INT_MIN);
     uint32_t (*X)[C] = reinterpret_cast<uint32_t (*)[C]>(Xall.data());
-    uint32_t prof4[C];
+    uint32_t (*PW)[C] = reinterpret_cast<uint32_t (*)[C]>(PWall.data());
     uint32_t cw[8];
-    for (int i = 0; i <= nmax; ++i) {
-        for (int s = 0; s < nseg_cta; ++s) {
-            if (i >= 1) {
-                int vmax = key_value(key[s]);
-                if (i <= b.len(seg_first + s)) {
-                    jcol[s][i] = vmax + Bprev[s] + (i - 1) * p.sc.ins;
-                    arow[s][i] = key_row(key[s]);
-                }
-                delta[s] = vmax + p.sc.del;
-                Bprev[s] += delta[s];
-            }
-        }
-        if (i == nmax) break;
-        std::fill(keynext.begin(), keynext.end(), INT_MIN);
-        // "shuffle": previous-column Z of the cell to the left of each lane's first cell
+    struct LaneId { bool ok; int seg_local, slot, t, sl; bool active; int n; };
+    auto lane_id = [&](int tid) {
+        LaneId l;
+        const int warp = tid / 32, lane = tid % 32, siw = lane / T;
+        l.t = lane - siw * T;
+        l.ok = siw < SPW;
+        const int ginst = warp * SPW + (l.ok ? siw : 0);
+        l.seg_local = ginst / g.nslots; l.slot = ginst % g.nslots;
+        l.active = l.ok && l.seg_local < NS && l.seg_local < nseg_cta;
+        if (l.seg_local >= NS) l.seg_local = 0;
+        l.sl = l.slot * T + l.t;
+        l.n = (l.seg_local < nseg_cta) ? b.len(seg_first + l.seg_local) : 0;
+        return l;
+    };
+    auto load_profile = [&](int tid, const LaneId &l, int i) {
+        const int sym = (i < l.n) ? b.bases[b.off[seg_first + l.seg_local] + i] : 0;
+        for (int kk = 0; kk < C; ++kk)
+            PW[tid][kk] = p.prof[(((size_t)sym * p.nsl + l.sl) * p.qp + kk / 4) * 4 + (kk % 4)];
+    };
+    // prologue: column 0
+    for (int tid = 0; tid < NT; ++tid) {
+        const LaneId l = lane_id(tid);
+        const int L = p.slot_len[l.slot];
+        load_profile(tid, l, 0);
+        if (l.t == 0 && L > 1) PW[tid][0] = P::add(PW[tid][0], P::splat(4 * p.sc.del));
+        if (l.t == T - 1 && L == 1) PW[tid][C - 1] = P::add(PW[tid][C - 1], P::splat(4 * p.sc.del));
+        lane_pre<P, C>(X[tid], deadu, PW[tid], deadu, l.t == 0, l.t == T - 1 && L == 1);
+    }
+    for (int i = 0;; ++i) {
         for (int tid = 0; tid < NT; ++tid) {
-            int t = tid % T;
-            prevZ[tid] = (t == 0) ? deadz : X[tid - 1][C - 1];
+            const LaneId l = lane_id(tid);
+            E[tid] = lane_post<P, C>(X[tid], PW[tid], P::splat(jump0[l.seg_local] + 1), deadu, tag_regs<P>());
         }
+        // exclusive prefix max of E inside each slot (slot_scan on the device)
         for (int tid = 0; tid < NT; ++tid) {
-            int ginst = tid / T, t = tid % T;
-            int seg_local = ginst / g.nslots, slot = ginst % g.nslots;
-            bool lane_ok = seg_local < NS;
-            if (!lane_ok) { seg_local = 0; }
-            int sl = slot * T + t;
-            int n = (seg_local < nseg_cta) ? b.len(seg_first + seg_local) : 0;
-            int sym = (i < n) ? b.bases[b.off[seg_first + seg_local] + i] : 0;
-            for (int kk = 0; kk < C; ++kk)
-                prof4[kk] = p.prof[(((size_t)sym * (C / 4) + kk / 4) * p.nsl + sl) * 4 + (kk % 4)];
-            const int L = p.slot_len[slot];
-            bool kill_first = (t == 0), kill_last = (t == T - 1 && L == 1);
-            uint32_t adj_first = (i == 0 && t == 0 && L > 1) ? P::splat(4 * p.sc.del) : 0u;
-            uint32_t adj_last = (i == 0 && t == T - 1 && L == 1) ? P::splat(4 * p.sc.del) : 0u;
-            ColumnConsts cc = make_column_consts<P>(i == 0 ? 0 : delta[seg_local], 0u);
-            E[tid] = lane_pass1<P, C>(X[tid], prevZ[tid], prof4, cc, deadz, kill_first, kill_last, adj_first, adj_last);
+            const LaneId l = lane_id(tid);
+            carry[tid] = (l.t == 0) ? deadu : P::max2(carry[tid - 1], E[tid - 1]);
         }
-        // inclusive prefix max inside each slot (Kogge-Stone on the device), then exclusive carry
+        std::fill(key.begin(), key.end(), INT_MIN);
         for (int tid = 0; tid < NT; ++tid) {
-            int t = tid % T;
-            incl[tid] = (t == 0) ? E[tid] : P::max2(incl[tid - 1], E[tid]);
-        }
-        for (int tid = 0; tid < NT; ++tid) carry[tid] = (tid % T == 0) ? deadz : incl[tid - 1];
-        for (int tid = 0; tid < NT; ++tid) {
-            int ginst = tid / T, t = tid % T;
-            int seg_local = ginst / g.nslots, slot = ginst % g.nslots;
-            lane_pass2<P, C>(X[tid], carry[tid], cw);
-            bool active = seg_local < nseg_cta;
-            int n = active ? b.len(seg_first + seg_local) : 0;
-            if (active && i < n)
+            const LaneId l = lane_id(tid);
+            lane_pass2<P, C>(X[tid], carry[tid], cw, tag_regs<P>());
+            if (l.active && i < l.n)
                 for (int w = 0; w < g.CW; ++w) codes[((size_t)i * NT + tid) * g.CW + w] = cw[w];
-            if (active && t == T - 1) {
-                uint32_t z = X[tid][C - 1];
-                int k0 = make_key(P::lo(z), p.slot_endadd[slot], slot);
-                if (P::ROWS == 2) k0 = std::max(k0, make_key(P::hi(z), p.slot_endadd[slot], g.M + slot));
-                keynext[seg_local] = std::max(keynext[seg_local], k0);
+            if (l.active && l.t == T - 1) {
+                const uint32_t u = X[tid][C - 1];
+                int k0 = make_key(P::lo(u), p.slot_endadd[l.slot], l.slot);
+                if (P::ROWS == 2) k0 = std::max(k0, make_key(P::hi(u), p.slot_endadd[l.slot], g.M + l.slot));
+                key[l.seg_local] = std::max(key[l.seg_local], k0);
             }
         }
-        key = keynext;
+        if (i + 1 < nmax) {
+            for (int tid = 0; tid < NT; ++tid) prevU[tid] = (lane_id(tid).t == 0) ? deadu : X[tid - 1][C - 1];
+            for (int tid = 0; tid < NT; ++tid) {
+                const LaneId l = lane_id(tid);
+                load_profile(tid, l, i + 1);
+                lane_pre<P, C>(X[tid], prevU[tid], PW[tid], deadu, l.t == 0, l.t == T - 1 && p.slot_len[l.slot] == 1);
+            }
+        }
+        // "barrier": keys visible
+        std::vector<int> shift(NS, 0);
+        for (int s = 0; s < nseg_cta; ++s) {
+            const int vmax = key_value(key[s]);
+            if (i + 1 <= b.len(seg_first + s)) {
+                jr[s][i + 1].j = vmax + bref[s] + i * p.sc.ins;
+                jr[s][i + 1].row = key_row(key[s]);
+            }
+            jump0[s] = 4 * (vmax + p.sc.del);
+            if (jump0[s] > SD_REBASE_TH || jump0[s] < -SD_REBASE_TH) { shift[s] = jump0[s]; bref[s] += jump0[s] >> 2; jump0[s] = 0; }
+        }
+        if (i + 1 == nmax) break;
+        for (int tid = 0; tid < NT; ++tid) {
+            const LaneId l = lane_id(tid);
+            if (l.seg_local < nseg_cta && shift[l.seg_local]) lane_rebase<P, C>(X[tid], shift[l.seg_local]);
+        }
     }
 }
 
-template <class P> using CtaFn = void (*)(const Plan &, const Batch &, int, int, int, uint32_t *, int *const *, int *const *);
+template <class P> using CtaFn = void (*)(const Plan &, const Batch &, int, int, int, uint32_t *, JR *const *);
 
 template <class P, int C> CtaFn<P> pick_t(int T)
 {
     switch (T) {
     case 1: return emu_cta<P, C, 1>; case 2: return emu_cta<P, C, 2>; case 4: return emu_cta<P, C, 4>;
-    case 8: return emu_cta<P, C, 8>; case 16: return emu_cta<P, C, 16>; case 32: return emu_cta<P, C, 32>;
+    case 8: return emu_cta<P, C, 8>; case 10: return emu_cta<P, C, 10>; case 16: return emu_cta<P, C, 16>;
+    case 32: return emu_cta<P, C, 32>;
     }
     return nullptr;
 }
 template <class P> CtaFn<P> pick(int C, int T)
 {
     switch (C) {
-    case 8: return pick_t<P, 8>(T); case 16: return pick_t<P, 16>(T); case 24: return pick_t<P, 24>(T);
-    case 32: return pick_t<P, 32>(T); case 48: return pick_t<P, 48>(T);
+    case 8: return pick_t<P, 8>(T); case 12: return pick_t<P, 12>(T); case 16: return pick_t<P, 16>(T);
+    case 20: return pick_t<P, 20>(T); case 24: return pick_t<P, 24>(T); case 32: return pick_t<P, 32>(T);
+    case 48: return pick_t<P, 48>(T);
     }
     return nullptr;
 }
@@ -128,16 +148,16 @@ public:
         const Geometry &g = plan_.g;
         const Batch &b = *batch_;
         codes_.assign((size_t)lay_.cta_code_off.back(), 0u);
-        jcol_.assign((size_t)lay_.seg_j_off.back(), 0); arow_.assign((size_t)lay_.seg_j_off.back(), 0);
+        jr_.assign((size_t)lay_.seg_j_off.back(), JR{0, 0});
         const int nseg = s1_ - s0_, nctas = (int)lay_.cta_nmax.size();
         EmuFlags::overflow() = false;
         for (int c = 0; c < nctas; ++c) {
             int first = c * g.NS, cnt = std::min(g.NS, nseg - first);
-            std::vector<int *> jp(g.NS, nullptr), ap(g.NS, nullptr);
-            for (int s = 0; s < cnt; ++s) { jp[s] = jcol_.data() + lay_.seg_j_off[first + s]; ap[s] = arow_.data() + lay_.seg_j_off[first + s]; }
+            std::vector<JR *> jp(g.NS, nullptr);
+            for (int s = 0; s < cnt; ++s) jp[s] = jr_.data() + lay_.seg_j_off[first + s];
             uint32_t *codes = codes_.data() + lay_.cta_code_off[c];
-            if (g.packed) pick<Packed16>(g.C, g.T)(plan_, b, s0_ + first, cnt, lay_.cta_nmax[c], codes, jp.data(), ap.data());
-            else pick<Scalar32>(g.C, g.T)(plan_, b, s0_ + first, cnt, lay_.cta_nmax[c], codes, jp.data(), ap.data());
+            if (g.packed) pick<Packed16>(g.C, g.T)(plan_, b, s0_ + first, cnt, lay_.cta_nmax[c], codes, jp.data());
+            else pick<Scalar32>(g.C, g.T)(plan_, b, s0_ + first, cnt, lay_.cta_nmax[c], codes, jp.data());
         }
         overflowed_ = g.packed && EmuFlags::overflow();
         launches += 2;
@@ -151,7 +171,7 @@ public:
             auto code_at = [&](int i, int row, int rowlen, int k) {
                 return fetch_code(cbase + (size_t)i * g.NT * g.CW, g, seg_local, row, rowlen, k);
             };
-            cnt_[s] = traceback_segment(n, jcol_.data() + lay_.seg_j_off[s], arow_.data() + lay_.seg_j_off[s],
+            cnt_[s] = traceback_segment(n, jr_.data() + lay_.seg_j_off[s],
                                         b.bases.data() + b.off[s0_ + s], ms_.rows.data(), ms_.row_off.data(),
                                         plan_.sc.ins, plan_.sc.del, plan_.sc.mismatch, plan_.sc.match, code_at,
                                         recs_.data() + lay_.seg_rec_off[s], n);
@@ -173,7 +193,7 @@ private:
     Plan plan_; MonomerSet ms_;
     const Batch *batch_ = nullptr; int s0_ = 0, s1_ = 0;
     CtaLayout lay_;
-    std::vector<uint32_t> codes_; std::vector<int> jcol_, arow_; std::vector<Record> recs_; std::vector<int> cnt_;
+    std::vector<uint32_t> codes_; std::vector<JR> jr_; std::vector<Record> recs_; std::vector<int> cnt_;
     bool overflowed_ = false;
 };
 

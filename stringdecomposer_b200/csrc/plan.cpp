@@ -37,9 +37,10 @@ void build_monomer_set(const std::vector<std::string> &forward, MonomerSet &ms)
 // Range proof for the packed s16x2 representation (DESIGN.md "score range").  With D=-del>=0, I=-ins>=0:
 //   live relative cells  rel in [min(s''min,0), D*(Lmax+1) + I + max(smax,0)]          (s'' = s + I + D)
 //   column shift         |delta| <= D*(Lmax+1) + I + max(|smax|,|smin|) + 1
-//   pad/dead level       s''pad = -(relmax + |s''min| + 2)
-// Every intermediate of lane_pass1/2 is (value +- 4*delta +- small), so 16 bits suffice when
-//   4*(|s''pad| + relmax + 2*dmax) + 64 <= 32767.
+//   registers are relative to Bref with |4*(B[i]-Bref)| <= SD_REBASE_TH (rebase otherwise)
+//   pad/dead level       s''pad = -(relmax + |s''min| + TH/4 + 2)
+// Every intermediate of lane_pre/post/pass2/rebase is (value +- 4*delta +- TH +- small), so 16 bits suffice when
+//   4*(|s''pad| + relmax + 2*dmax) + 2*TH + 64 <= 32767.
 // The host emulator traps any 16-bit overflow, which is how the tests keep this proof honest.
 bool packed_range_ok(const MonomerSet &ms, const Scoring &sc, int *deadz, int *pad_s)
 {
@@ -50,16 +51,16 @@ bool packed_range_ok(const MonomerSet &ms, const Scoring &sc, int *deadz, int *p
     const int64_t L = std::max(ms.Lmax, 2);
     const int64_t relmax = D * (L + 2) + I + std::max<int64_t>(smax, 0) + 2 * std::max(std::llabs(s2min), std::llabs(s2max)) + 4;
     const int64_t dmax = D * (L + 1) + I + std::max(std::llabs(smax), std::llabs(smin)) + 1;
-    const int64_t pad = relmax + std::llabs(s2min) + 2;
-    if (4 * (pad + relmax + 2 * dmax) + 64 > 32767) return false;
+    const int64_t pad = relmax + std::llabs(s2min) + SD_REBASE_TH / 4 + 2;
+    if (4 * (pad + relmax + 2 * dmax) + 2 * SD_REBASE_TH + 64 > 32767) return false;
     if (deadz) *deadz = (int)(-4 * pad + 3);
     if (pad_s) *pad_s = (int)(-pad);
     return true;
 }
 
 // Kernel instantiations compiled into the library (sweep_kernels.cu instantiates exactly this table).
-static const int kC[] = {8, 16, 24, 32, 48};
-static const int kT[] = {1, 2, 4, 8, 16, 32};
+static const int kC[] = {8, 12, 16, 20, 24, 32, 48};
+static const int kT[] = {1, 2, 4, 8, 10, 16, 32};
 bool geometry_compiled(int packed, int C, int T)
 {
     (void)packed;
@@ -122,12 +123,15 @@ Plan make_plan(const MonomerSet &ms, const Scoring &sc, int max_seg_len, int64_t
         if (C * T < ms.Lmax) continue;
         int ls = nslots * T;                        // lanes per segment
         if (ls > 1024) continue;
-        size_t prof_bytes = (size_t)5 * C * ls * 4;
+        const int qpc = (C / 4) | 1;
+        size_t prof_bytes = (size_t)5 * qpc * ls * 16;
         for (int NS = 1; NS <= 16; ++NS) {
             if (fNS && NS != fNS) continue;
+            const int spw = 32 / T;
+            int NT = (NS * nslots + spw - 1) / spw * 32;
             int lanes = NS * ls;
-            if (lanes > 1024) break;
-            int NT = (lanes + 31) / 32 * 32;
+            if (NT > 1024) break;
+            if ((int64_t)NT * (C + 72) > 65536) continue;       // register file (verified against the real kernel at configure time)
             size_t smem = prof_bytes + (size_t)NS * ((size_t)max_seg_len + 64) + 256;
             if (smem > kSmemLimit) continue;
             double util = (double)lanes / NT;
@@ -144,9 +148,10 @@ Plan make_plan(const MonomerSet &ms, const Scoring &sc, int max_seg_len, int64_t
     g.CW = (g.C + cpw - 1) / cpw;
     p.nsl = nslots * g.T;
 
-    // profile words: prof[sym][q][sl][e] = 4*s''(sym, row cell k) with k = t*C + 4q + e; pad cells get 4*pad_s.
+    // profile words: prof[sym][sl][q][e] = 4*s''(sym, row cell k) - 1 with k = t*C + 4q + e; pad cells get 4*pad_s - 1.
     const int C = g.C, T = g.T, SL = C * T;
-    p.prof.assign((size_t)5 * (C / 4) * p.nsl * 4, 0u);
+    p.qp = (C / 4) | 1;
+    p.prof.assign((size_t)5 * p.nsl * p.qp * 4, 0u);
     p.slot_len.resize(nslots); p.slot_endadd.resize(nslots);
     const int shift = -sc.ins - sc.del;
     for (int slot = 0; slot < nslots; ++slot) {
@@ -162,10 +167,10 @@ Plan make_plan(const MonomerSet &ms, const Scoring &sc, int max_seg_len, int64_t
                     lo = (ms.rows[ms.row_off[slot] + k] == sym ? sc.match : sc.mismatch) + shift;
                     if (packed) hi = (ms.rows[ms.row_off[ms.M + slot] + k] == sym ? sc.match : sc.mismatch) + shift;
                 }
-                uint32_t w = packed ? (((uint32_t)(4 * lo) & 0xffffu) | ((uint32_t)(4 * hi) << 16)) : (uint32_t)(4 * lo);
+                uint32_t w = packed ? (((uint32_t)(4 * lo - 1) & 0xffffu) | ((uint32_t)(4 * hi - 1) << 16)) : (uint32_t)(4 * lo - 1);
                 int t = pos / C, kk = pos % C, q = kk / 4, e = kk % 4;
                 int sl = slot * T + t;
-                p.prof[(((size_t)sym * (C / 4) + q) * p.nsl + sl) * 4 + e] = w;
+                p.prof[(((size_t)sym * p.nsl + sl) * p.qp + q) * 4 + e] = w;
             }
     }
     return p;

@@ -13,7 +13,12 @@
 // a 2-bit priority tag in the low bits (left/del=3 > up/ins=2 > diag=1 > jump=0), so that a plain
 // integer max reproduces the reference's traceback priority del > ins > diag > jump
 // (main.cpp:242-253) and the backpointer is (3 - tag) = reference code {0:del,1:ins,2:diag,3:jump}.
-// State registers hold Z = 4*rel + 3 ("tag-3 form").
+// State registers hold U = 4*rel + 2 ("tag-2 form": already the insertion candidate of the next column);
+// rel is relative to a per-segment reference base Bref that is moved ("rebase") only when the jump operand
+// 4*(B[i]-Bref) leaves +-SD_REBASE_TH, so no per-column renormalisation work is needed.
+// Per cell and column the sweep issues: 2 VIADDMNMX (one of them independent of J[i], so it runs before the
+// column barrier), 0.5 VIMNMX3 (lane maximum for the cross-lane scan), VIMNMX + LOP3 (deletion chain), and three
+// plain integer ops that ptxas places on the FMA pipe (IMAD.IADD / IMAD): backpointer extraction and re-tagging.
 #pragma once
 #include <stdint.h>
 
@@ -42,6 +47,7 @@ struct Packed16 {
     static constexpr int ROWS = 2;             // DP rows per slot
     static constexpr int CELLS_PER_WORD = 8;   // backpointer cells per 32-bit word (per half: 8 x 2 bit)
     static constexpr uint32_t TAGMASK = 0x00030003u;
+    static constexpr uint32_t ONE = 0x00010001u;
     static SD_HD uint32_t splat(int v) { return ((uint32_t)v & 0xffffu) | ((uint32_t)v << 16); }
     static SD_HD int lo(uint32_t a) { return (int)(int16_t)(a & 0xffffu); }
     static SD_HD int hi(uint32_t a) { return (int)(int16_t)(a >> 16); }
@@ -74,6 +80,7 @@ struct Packed16 {
 #endif
     }
     static SD_HD uint32_t tag3(uint32_t a) { return a | TAGMASK; }
+    static SD_HD uint32_t tag2(uint32_t a) { return (a | TAGMASK) ^ ONE; }     // one LOP3
 };
 
 // One DP row per 32-bit register; used when the score range does not provably fit 14+2 bits.
@@ -81,6 +88,7 @@ struct Scalar32 {
     static constexpr int ROWS = 1;
     static constexpr int CELLS_PER_WORD = 16;
     static constexpr uint32_t TAGMASK = 3u;
+    static constexpr uint32_t ONE = 1u;
     static SD_HD uint32_t splat(int v) { return (uint32_t)v; }
     static SD_HD int lo(uint32_t a) { return (int)a; }
     static SD_HD int hi(uint32_t a) { return (int)a; }
@@ -101,80 +109,97 @@ struct Scalar32 {
     }
     static SD_HD uint32_t add(uint32_t a, uint32_t b) { return a + b; }
     static SD_HD uint32_t tag3(uint32_t a) { return a | 3u; }
+    static SD_HD uint32_t tag2(uint32_t a) { return (a | 3u) ^ 1u; }
 };
 
-// Per-column uniform operands of one segment.
-struct ColumnConsts {
-    uint32_t addc_dg;   // splat(-2 - 4*delta): tag-3 form -> diag candidate (tag 1) in this column's base
-    uint32_t addc_up;   // splat(-1 - 4*delta): tag-3 form -> insertion candidate (tag 2)
-    uint32_t jump0;     // the jump operand: 0 relative to the column base.  Passed as an opaque run-time zero so
-                        // that ptxas keeps it in one register instead of materialising a packed zero per cell.
-};
+// TAGMASK and ONE as run-time register values: ptxas then folds (h | TAGMASK) ^ ONE into one three-register LOP3
+// instead of two LOP3 with an immediate each.
+struct TagRegs { uint32_t mask3, one; };
+template <class P> SD_HD TagRegs tag_regs() { TagRegs r; r.mask3 = P::TAGMASK; r.one = P::ONE; return r; }
 
-template <class P> SD_HD ColumnConsts make_column_consts(int delta, uint32_t zero)
-{
-    ColumnConsts c;
-    c.jump0 = zero;
-    c.addc_dg = P::splat(-2 - 4 * delta);
-    c.addc_up = P::splat(-1 - 4 * delta);
-    return c;
-}
+constexpr int SD_REBASE_TH = 4096;      // |4*(B[i]-Bref)| above this triggers a rebase of the lane registers
 
-// Pass 1 of a column for one lane: the three chain-free candidates of its C cells.
-//   X[kk] in : Z (tag-3 form) of the previous column          X[kk] out: m2 = max(up, diag, jump), tagged
-//   prevZ    : previous-column Z of the cell left of X[0] (the left lane's X[C-1]; DEADZ for lane 0 of a slot)
-//   prof     : C profile words 4*s'' (packed per half) for this column's read symbol, prof[kk*stride]
+// Pass 1a ("pre", independent of J[i]): X[kk] <- max(diag, up) for the lane's C cells.
+//   X[kk] in : U (tag-2 form) of the previous column        X[kk] out: max(U[k-1] + p[k], U[k])   (tags 1 / 2)
+//   prevU    : previous-column U of the cell left of X[0] (the left lane's X[C-1]; dead for lane 0 of a slot)
+//   pw       : profile words p = 4*s'' - 1 (packed per half) for this column's read symbol; pad cells very negative
 //   kill_first / kill_last: the cell is a k==0 cell -- no insertion candidate (main.cpp:194)
-//   adj_first / adj_last  : added to the profile word of X[0] / X[C-1] (column 0 only, main.cpp:173-177 vs :180)
-// Returns the lane's chain end max_k(m2[k]) in tag-3 form (what the lane hands to the lanes on its right).
 template <class P, int C>
-SD_HD uint32_t lane_pass1(uint32_t (&X)[C], uint32_t prevZ, const uint32_t *prof4, ColumnConsts cc, uint32_t deadz,
-                          bool kill_first, bool kill_last, uint32_t adj_first, uint32_t adj_last)
+SD_HD void lane_pre(uint32_t (&X)[C], uint32_t prevU, const uint32_t (&pw)[C], uint32_t deadu, bool kill_first, bool kill_last)
 {
-    uint32_t prev = prevZ;
-    uint32_t E = deadz;
+    uint32_t prev = prevU;
 #pragma unroll
     for (int kk = 0; kk < C; ++kk) {
-        uint32_t s4 = prof4[kk];
-        if (kk == 0) s4 = P::add(s4, adj_first);
-        if (kk == C - 1) s4 = P::add(s4, adj_last);
-        uint32_t m1 = P::addmax(prev, cc.addc_dg, cc.jump0);     // max(diag', jump'=0)
-        uint32_t m1s = P::add(m1, s4);
         uint32_t up = X[kk];
-        prev = up;
-        if (kk == 0 && kill_first) up = deadz;
-        if (kk == C - 1 && kill_last) up = deadz;
-        uint32_t m2 = P::addmax(up, cc.addc_up, m1s);
+        const uint32_t keep = up;
+        if (kk == 0 && kill_first) up = deadu;
+        if (kk == C - 1 && kill_last) up = deadu;
+        X[kk] = P::addmax(prev, pw[kk], up);
+        prev = keep;
+    }
+}
+
+// Pass 1b ("post"): add the jump candidate 4*(B[i]-Bref) + 4*s'' (tag 0) once J[i] is known.
+// jump0p1 = splat(4*(B[i]-Bref) + 1) (the +1 undoes the -1 folded into the profile words).
+// Returns the lane maximum in tag-2 form: what the lane hands to the lanes on its right (deletion chain).
+template <class P, int C>
+SD_HD uint32_t lane_post(uint32_t (&X)[C], const uint32_t (&pw)[C], uint32_t jump0p1, uint32_t deadu, TagRegs tr)
+{
+    uint32_t E = deadu;
+#pragma unroll
+    for (int kk = 0; kk < C; ++kk) {
+        const uint32_t m2 = P::addmax(pw[kk], jump0p1, X[kk]);
         X[kk] = m2;
         E = P::max2(E, m2);
     }
-    return P::tag3(E);
+    return (E | tr.mask3) ^ tr.one;
+}
+
+// Constant that turns the accumulated (U - h) digits of an n-cell word into the 2-bit codes (U + 1 - h).
+template <class P> constexpr uint32_t code_bias(int ncell)
+{
+    uint32_t v = 0;
+    for (int c = 0; c < ncell; ++c) v = v * 4u + 1u;
+    return v * P::ONE;
 }
 
 // Pass 2: run the deletion chain (prefix max) through the lane with the carry from the lanes on its left,
-// leave the new Z in X and emit the 2-bit backpointers (3 - tag) of the C cells.
+// leave the new U in X and emit the 2-bit backpointers (3 - tag) of the C cells.
+//   h = max(Uleft + 1, m2)      tagged winner (left has tag 3 and wins ties: main.cpp:242 comes first)
+//   U = (h | 3) ^ 1             new state, tag-2 form                 code = U + 1 - h  in {0,1,2,3}
 // Word layout: word wi holds cells [wi*CPW, wi*CPW + ncell); cell c of the word sits at bits 2*(ncell-1-c)
 // (Packed16: forward row in bits 0..15, reverse-complement row in bits 16..31).
 template <class P, int C>
-SD_HD void lane_pass2(uint32_t (&X)[C], uint32_t carryZ, uint32_t *codes)
+SD_HD void lane_pass2(uint32_t (&X)[C], uint32_t carryU, uint32_t *codes, TagRegs tr)
 {
     constexpr int CPW = P::CELLS_PER_WORD;
-    uint32_t zl = carryZ;
+    uint32_t ul = carryU;
     uint32_t w = 0;
 #pragma unroll
     for (int kk = 0; kk < C; ++kk) {
-        uint32_t h = P::max2(zl, X[kk]);
-        zl = P::tag3(h);
-        w = w * 4u + (zl - h);
-        X[kk] = zl;
-        if ((kk + 1) % CPW == 0 || kk == C - 1) { codes[kk / CPW] = w; w = 0; }
+        const uint32_t h = P::addmax(ul, tr.one, X[kk]);
+        ul = (h | tr.mask3) ^ tr.one;
+        w = w * 4u + ul - h;                     // digits in {-1..2}; biased once per word below
+        X[kk] = ul;
+        if ((kk + 1) % CPW == 0) { codes[kk / CPW] = w + code_bias<P>(CPW); w = 0; }
+        else if (kk == C - 1) { codes[kk / CPW] = w + code_bias<P>(C % CPW); w = 0; }
     }
+}
+
+// Rebase: shift every register of the lane by -shift4 (packed per half).
+template <class P, int C>
+SD_HD void lane_rebase(uint32_t (&X)[C], int shift4)
+{
+    const uint32_t d = P::splat(-shift4);
+#pragma unroll
+    for (int kk = 0; kk < C; ++kk) X[kk] = P::add(X[kk], d);
 }
 
 // Jump key of an end cell: (relative end score + (L-1)*del) * 4096 + (4095 - row): a plain integer max
 // over the keys yields max score and, on ties, the lowest row (main.cpp:212 strict '<', :230-236 first match).
 constexpr int SD_KEY_ROWS = 4096;
 SD_HD int make_key(int z_end, int endadd, int row) { return ((z_end >> 2) + endadd) * SD_KEY_ROWS + (SD_KEY_ROWS - 1 - row); }
+SD_HD int key_const(int endadd, int row) { return endadd * SD_KEY_ROWS + (SD_KEY_ROWS - 1 - row); }      // key = (u>>2)*4096 + const
 SD_HD int key_value(int key) { return key >> 12; }
 SD_HD int key_row(int key) { return SD_KEY_ROWS - 1 - (key & (SD_KEY_ROWS - 1)); }
 
@@ -192,6 +217,12 @@ struct Geometry {
 };
 
 struct Record { int32_t row, start, end, score; };
+struct JR { int32_t j, row; };      // per column i: J[i] = max_r H[i-1][r][last] and the lowest row attaining it
+
+// Lanes of a slot never straddle a warp: a warp holds 32/T whole slots (the remaining lanes idle when T does not
+// divide 32), slot instance g of the CTA lives in warp g / spw at lane (g % spw)*T + t.
+SD_HD int slots_per_warp(int T) { return 32 / T; }
+SD_HD int lane_tid(int T, int ginst, int t) { const int spw = 32 / T; return (ginst / spw) * 32 + (ginst % spw) * T + t; }
 
 // Decode the backpointer of cell k (k>=1... any k inside the row) of `row` in column i of a segment.
 // codes_col points at the first word of column i of the CTA that owns the segment.
@@ -203,30 +234,30 @@ SD_HD int fetch_code(const uint32_t *codes_col, const Geometry &g, int seg_local
     int cpw = g.packed ? 8 : 16;
     int wi = kk / cpw, c = kk - wi * cpw;
     int ncell = g.C - wi * cpw; if (ncell > cpw) ncell = cpw;
-    int tid = (seg_local * g.nslots + slot) * g.T + t;
+    int tid = lane_tid(g.T, seg_local * g.nslots + slot, t);
     uint32_t w = codes_col[(size_t)tid * g.CW + wi];
     int sh = 2 * (ncell - 1 - c) + ((g.packed && row >= g.M) ? 16 : 0);
     return (int)((w >> sh) & 3u);
 }
 
 // Traceback of one segment from the 2-bit backpointers (reference main.cpp:217-267).
-//   jcol[i], i=1..n : J[i] = max_r H[i-1][r][last]  (jcol[n] is the final score), arow[i] its lowest row.
+//   jr[i], i=1..n : J[i] = max_r H[i-1][r][last] (jr[n].j is the final score) and its lowest row.
 //   k == 0 cells are decided here from J and the two symbols involved (main.cpp:245 tests the insertion
 //   equality at k==0 although the forward pass never takes that move, main.cpp:194).
 // Records come out last-to-first (the caller reverses, main.cpp:268).  Returns the count or -1 on overflow.
 template <class CodeAt>
-SD_HD int traceback_segment(int n, const int *jcol, const int *arow, const uint8_t *seg, const uint8_t *rows,
+SD_HD int traceback_segment(int n, const JR *jr, const uint8_t *seg, const uint8_t *rows,
                             const int *row_off, int ins, int del, int mismatch, int match,
                             CodeAt code_at, Record *out, int cap)
 {
     (void)del;
     int cnt = 0;
     int i = n - 1;
-    int r = arow[n];
+    int r = jr[n].row;
     int last = row_off[r + 1] - row_off[r] - 1;
     int k = last;
     int end = i;
-    int end_score = jcol[n];
+    int end_score = jr[n].j;
     for (;;) {
         int code;
         if (k == 0) {
@@ -234,8 +265,8 @@ SD_HD int traceback_segment(int n, const int *jcol, const int *arow, const uint8
             if (i != 0) {
                 int s_here = rows[row_off[r]] == seg[i] ? match : mismatch;
                 int s_prev = rows[row_off[r]] == seg[i - 1] ? match : mismatch;
-                int h_here = jcol[i] + s_here;                               // H[i][r][0], main.cpp:191-193
-                int h_prev = (i == 1) ? s_prev : jcol[i - 1] + s_prev;       // H[i-1][r][0] (row 0: main.cpp:173-177)
+                int h_here = jr[i].j + s_here;                               // H[i][r][0], main.cpp:191-193
+                int h_prev = (i == 1) ? s_prev : jr[i - 1].j + s_prev;       // H[i-1][r][0] (row 0: main.cpp:173-177)
                 if (h_here == h_prev + ins) code = 1;
             }
         } else {
@@ -248,10 +279,10 @@ SD_HD int traceback_segment(int n, const int *jcol, const int *arow, const uint8
         Record rec;
         rec.row = r; rec.start = i; rec.end = end;
         if (i == 0) { rec.score = end_score; out[cnt++] = rec; break; }      // main.cpp:258-262
-        rec.score = end_score - jcol[i];                                      // main.cpp:253-257
+        rec.score = end_score - jr[i].j;                                      // main.cpp:253-257
         out[cnt++] = rec;
-        end_score = jcol[i];
-        r = arow[i];
+        end_score = jr[i].j;
+        r = jr[i].row;
         --i;
         last = row_off[r + 1] - row_off[r] - 1;
         k = last; end = i;

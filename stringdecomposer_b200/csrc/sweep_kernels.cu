@@ -33,132 +33,199 @@ namespace sdb {
     } while (0)
 
 struct SweepArgs {
-    const uint4 *prof; int prof_u4;
-    const uint8_t *bases; const int64_t *seg_off;      // seg_off indexed by global segment id
-    int seg_begin, nseg;                                // this launch covers segments [seg_begin, seg_begin+nseg)
+    const uint4 *prof; int prof_u4;                    // [5][nsl][qp] uint4
+    const uint8_t *bases; const int64_t *seg_off;      // seg_off indexed by segment id within the staged wave
+    int nseg;
     const int *cta_nmax; const int64_t *cta_code_off; const int64_t *seg_j_off;
-    uint32_t *codes; int *jcol; int *arow;
+    uint32_t *codes; JR *jr;
     const int *slot_len; const int *slot_endadd;
-    int nslots, M, NS, NT, CW, nsl;
+    int nslots, M, NS, NT, CW, nsl, qp;
     int ins, del, deadz;
     int seg_stride;
-    uint32_t zero;          // always 0 (see ColumnConsts::jump0)
+    int wps;                // warps per segment (FAST only, <= 4)
+    int kstride;            // ints per key buffer
+    TagRegs tr;             // TAGMASK / ONE of the policy, passed as run-time values (sweep_core.cuh: TagRegs)
 };
 
-template <class P, int C, int T>
+// Exclusive prefix max of the lane maxima over the T lanes of a slot (deletion chain carried across lanes).
+template <class P, int T>
+__device__ __forceinline__ uint32_t slot_scan(uint32_t E, int t, const int (&srcl)[T > 2 ? T - 2 : 1], uint32_t dead)
+{
+    if (T == 1) return dead;
+    uint32_t pv = __shfl_up_sync(0xffffffffu, E, 1);
+    if (t == 0) pv = dead;
+    if (T == 2) return pv;
+    if (T <= 10) {
+        // flat: every lane pulls the (already exclusive) value of each lane further left in one round of independent
+        // shuffles; lanes without such a neighbour re-read lane 0 of their slot, whose value is "dead" (harmless)
+        uint32_t acc = pv;
+#pragma unroll
+        for (int d = 1; d <= T - 2; ++d) acc = P::max2(acc, __shfl_sync(0xffffffffu, pv, srcl[d - 1]));
+        return acc;
+    }
+#pragma unroll
+    for (int d = 1; d < T; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, pv, d);
+        if (t >= d) pv = P::max2(pv, o);
+    }
+    return pv;
+}
+
+// FAST: every warp serves exactly one segment and a segment has <= 4 warps: the per-column (score,row) key is
+// reduced with CREDUX inside the warp and exchanged through one aligned int4 row of shared memory.
+// !FAST: arbitrary lane->segment mapping; keys meet in shared-memory atomicMax (three rotating buffers).
+template <class P, int C, int T, bool FAST>
 __global__ void sweep_kernel(const SweepArgs a)
 {
     extern __shared__ uint4 smem_u4[];
     uint4 *sprof = smem_u4;
-    int *skey = reinterpret_cast<int *>(sprof + a.prof_u4);             // [3][NS]
-    uint8_t *schar = reinterpret_cast<uint8_t *>(skey + 3 * a.NS + ((4 - (3 * a.NS) % 4) % 4));
+    int *skey = reinterpret_cast<int *>(sprof + a.prof_u4);             // key buffers, 16-byte aligned rows
+    const int NS = a.NS, NT = a.NT;
+    const int kstride = a.kstride;
+    uint8_t *schar = reinterpret_cast<uint8_t *>(skey + 3 * kstride);
 
     const int tid = threadIdx.x, cta = blockIdx.x;
-    const int NS = a.NS, NT = a.NT;
-    const int ginst = tid / T, t = tid % T;
+    const int warp = tid >> 5, lane = tid & 31;
+    constexpr int SPW = 32 / T;
+    const int siw = lane / T, t = lane - siw * T;
+    const bool lane_ok = siw < SPW;
+    const int ginst = warp * SPW + (lane_ok ? siw : 0);
     int seg_local = ginst / a.nslots;
-    const int slot = ginst % a.nslots;
-    const int first = cta * NS;                                         // first segment (local to this launch)
-    const bool active = seg_local < NS && first + seg_local < a.nseg;
+    const int slot = ginst - seg_local * a.nslots;
+    const int first = cta * NS;                                         // first segment of the CTA (within the launch)
+    const bool active = lane_ok && seg_local < NS && first + seg_local < a.nseg;
     if (seg_local >= NS) seg_local = 0;
     const int nmax = a.cta_nmax[cta];
     int n_seg = 0;
-    if (active) n_seg = (int)(a.seg_off[a.seg_begin + first + seg_local + 1] - a.seg_off[a.seg_begin + first + seg_local]);
+    if (active) n_seg = (int)(a.seg_off[first + seg_local + 1] - a.seg_off[first + seg_local]);
 
     // stage profile, segment symbols and keys
     for (int x = tid; x < a.prof_u4; x += NT) sprof[x] = a.prof[x];
     for (int s = 0; s < NS; ++s) {
         int n = 0; const uint8_t *src = nullptr;
         if (first + s < a.nseg) {
-            const int64_t o = a.seg_off[a.seg_begin + first + s];
-            n = (int)(a.seg_off[a.seg_begin + first + s + 1] - o);
+            const int64_t o = a.seg_off[first + s];
+            n = (int)(a.seg_off[first + s + 1] - o);
             src = a.bases + o;
         }
         for (int x = tid; x < a.seg_stride; x += NT) schar[s * a.seg_stride + x] = (x < n) ? src[x] : (uint8_t)0;
     }
-    for (int x = tid; x < 3 * NS; x += NT) skey[x] = INT_MIN;
+    for (int x = tid; x < 3 * kstride; x += NT) skey[x] = INT_MIN;
     __syncthreads();
 
-    const int sl = slot * T + t;
     const int L = a.slot_len[slot];
     const int endadd = a.slot_endadd[slot];
-    const uint32_t deadz = P::splat(a.deadz);
+    const uint32_t deadu = P::splat(a.deadz - 1);
+    const TagRegs tr = a.tr;
     const bool kill_first = (t == 0), kill_last = (t == T - 1 && L == 1);
     const bool j_writer = active && slot == 0 && t == 0;
-    int *jdst = a.jcol + (active ? a.seg_j_off[first + seg_local] : 0);
-    int *adst = a.arow + (active ? a.seg_j_off[first + seg_local] : 0);
-    uint32_t *cdst = a.codes + a.cta_code_off[cta] + (size_t)tid * a.CW;
+    const bool is_end = active && t == T - 1;
+    const int kc_lo = key_const(endadd, slot), kc_hi = key_const(endadd, a.M + slot);
+    JR *jptr = a.jr + (active ? a.seg_j_off[first + seg_local] : 0);
+    uint32_t *cptr = a.codes + a.cta_code_off[cta] + (size_t)tid * a.CW;
     const size_t cstride = (size_t)NT * a.CW;
-    const uint8_t *mychar = schar + seg_local * a.seg_stride;
-
-    uint32_t X[C];
+    const uint8_t *cp = schar + seg_local * a.seg_stride;               // symbol of the column being prepared
+    const uint4 *myprof = sprof + (size_t)(slot * T + t) * a.qp;
+    const int sym_stride = a.nsl * a.qp;
+    int srcl[T > 2 ? T - 2 : 1];
 #pragma unroll
-    for (int kk = 0; kk < C; ++kk) X[kk] = deadz;
+    for (int d = 1; d <= T - 2; ++d) srcl[d - 1] = lane - min(d, t);
+    // FAST: segment s of the CTA owns int4 row s of each key buffer, its warps write one int each
+    const int wseg = FAST ? warp / a.wps : 0;
+    int *key_wr = skey + (FAST ? wseg * 4 + (warp - wseg * a.wps) : seg_local);
+    const int *key_rd = skey + (FAST ? wseg * 4 : seg_local);
 
-    int bprev = a.ins;            // column base B[0] = ins (row-0 rule, main.cpp:180)
-    int delta = 0;
-    int kcur = 0, knext = 1, kclr = 2;    // key buffers: read / accumulate / clear
-    for (int i = 0;; ++i) {
-        if (i >= 1) {
-            const int key = skey[kcur * NS + seg_local];
-            const int vmax = key_value(key);
-            if (j_writer && i <= n_seg) { jdst[i] = vmax + bprev + (i - 1) * a.ins; adst[i] = key_row(key); }
-            delta = vmax + a.del;
-            bprev += delta;
-        }
-        if (i == nmax) break;
-        if (tid < NS) skey[kclr * NS + tid] = INT_MIN;
-
-        const int sym = mychar[i];
-        const uint4 *pp = sprof + (size_t)sym * (C / 4) * a.nsl + sl;
-        uint32_t pw[C];
+    uint32_t X[C], pw[C];
+#pragma unroll
+    for (int kk = 0; kk < C; ++kk) X[kk] = deadu;
+    auto load_profile = [&](int sym) {
+        const uint4 *pp = myprof + sym * sym_stride;
 #pragma unroll
         for (int q = 0; q < C / 4; ++q) {
-            const uint4 v = pp[(size_t)q * a.nsl];
+            const uint4 v = pp[q];
             pw[4 * q] = v.x; pw[4 * q + 1] = v.y; pw[4 * q + 2] = v.z; pw[4 * q + 3] = v.w;
         }
-        uint32_t prevZ = deadz;
-        if (T > 1) { prevZ = __shfl_up_sync(0xffffffffu, X[C - 1], 1, T); if (t == 0) prevZ = deadz; }
-        uint32_t adj_first = 0u, adj_last = 0u;
-        if (i == 0) {
-            if (t == 0 && L > 1) adj_first = P::splat(4 * a.del);
-            if (t == T - 1 && L == 1) adj_last = P::splat(4 * a.del);
-        }
-        const ColumnConsts cc = make_column_consts<P>(delta, a.zero);
-        uint32_t E = lane_pass1<P, C>(X, prevZ, pw, cc, deadz, kill_first, kill_last, adj_first, adj_last);
+    };
 
-        uint32_t carry = deadz;
-        if (T > 1) {
-            uint32_t incl = E;
-#pragma unroll
-            for (int d = 1; d < T; d <<= 1) {
-                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d, T);
-                if (t >= d) incl = P::max2(incl, o);
-            }
-            carry = __shfl_up_sync(0xffffffffu, incl, 1, T);
-            if (t == 0) carry = deadz;
-        }
-        uint32_t cw[(C + P::CELLS_PER_WORD - 1) / P::CELLS_PER_WORD];
-        lane_pass2<P, C>(X, carry, cw);
+    // column 0: everything dead, base B[0] = ins (row-0 rule, main.cpp:180); the k==0 cell is s(0,0) itself
+    // (main.cpp:173-177), i.e. one `del` more than the generic jump candidate
+    load_profile(*cp++);
+    if (t == 0 && L > 1) pw[0] = P::add(pw[0], P::splat(4 * a.del));
+    if (t == T - 1 && L == 1) pw[C - 1] = P::add(pw[C - 1], P::splat(4 * a.del));
+    lane_pre<P, C>(X, deadu, pw, deadu, kill_first, kill_last);
+    int jbase = a.ins;            // Bref + i*ins: J[i+1] = vmax + jbase
+    int jump0 = 0;                // 4*(B[i] - Bref)
+    int kb = 0;                   // key buffer in use (FAST: 2 buffers alternate; else 3 rotate)
+    int n_store = n_seg;          // columns whose backpointers are still to be written
+    int n_j = j_writer ? n_seg : 0;
+#pragma unroll 1
+    for (int i = 0; i < nmax; ++i) {
+        const uint32_t E = lane_post<P, C>(X, pw, P::splat(jump0 + 1), deadu, tr);
+        const uint32_t carry = slot_scan<P, T>(E, t, srcl, deadu);
+        constexpr int NW = (C + P::CELLS_PER_WORD - 1) / P::CELLS_PER_WORD;
+        uint32_t cw[NW];
+        lane_pass2<P, C>(X, carry, cw, tr);
 
-        if (active && i < n_seg) {
-            uint32_t *d = cdst + (size_t)i * cstride;
-            constexpr int NW = (C + P::CELLS_PER_WORD - 1) / P::CELLS_PER_WORD;
-            if (NW == 2) *reinterpret_cast<uint2 *>(d) = make_uint2(cw[0], cw[1]);
-            else if (NW == 4) *reinterpret_cast<uint4 *>(d) = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+        if (n_store > 0) {
+            if (NW == 2) *reinterpret_cast<uint2 *>(cptr) = make_uint2(cw[0], cw[1]);
+            else if (NW == 4) *reinterpret_cast<uint4 *>(cptr) = make_uint4(cw[0], cw[1], cw[2], cw[3]);
             else {
 #pragma unroll
-                for (int w = 0; w < NW; ++w) d[w] = cw[w];
+                for (int w = 0; w < NW; ++w) cptr[w] = cw[w];
             }
         }
-        if (t == T - 1 && active) {
-            const uint32_t z = X[C - 1];
-            int key = make_key(P::lo(z), endadd, slot);
-            if (P::ROWS == 2) key = max(key, make_key(P::hi(z), endadd, a.M + slot));
-            atomicMax(&skey[knext * NS + seg_local], key);
+        --n_store;
+        cptr += cstride;
+
+        // row ends -> (score,row) key of the segment: key = (u >> 2) * 4096 + (endadd * 4096 + 4095 - row)
+        const uint32_t u = X[C - 1];
+        int key;
+        if (P::ROWS == 2) {
+            const int klo = ((int)(u << 16) >> 18) * SD_KEY_ROWS + kc_lo;
+            const int khi = ((int)u >> 18) * SD_KEY_ROWS + kc_hi;
+            key = max(klo, khi);
+        } else {
+            key = ((int)u >> 2) * SD_KEY_ROWS + kc_lo;
         }
+        if (!is_end) key = INT_MIN;
+        int *kbuf = skey + kb * kstride;
+        if (FAST) {
+            const int wk = __reduce_max_sync(0xffffffffu, key);
+            if (lane == 0) key_wr[kb * kstride] = wk;
+        } else {
+            const int kclr = (kb == 0) ? 2 : kb - 1;                    // buffer read two columns ago
+            if (tid < NS) skey[kclr * kstride + tid] = INT_MIN;
+            if (is_end) atomicMax(&key_wr[kb * kstride], key);
+        }
+        (void)kbuf;
+        // J-independent half of the next column, overlapping the barrier wait (the symbol buffer is padded, so
+        // the one extra round after the last column reads a harmless 0)
+        load_profile(*cp++);
+        uint32_t prevU = deadu;
+        if (T > 1) { prevU = __shfl_up_sync(0xffffffffu, X[C - 1], 1); if (t == 0) prevU = deadu; }
+        lane_pre<P, C>(X, prevU, pw, deadu, kill_first, kill_last);
+
         __syncthreads();
-        const int tmp = kcur; kcur = knext; knext = kclr; kclr = tmp;
+        int k2;
+        if (FAST) {
+            const int4 v = *reinterpret_cast<const int4 *>(key_rd + kb * kstride);
+            k2 = max(max(v.x, v.y), max(v.z, v.w));
+            kb ^= 1;
+        } else {
+            k2 = key_rd[kb * kstride];
+            kb = (kb == 2) ? 0 : kb + 1;
+        }
+        const int vmax = k2 >> 12;
+        ++jptr;
+        if (n_j > 0) *jptr = JR{vmax + jbase, SD_KEY_ROWS - 1 - (k2 & (SD_KEY_ROWS - 1))};
+        --n_j;
+        jbase += a.ins;
+        jump0 = 4 * (vmax + a.del);
+        if (jump0 > SD_REBASE_TH || jump0 < -SD_REBASE_TH) {
+            lane_rebase<P, C>(X, jump0);
+            jbase += jump0 >> 2;
+            jump0 = 0;
+        }
     }
 }
 
@@ -166,8 +233,8 @@ __global__ void sweep_kernel(const SweepArgs a)
 struct TbArgs {
     Geometry g;
     const uint32_t *codes; const int64_t *cta_code_off;
-    const int *jcol; const int *arow; const int64_t *seg_j_off;
-    const uint8_t *bases; const int64_t *seg_off; int seg_begin, nseg;
+    const JR *jr; const int64_t *seg_j_off;
+    const uint8_t *bases; const int64_t *seg_off; int nseg;
     const uint8_t *rows; const int *row_off;
     int ins, del, mismatch, match;
     Record *scratch; const int64_t *seg_rec_off; int *counts;
@@ -179,12 +246,12 @@ __global__ void traceback_kernel(const TbArgs a)
     if (s >= a.nseg) return;
     const Geometry g = a.g;
     const int cta = s / g.NS, seg_local = s % g.NS;
-    const int64_t o = a.seg_off[a.seg_begin + s];
-    const int n = (int)(a.seg_off[a.seg_begin + s + 1] - o);
+    const int64_t o = a.seg_off[s];
+    const int n = (int)(a.seg_off[s + 1] - o);
     const uint32_t *cbase = a.codes + a.cta_code_off[cta];
     const size_t cstride = (size_t)g.NT * g.CW;
     auto code_at = [&](int i, int row, int rowlen, int k) { return fetch_code(cbase + (size_t)i * cstride, g, seg_local, row, rowlen, k); };
-    a.counts[s] = traceback_segment(n, a.jcol + a.seg_j_off[s], a.arow + a.seg_j_off[s], a.bases + o, a.rows, a.row_off,
+    a.counts[s] = traceback_segment(n, a.jr + a.seg_j_off[s], a.bases + o, a.rows, a.row_off,
                                     a.ins, a.del, a.mismatch, a.match, code_at, a.scratch + a.seg_rec_off[s], n);
 }
 
@@ -222,23 +289,26 @@ template <int MODE> __global__ void int_peak_kernel(unsigned *out, unsigned seed
 }
 
 // ---------------------------------------------------------------------------------------------
-template <class P, int C> static const void *kern_t(int T)
+template <class P, int C, bool F> static const void *kern_t(int T)
 {
     switch (T) {
-    case 1: return (const void *)sweep_kernel<P, C, 1>; case 2: return (const void *)sweep_kernel<P, C, 2>;
-    case 4: return (const void *)sweep_kernel<P, C, 4>; case 8: return (const void *)sweep_kernel<P, C, 8>;
-    case 16: return (const void *)sweep_kernel<P, C, 16>; case 32: return (const void *)sweep_kernel<P, C, 32>;
+    case 1: return (const void *)sweep_kernel<P, C, 1, F>; case 2: return (const void *)sweep_kernel<P, C, 2, F>;
+    case 4: return (const void *)sweep_kernel<P, C, 4, F>; case 8: return (const void *)sweep_kernel<P, C, 8, F>;
+    case 10: return (const void *)sweep_kernel<P, C, 10, F>;
+    case 16: return (const void *)sweep_kernel<P, C, 16, F>; case 32: return (const void *)sweep_kernel<P, C, 32, F>;
     }
     return nullptr;
 }
-template <class P> static const void *kern(int C, int T)
+template <class P, bool F> static const void *kern_c(int C, int T)
 {
     switch (C) {
-    case 8: return kern_t<P, 8>(T); case 16: return kern_t<P, 16>(T); case 24: return kern_t<P, 24>(T);
-    case 32: return kern_t<P, 32>(T); case 48: return kern_t<P, 48>(T);
+    case 8: return kern_t<P, 8, F>(T); case 12: return kern_t<P, 12, F>(T); case 16: return kern_t<P, 16, F>(T);
+    case 20: return kern_t<P, 20, F>(T); case 24: return kern_t<P, 24, F>(T); case 32: return kern_t<P, 32, F>(T);
+    case 48: return kern_t<P, 48, F>(T);
     }
     return nullptr;
 }
+template <class P> static const void *kern(int C, int T, bool fast) { return fast ? kern_c<P, true>(C, T) : kern_c<P, false>(C, T); }
 
 namespace {
 
@@ -280,7 +350,9 @@ public:
         SD_CUDA(cudaSetDevice(dev_));
         plan_ = p; ms_ = ms;
         const Geometry &g = p.g;
-        kernel_ = g.packed ? kern<Packed16>(g.C, g.T) : kern<Scalar32>(g.C, g.T);
+        const int spw = 32 / g.T;
+        fast_ = (g.nslots % spw == 0) && (g.nslots / spw <= 4);
+        kernel_ = g.packed ? kern<Packed16>(g.C, g.T, fast_) : kern<Scalar32>(g.C, g.T, fast_);
         if (!kernel_) throw PlanError{"no sweep kernel compiled for this geometry"};
         cudaFuncAttributes fa;
         SD_CUDA(cudaFuncGetAttributes(&fa, kernel_));
@@ -328,7 +400,7 @@ public:
         d_ctanmax_.need(lay_.cta_nmax.size() * 4); d_ctacode_.need(lay_.cta_code_off.size() * 8);
         d_segj_.need(lay_.seg_j_off.size() * 8); d_segrec_.need(lay_.seg_rec_off.size() * 8);
         d_codes_.need((size_t)lay_.cta_code_off.back() * 4 + 16);
-        d_jcol_.need((size_t)lay_.seg_j_off.back() * 4 + 16); d_arow_.need((size_t)lay_.seg_j_off.back() * 4 + 16);
+        d_jr_.need((size_t)lay_.seg_j_off.back() * sizeof(JR) + 16);
         d_scratch_.need((size_t)lay_.seg_rec_off.back() * sizeof(Record) + 16);
         d_counts_.need((size_t)nseg_ * 4 + 16); d_outoff_.need(((size_t)nseg_ + 1) * 8);
         SD_CUDA(cudaEventRecord(ev_[0], st_));
@@ -353,14 +425,19 @@ public:
         SweepArgs a;
         a.prof = d_prof_.as<uint4>(); a.prof_u4 = (int)(plan_.prof.size() / 4);
         a.bases = d_bases_.as<uint8_t>(); a.seg_off = d_segoff_.as<int64_t>();
-        a.seg_begin = 0; a.nseg = nseg_;
+        a.nseg = nseg_;
         a.cta_nmax = d_ctanmax_.as<int>(); a.cta_code_off = d_ctacode_.as<int64_t>(); a.seg_j_off = d_segj_.as<int64_t>();
-        a.codes = d_codes_.as<uint32_t>(); a.jcol = d_jcol_.as<int>(); a.arow = d_arow_.as<int>();
+        a.codes = d_codes_.as<uint32_t>(); a.jr = d_jr_.as<JR>();
         a.slot_len = d_slotlen_.as<int>(); a.slot_endadd = d_slotend_.as<int>();
-        a.nslots = g.nslots; a.M = g.M; a.NS = g.NS; a.NT = g.NT; a.CW = g.CW; a.nsl = plan_.nsl;
+        a.nslots = g.nslots; a.M = g.M; a.NS = g.NS; a.NT = g.NT; a.CW = g.CW; a.nsl = plan_.nsl; a.qp = plan_.qp;
         a.ins = plan_.sc.ins; a.del = plan_.sc.del; a.deadz = plan_.deadz;
-        a.seg_stride = (nmax_ + 16) / 16 * 16; a.zero = 0u;
-        const size_t smem = plan_.prof.size() * 4 + ((size_t)3 * g.NS + 4) * 4 + (size_t)g.NS * a.seg_stride;
+        a.seg_stride = (nmax_ + 16) / 16 * 16;
+        const int spw = 32 / g.T;
+        a.wps = fast_ ? g.nslots / spw : 1;
+        a.kstride = fast_ ? g.NS * 4 : (g.NS + 3) / 4 * 4;
+        a.tr = g.packed ? tag_regs<Packed16>() : tag_regs<Scalar32>();
+        const int kstride = a.kstride;
+        const size_t smem = plan_.prof.size() * 4 + (size_t)3 * kstride * 4 + (size_t)g.NS * a.seg_stride;
         if (smem > (size_t)prop_.sharedMemPerBlockOptin) throw PlanError{"sweep geometry needs more shared memory than the SM has"};
         SD_CUDA(cudaFuncSetAttribute(kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int nctas = (int)lay_.cta_nmax.size();
@@ -369,8 +446,8 @@ public:
         SD_CUDA(cudaLaunchKernel(kernel_, dim3(nctas), dim3(g.NT), args, smem, st_));
         SD_CUDA(cudaEventRecord(ev_[1], st_));
         TbArgs t;
-        t.g = g; t.codes = a.codes; t.cta_code_off = a.cta_code_off; t.jcol = a.jcol; t.arow = a.arow; t.seg_j_off = a.seg_j_off;
-        t.bases = a.bases; t.seg_off = a.seg_off; t.seg_begin = 0; t.nseg = nseg_;
+        t.g = g; t.codes = a.codes; t.cta_code_off = a.cta_code_off; t.jr = a.jr; t.seg_j_off = a.seg_j_off;
+        t.bases = a.bases; t.seg_off = a.seg_off; t.nseg = nseg_;
         t.rows = d_rows_.as<uint8_t>(); t.row_off = d_rowoff_.as<int>();
         t.ins = plan_.sc.ins; t.del = plan_.sc.del; t.mismatch = plan_.sc.mismatch; t.match = plan_.sc.match;
         t.scratch = d_scratch_.as<Record>(); t.seg_rec_off = d_segrec_.as<int64_t>(); t.counts = d_counts_.as<int>();
@@ -420,13 +497,14 @@ private:
     cudaDeviceProp prop_{};
     Plan plan_; MonomerSet ms_;
     const void *kernel_ = nullptr;
+    bool fast_ = false;
     CtaLayout lay_;
     int s0_ = 0, s1_ = 0, nseg_ = 0, nmax_ = 0;
     std::vector<int64_t> hoff_, houtoff_;
     std::vector<int> hcnt_;
     DevBuf d_prof_, d_slotlen_, d_slotend_, d_rows_, d_rowoff_;
     DevBuf d_bases_, d_segoff_, d_ctanmax_, d_ctacode_, d_segj_, d_segrec_;
-    DevBuf d_codes_, d_jcol_, d_arow_, d_scratch_, d_counts_, d_outoff_, d_dense_;
+    DevBuf d_codes_, d_jr_, d_scratch_, d_counts_, d_outoff_, d_dense_;
 };
 
 } // namespace

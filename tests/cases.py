@@ -1,0 +1,42 @@
+"""Helpers shared by the test modules: golden-case loading and running dp-compatible binaries."""
+import json
+import os
+import subprocess
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLDEN = os.path.join(HERE, "golden")
+DP_CUDA = os.path.join(ROOT, "stringdecomposer_b200", "build", "bin", "dp")
+DP_EMU = os.path.join(ROOT, "stringdecomposer_b200", "build", "bin", "dp_emu")
+DP_ORACLE = os.path.join(ROOT, "oracle", "_build", "oracle_dp")
+DP_REF = os.path.join(ROOT, "oracle", "_ref", "dp")
+
+
+def load_cases():
+    with open(os.path.join(GOLDEN, "edge_cases.json")) as f:
+        return json.load(f)["cases"]
+
+
+def run_case(binary, case, env=None):
+    """-> (status, stdout, stderr) of `binary` on a golden case, temp paths stripped from stderr."""
+    e = dict(os.environ)
+    e.update(env or {})
+    with tempfile.TemporaryDirectory() as td:
+        if case.get("argv_raw") is not None:
+            p = subprocess.run([binary] + case["argv_raw"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=e)
+        else:
+            rp, mp = os.path.join(td, "reads.fa"), os.path.join(td, "monomers.fa")
+            open(rp, "w", newline="").write(case["reads_fa"])
+            open(mp, "w", newline="").write(case["monomers_fa"])
+            p = subprocess.run([binary, rp, mp] + case["argv_tail"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, cwd=td, env=e)
+        return p.returncode, p.stdout.decode(), p.stderr.decode().replace(td + "/", "")
+
+
+def check_case(binary, case, env=None, check_stderr=True):
+    st, out, err = run_case(binary, case, env)
+    assert st == case["status"], "%s: status %d != %d\n%s" % (case["name"], st, case["status"], err[-400:])
+    assert out == case["stdout"], "%s: raw TSV differs from the reference" % case["name"]
+    if check_stderr:
+        keep = [ln for ln in err.splitlines() if not ln.startswith("[sd_b200]")]
+        assert keep == case["stderr"].splitlines(), "%s: stderr differs:\n%s\n--- expected\n%s" % (case["name"], err, case["stderr"])

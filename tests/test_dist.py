@@ -1,0 +1,66 @@
+"""world_size-2 gloo test of the multi-GPU plumbing bench.py uses: every rank decomposes its own shard (no collective on
+the data path), timing is reduced with MAX and work with SUM.  Runs on CPU with the host emulator as the device."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import cases
+
+WORKER = textwrap.dedent("""
+    import os, sys, json
+    sys.path.insert(0, %r); sys.path.insert(0, %r)
+    import torch, torch.distributed as dist
+    import numpy as np
+    dist.init_process_group("gloo")
+    rank, ws = dist.get_rank(), dist.get_world_size()
+    from stringdecomposer_b200 import synth, Decomposer
+    from stringdecomposer_b200.hostpipe import segment_reads
+    import sd_oracle
+    names, mons = synth.load_dxz1()
+    arr = synth.hor_array(mons, 6000, 0.02, seed=40)          # same array everywhere; ranks take alternating shards
+    segs, where = segment_reads([arr], 1000, 300, flavour="emu")
+    mine = [s for i, s in enumerate(segs) if i %% ws == rank]
+    d = Decomposer(mons, flavour="emu")
+    recs, off = d.decompose(mine)
+    ok = 1
+    for j, s in enumerate(mine):
+        want = sd_oracle.align_segment(s, mons)
+        got = [(int(r["row"]), int(r["start"]), int(r["end"]), float(r["score"])) for r in recs[off[j]:off[j+1]]]
+        ok &= int(got == want)
+    t = torch.tensor([float(rank + 1)], dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    c = torch.tensor([float(len(mine)), float(ok)], dtype=torch.float64); dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    dist.barrier()
+    if rank == 0:
+        print(json.dumps({"max": t.item(), "segments": c[0].item(), "ok": c[1].item(), "total": len(segs)}))
+    dist.destroy_process_group()
+""")
+
+
+def test_two_rank_sharding_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % (cases.ROOT, os.path.join(cases.ROOT, "oracle")))
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29517", str(script)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+    assert p.returncode == 0, p.stderr.decode()[-2000:]
+    import json
+    line = [ln for ln in p.stdout.decode().splitlines() if ln.startswith("{")][-1]
+    d = json.loads(line)
+    assert d["max"] == 2.0 and d["ok"] == 2.0 and d["segments"] == d["total"]
+
+
+def test_multi_device_engine_split_is_exact():
+    # the in-library multi-device path (SD_DEVICES) partitions segments contiguously; with the emulator there is one
+    # backend, so check the split arithmetic through the public segment API instead: concatenated shards == whole
+    from stringdecomposer_b200 import synth, Decomposer
+    names, mons = synth.load_dxz1()
+    arr = synth.hor_array(mons, 5000, 0.02, seed=41)
+    from stringdecomposer_b200.hostpipe import segment_reads
+    segs, _ = segment_reads([arr], 700, 200, flavour="emu")
+    d = Decomposer(mons, flavour="emu")
+    whole, woff = d.decompose(segs)
+    a, aoff = d.decompose(segs[:3])
+    b, boff = d.decompose(segs[3:])
+    import numpy as np
+    assert (np.concatenate([a, b]) == whole).all()
+    assert list(aoff) + [int(x) + int(aoff[-1]) for x in boff[1:]] == list(woff)

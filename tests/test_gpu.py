@@ -1,0 +1,175 @@
+"""GPU parity tests (run on the B200 box with -m gpu).  Everything goes through the C ABI (libsd_b200.so) or the
+drop-in dp binary; the oracle is only the checker."""
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import cases
+import sd_oracle
+from stringdecomposer_b200 import synth, Decomposer, decompose_reads, device_count, int_peak
+from stringdecomposer_b200.hostpipe import segment_reads
+
+pytestmark = pytest.mark.gpu
+
+
+def as_tuples(recs):
+    return [(int(r["row"]), int(r["start"]), int(r["end"]), float(r["score"])) for r in recs]
+
+
+def test_native_library_is_the_one_running():
+    d = Decomposer(["ACGTACGTAC"], devices=[0])
+    recs, off = d.decompose(["ACGTACGTACGGTACGTAC"])
+    st = d.stats()
+    assert st["launches"] >= 2 and st["n_devices"] == 1 and st["cells"] == 19 * 20
+    maps = open("/proc/self/maps").read()
+    assert "libsd_b200.so" in maps and "libsd_emu.so" not in maps
+
+
+@pytest.mark.parametrize("scoring,fixture", [(None, "config1_raw_default.tsv"), ((-2, -2, -3, 1), "config1_raw_s-2-2-3+1.tsv")])
+def test_config1_golden_through_dp_binary(scoring, fixture):
+    st, out, err = sd_oracle.run_cli(cases.DP_CUDA, os.path.join(cases.GOLDEN, "config1_read.fa"),
+                                     os.path.join(cases.GOLDEN, "DXZ1_star_monomers.fa"), scoring=scoring)
+    assert st == 0, err
+    assert out == open(os.path.join(cases.GOLDEN, fixture), "rb").read()
+    if scoring is None:
+        got = ["\t".join(ln.split("\t")[:4]) for ln in out.decode().splitlines()]
+        assert got == open(os.path.join(cases.GOLDEN, "config1_cols1-4.tsv")).read().splitlines()
+
+
+@pytest.mark.parametrize("case", cases.load_cases(), ids=lambda c: c["name"])
+def test_edge_cases_through_dp_binary(case):
+    cases.check_case(cases.DP_CUDA, case)
+
+
+@pytest.mark.parametrize("geom", ["8,32,1", "16,16,1", "24,8,1", "24,8,2", "32,8,1", "48,4,2", "48,4,3", "16,16,2", "20,10,1", "20,10,2", "12,16,1"])
+@pytest.mark.parametrize("force32", ["0", "1"])
+def test_every_geometry_and_both_widths(geom, force32):
+    picked = [c for c in cases.load_cases() if c["name"] in ("multi_read", "scoring_-3_-2_-4_2", "N_in_monomer", "dup_monomers_rev",
+                                                             "len_5501_default")]
+    for case in picked:
+        cases.check_case(cases.DP_CUDA, case, env={"SD_GEOM": geom, "SD_FORCE_S32": force32})
+
+
+@pytest.mark.parametrize("geom", ["8,1,4", "8,2,2", "16,1,1", "24,1,2", "32,2,1", "48,1,1", "8,4,3", "48,32,1"])
+def test_small_and_large_slots(geom):
+    C, T, _ = map(int, geom.split(","))
+    for seed in range(4):
+        rn, rr, mn, mm = synth.random_case(300 + seed, mono_len=(1, min(C * T, 700)), read_len=(1, 500), n_monomers=(1, 5))
+        want = sd_oracle.decompose_reads(rn, rr, mn, mm, part_size=150, overlap=40)
+        os.environ["SD_GEOM"] = geom
+        try:
+            got = decompose_reads(rn, rr, mn, mm, part_size=150, overlap=40)
+        finally:
+            del os.environ["SD_GEOM"]
+        assert got == want
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_fuzz_against_oracle(seed):
+    al = ["A", "AT", "AC", "ACGT", "ACGTN"][seed % 5]
+    scorings = [(-1, -1, -1, 1), (-2, -2, -3, 1), (-3, -2, -4, 2), (0, -1, -1, 1), (-1, 0, -2, 2), (-4, -1, -1, 1), (-1, -4, -1, 2),
+                (-9, -30, -9, 2), (1, -1, -1, 1)]
+    sc = scorings[seed % len(scorings)]
+    part, ov = [(50, 10), (120, 30), (300, 100), (5000, 500)][seed % 4]
+    rn, rr, mn, mm = synth.random_case(5000 + seed, alphabet=al, mono_len=(1, 200), read_len=(1, 1500))
+    want = sd_oracle.decompose_reads(rn, rr, mn, mm, part_size=part, overlap=ov, scoring=sc)
+    got = decompose_reads(rn, rr, mn, mm, part_size=part, overlap=ov, scoring=sc)
+    assert got == want
+
+
+def test_segment_records_and_staged_api():
+    names, mons = synth.load_dxz1()
+    arr = synth.hor_array(mons, 20000, 0.04, seed=21)
+    segs, _ = segment_reads([arr], 1500, 300)
+    d = Decomposer(mons, devices=[0])
+    recs, off = d.decompose(segs)
+    for j in (0, 3, len(segs) - 1):
+        assert as_tuples(recs[off[j]:off[j + 1]]) == sd_oracle.align_segment(segs[j], mons)
+    d.stage(segs)
+    ms = d.run_staged()
+    ms2 = d.run_staged()
+    r2, o2 = d.fetch_staged()
+    assert ms > 0 and ms2 > 0 and (r2 == recs).all() and (o2 == off).all()
+    d.close()
+
+
+def test_waves_do_not_change_the_result():
+    rn, rr, mn, mm = synth.random_case(77, read_len=(2000, 3000), n_reads=(3, 3))
+    want = sd_oracle.decompose_reads(rn, rr, mn, mm, part_size=300, overlap=100)
+    os.environ["SD_WAVE_BYTES"] = "300000"
+    try:
+        got = decompose_reads(rn, rr, mn, mm, part_size=300, overlap=100)
+    finally:
+        del os.environ["SD_WAVE_BYTES"]
+    assert got == want
+
+
+def test_score_width_switch_on_device():
+    names, mons = synth.load_dxz1()
+    seg = synth.hor_array(mons, 3000, 0.05, seed=9)
+    for sc, packed in (((-1, -1, -1, 1), 1), ((-2, -2, -3, 1), 1), ((-9, -30, -9, 2), 0), ((1, -1, -1, 1), 0)):
+        d = Decomposer(mons, *sc, devices=[0])
+        recs, off = d.decompose([seg])
+        assert d.stats()["packed"] == packed
+        assert as_tuples(recs) == sd_oracle.align_segment(seg, mons, sc)
+        d.close()
+
+
+def test_config2_full_size_properties_and_sampled_parity():
+    # BASELINE config 2 at full size: 2 Mb array, 400 segments.  Size-independent properties on every segment,
+    # oracle parity on a sample (the oracle needs ~0.2 s and 180 MB per segment).
+    rn, reads, mn, mons = synth.config2()
+    segs, where = segment_reads(reads, 5000, 500)
+    assert len(segs) == 400
+    d = Decomposer(mons, devices=[0])
+    recs, off = d.decompose(segs)
+    recs2, off2 = d.decompose(segs)
+    assert (recs == recs2).all() and (off == off2).all()              # deterministic
+    R = 2 * len(mons)
+    for j, s in enumerate(segs):
+        r = recs[off[j]:off[j + 1]]
+        assert len(r) > 0 and r["start"][0] == 0 and r["end"][-1] == len(s) - 1
+        assert (r["start"][1:] == r["end"][:-1] + 1).all()           # alignments tile the segment
+        assert (r["row"] >= 0).all() and (r["row"] < R).all()
+        assert (r["start"] <= r["end"]).all()
+    for j in (0, 57, 199, 311, 399):
+        want = sd_oracle.align_segment(segs[j], mons)
+        assert as_tuples(recs[off[j]:off[j + 1]]) == want
+        # the segment scores telescope to the best final score (main.cpp:253-257)
+        assert sum(w[3] for w in want) == float(recs[off[j]:off[j + 1]]["score"].sum())
+    st = d.stats()
+    assert st["cells"] == 2 * sum(len(s) for s in segs) * 2 * sum(len(m) for m in mons)
+    d.close()
+
+
+def test_config4_custom_scoring_sample():
+    rn, reads, mn, mons = synth.config4(n_reads=6, read_len=15000)
+    sc = (-2, -2, -3, 1)
+    want = sd_oracle.decompose_reads(rn, reads, mn, mons, scoring=sc)
+    assert decompose_reads(rn, reads, mn, mons, scoring=sc) == want
+    # part 20000 leaves the proven s16 range for this scoring -> s32 sweep, same answer as the oracle
+    want = sd_oracle.decompose_reads(rn[:2], reads[:2], mn, mons, part_size=20000, overlap=500, scoring=sc)
+    assert decompose_reads(rn[:2], reads[:2], mn, mons, part_size=20000, overlap=500, scoring=sc) == want
+
+
+def test_config3_noisy_reads_sample():
+    rn, reads, mn, mons = synth.config3(n_reads=3, read_len=30000)
+    want = sd_oracle.decompose_reads(rn, reads, mn, mons)
+    assert decompose_reads(rn, reads, mn, mons) == want
+
+
+def test_multi_gpu_output_identical():
+    if device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    rn, reads, mn, mons = synth.config3(n_reads=4, read_len=30000)
+    one = decompose_reads(rn, reads, mn, mons, devices=[0])
+    allg = decompose_reads(rn, reads, mn, mons, devices="all")
+    assert one == allg
+
+
+def test_int_peak_probe():
+    alu, both, mhz = int_peak(0)
+    assert 5e12 < alu < 4e13 and both >= alu * 0.9 and 500 < mhz < 2500

@@ -1,0 +1,137 @@
+"""CPU suite for the host side of the product: the C ABI surface, segmentation / overlap resolution / FASTA
+contract, and the kernel algebra run through the host emulator (libsd_emu.so -- the same per-lane functions the
+sm_100a kernels execute) against the oracle.  No CUDA compute happens here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import cases
+import sd_oracle
+from stringdecomposer_b200 import _lib, synth, Decomposer, SdError, decompose_reads, segment_read, postprocess, RECORD_DTYPE
+
+
+def test_cuda_library_loads_and_exports_every_declared_symbol():
+    hdr = open(os.path.join(cases.ROOT, "include", "sd_b200.h")).read()
+    declared = set(re.findall(r"\b(sd_[a-z_]+)\s*\(", hdr))
+    assert declared == set(_lib.SYMBOLS)
+    lib = ctypes.CDLL(_lib.library_path("cuda"))
+    for s in declared:
+        assert hasattr(lib, s), s
+    assert b"sm_100a" in ctypes.cast(_lib.load_library("cuda").sd_version(), ctypes.c_char_p).value \
+        if False else True
+    assert "sm_100a" in _lib.load_library("cuda").sd_version().decode()
+
+
+def test_product_library_has_no_cpu_path():
+    # without a GPU the CUDA library must refuse, not fall back
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(SdError) as e:
+        Decomposer(["ACGT"], flavour="cuda")
+    assert e.value.status == 2
+    import subprocess
+    p = subprocess.run([cases.DP_CUDA, os.path.join(cases.GOLDEN, "config1_read.fa"), os.path.join(cases.GOLDEN, "DXZ1_star_monomers.fa"),
+                        "1", "5000", "500"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert p.returncode != 0 and p.stdout == b"" and b"no CUDA device" in p.stderr
+
+
+@pytest.mark.parametrize("L,part,ov", [(1, 1000, 300), (299, 1000, 300), (300, 1000, 300), (1299, 1000, 300), (1300, 1000, 300),
+                                       (1301, 1000, 300), (94871, 5000, 500), (5499, 5000, 500), (5500, 5000, 500), (5501, 5000, 500),
+                                       (10000, 5000, 500), (700, 700, 50), (20000, 20000, 500), (123456, 777, 1000)])
+def test_segmentation_matches_oracle(L, part, ov):
+    assert segment_read(L, part, ov, flavour="emu") == sd_oracle.segment_read(L, part, ov)
+    assert segment_read(L, part, ov, flavour="cuda") == sd_oracle.segment_read(L, part, ov)
+
+
+def test_postprocess_matches_oracle():
+    rng = np.random.default_rng(3)
+    for trial in range(200):
+        n = int(rng.integers(0, 40))
+        starts = np.sort(rng.integers(0, 3000, n))
+        recs = np.zeros(n, dtype=RECORD_DTYPE)
+        recs["start"] = starts
+        recs["end"] = starts + rng.integers(0, 400, n)
+        recs["row"] = rng.integers(0, 24, n)
+        recs["score"] = rng.integers(-50, 200, n)
+        got = postprocess(recs, flavour="emu")
+        want = sd_oracle.postprocess([(int(r["row"]), int(r["start"]), int(r["end"]), float(r["score"])) for r in recs])
+        assert [(int(r["row"]), int(r["start"]), int(r["end"]), float(r["score"])) for r in got] == want
+
+
+@pytest.mark.parametrize("case", cases.load_cases(), ids=lambda c: c["name"])
+def test_emulated_kernels_match_reference_on_edge_cases(case):
+    cases.check_case(cases.DP_EMU, case)
+
+
+@pytest.mark.parametrize("geom", ["8,32,1", "16,16,1", "24,8,1", "24,8,2", "32,8,1", "48,4,2", "48,4,3", "20,10,1", "20,10,2", "12,16,1"])
+@pytest.mark.parametrize("force32", ["0", "1"])
+def test_emulated_kernels_every_geometry(geom, force32):
+    # same answer whatever the lane layout, packed s16x2 and s32 (the emulator traps 16-bit overflow)
+    picked = [c for c in cases.load_cases() if c["name"] in ("multi_read", "scoring_-3_-2_-4_2", "N_in_monomer", "dup_monomers_rev")]
+    for case in picked:
+        cases.check_case(cases.DP_EMU, case, env={"SD_GEOM": geom, "SD_FORCE_S32": force32})
+
+
+@pytest.mark.parametrize("geom", ["8,1,4", "8,2,2", "16,1,1", "24,1,2", "32,2,1", "48,1,1", "8,4,3", "12,10,2", "20,2,5"])
+def test_emulated_kernels_small_slots(geom):
+    C, T, _ = map(int, geom.split(","))
+    for seed in range(6):
+        rn, rr, mn, mm = synth.random_case(200 + seed, mono_len=(1, C * T), read_len=(1, 400))
+        want = sd_oracle.decompose_reads(rn, rr, mn, mm, part_size=150, overlap=40)
+        os.environ["SD_GEOM"] = geom
+        try:
+            got = decompose_reads(rn, rr, mn, mm, part_size=150, overlap=40, flavour="emu")
+        finally:
+            del os.environ["SD_GEOM"]
+        assert got == want
+
+
+def test_emulated_config1_full_golden():
+    st, out, err = sd_oracle.run_cli(cases.DP_EMU, os.path.join(cases.GOLDEN, "config1_read.fa"),
+                                     os.path.join(cases.GOLDEN, "DXZ1_star_monomers.fa"))
+    assert st == 0
+    assert out == open(os.path.join(cases.GOLDEN, "config1_raw_default.tsv"), "rb").read()
+
+
+def test_waves_do_not_change_the_result():
+    rn, rr, mn, mm = synth.random_case(77, read_len=(2000, 3000), n_reads=(3, 3))
+    want = sd_oracle.decompose_reads(rn, rr, mn, mm, part_size=300, overlap=100)
+    os.environ["SD_WAVE_BYTES"] = "200000"
+    try:
+        got = decompose_reads(rn, rr, mn, mm, part_size=300, overlap=100, flavour="emu")
+    finally:
+        del os.environ["SD_WAVE_BYTES"]
+    assert got == want
+
+
+def test_score_range_switch():
+    # wide penalties must leave the packed s16x2 domain and still be exact (the emulator traps overflow)
+    names, mons = synth.load_dxz1()
+    seg = synth.hor_array(mons, 1500, 0.05, seed=9)
+    for sc, packed in (((-1, -1, -1, 1), 1), ((-2, -2, -3, 1), 1), ((-9, -30, -9, 2), 0), ((1, -1, -1, 1), 0)):
+        d = Decomposer(mons, *sc, flavour="emu")
+        recs, off = d.decompose([seg])
+        assert d.stats()["packed"] == packed
+        want = sd_oracle.align_segment(seg, mons, sc)
+        assert [(int(r["row"]), int(r["start"]), int(r["end"]), float(r["score"])) for r in recs] == want
+        d.close()
+
+
+def test_unsupported_inputs_fail_loudly():
+    with pytest.raises(SdError):
+        Decomposer(["ACGU"], flavour="emu")
+    d = Decomposer(["ACGT"], flavour="emu")
+    with pytest.raises(SdError):
+        d.decompose(["ACGTX"])
+    with pytest.raises(SdError):
+        d.decompose(["ACGT", ""])
+    d.close()
+    # ed_thr pre-filter is not built: the CLI must refuse instead of silently running the unfiltered DP
+    case = dict(cases.load_cases()[0])
+    case["argv_tail"] = ["1", "1000", "300", "-1", "-1", "-1", "1", "5"]
+    st, out, err = cases.run_case(cases.DP_EMU, case)
+    assert st != 0 and out == "" and "ed_thr" in err
