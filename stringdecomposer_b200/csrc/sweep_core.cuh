@@ -248,7 +248,7 @@ SD_HD int fetch_code(const uint32_t *codes_col, const Geometry &g, int seg_local
 template <class CodeAt>
 SD_HD int traceback_segment(int n, const JR *jr, const uint8_t *seg, const uint8_t *rows,
                             const int *row_off, int ins, int del, int mismatch, int match,
-                            CodeAt code_at, Record *out, int cap)
+                            CodeAt code_at, Record *out, int cap, bool writer = true)
 {
     (void)del;
     int cnt = 0;
@@ -278,9 +278,10 @@ SD_HD int traceback_segment(int n, const JR *jr, const uint8_t *seg, const uint8
         if (cnt >= cap) return -1;
         Record rec;
         rec.row = r; rec.start = i; rec.end = end;
-        if (i == 0) { rec.score = end_score; out[cnt++] = rec; break; }      // main.cpp:258-262
+        if (i == 0) { rec.score = end_score; if (writer) out[cnt] = rec; ++cnt; break; }      // main.cpp:258-262
         rec.score = end_score - jr[i].j;                                      // main.cpp:253-257
-        out[cnt++] = rec;
+        if (writer) out[cnt] = rec;
+        ++cnt;
         end_score = jr[i].j;
         r = jr[i].row;
         --i;

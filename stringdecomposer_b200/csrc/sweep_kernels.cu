@@ -238,21 +238,122 @@ struct TbArgs {
     const uint8_t *rows; const int *row_off;
     int ins, del, mismatch, match;
     Record *scratch; const int64_t *seg_rec_off; int *counts;
+    int invC;               // ceil(65536 / C): pos / C == (pos * invC) >> 16 for every pos < C*T (checked on the host)
 };
 
-__global__ void traceback_kernel(const TbArgs a)
+// Warp-cooperative traceback (reference main.cpp:217-267 through the 2-bit backpointers; same state machine as
+// sweep_core.cuh: traceback_segment, which the host emulator runs).
+// One warp per segment.  Lane d of the warp owns column i0-d of a 32-column window and keeps, in registers, the
+// three consecutive backpointer words around the cell the diagonal through the current position predicts.  Every
+// round all lanes decode "their" cell on that diagonal at once; a ballot finds the first column whose move is not
+// diagonal, the walk jumps over the whole diagonal run, and only the odd move (deletion, insertion, close, k==0)
+// is handled serially.  The window is refilled (one HBM round trip) when the path leaves it.
+constexpr int TB_WARPS = 4;
+__global__ void __launch_bounds__(TB_WARPS * 32) traceback_kernel(const TbArgs a)
 {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = blockIdx.x * TB_WARPS + (threadIdx.x >> 5);
     if (s >= a.nseg) return;
+    const int lane = threadIdx.x & 31;
     const Geometry g = a.g;
     const int cta = s / g.NS, seg_local = s % g.NS;
     const int64_t o = a.seg_off[s];
     const int n = (int)(a.seg_off[s + 1] - o);
+    const uint8_t *seg = a.bases + o;
+    const JR *jr = a.jr + a.seg_j_off[s];
     const uint32_t *cbase = a.codes + a.cta_code_off[cta];
     const size_t cstride = (size_t)g.NT * g.CW;
-    auto code_at = [&](int i, int row, int rowlen, int k) { return fetch_code(cbase + (size_t)i * cstride, g, seg_local, row, rowlen, k); };
-    a.counts[s] = traceback_segment(n, a.jr + a.seg_j_off[s], a.bases + o, a.rows, a.row_off,
-                                    a.ins, a.del, a.mismatch, a.match, code_at, a.scratch + a.seg_rec_off[s], n);
+    const int C = g.C, CW = g.CW, cshift = g.packed ? 3 : 4, cpw = 1 << cshift, invC = a.invC;
+    const int maxwl = g.T * CW - 1;
+    Record *out = a.scratch + a.seg_rec_off[s];
+
+    // walk state (warp-uniform)
+    int i = n - 1;
+    int r = jr[n].row;
+    int last = a.row_off[r + 1] - a.row_off[r] - 1;
+    int k = last, end = i, end_score = jr[n].j, cnt = 0;
+    // window (per lane)
+    int i0 = -1000, row0 = -1, half = 0;
+    uint32_t w0 = 0, w1 = 0, w2 = 0; int wb = 0; bool colok = false;
+
+    for (;;) {
+        if (k == 0) {
+            // k == 0: the insertion equality is tested although the forward pass never takes that move (main.cpp:245
+            // vs :194); decide it from J and the symbols involved, else close the alignment (main.cpp:252-262)
+            bool ins_move = false;
+            if (i != 0) {
+                const uint8_t m0 = a.rows[a.row_off[r]];
+                const int s_here = m0 == seg[i] ? a.match : a.mismatch;
+                const int s_prev = m0 == seg[i - 1] ? a.match : a.mismatch;
+                const int h_here = jr[i].j + s_here;
+                const int h_prev = (i == 1) ? s_prev : jr[i - 1].j + s_prev;
+                ins_move = (h_here == h_prev + a.ins);
+            }
+            if (ins_move) { --i; continue; }
+        } else {
+            if (r != row0 || i > i0 || i <= i0 - 32) {
+                // refill: lane d loads the words around cell k-d of column i-d
+                i0 = i; row0 = r;
+                const int slot = g.packed ? (r < g.M ? r : r - g.M) : r;
+                half = (g.packed && r >= g.M) ? 16 : 0;
+                const size_t word0 = (size_t)lane_tid(g.T, seg_local * g.nslots + slot, 0) * CW;
+                const int c = i - lane;
+                colok = c >= 0;
+                if (colok) {
+                    const int kp = max(k - lane, 0);
+                    const int t = (kp * invC) >> 16;
+                    const int wl = t * CW + ((kp - t * C) >> cshift);
+                    wb = min(max(wl - 1, 0), max(maxwl - 2, 0));
+                    const uint32_t *col = cbase + (size_t)c * cstride + word0;
+                    w0 = col[wb]; w1 = col[min(wb + 1, maxwl)]; w2 = col[min(wb + 2, maxwl)];
+                }
+            }
+            const int dcur = i0 - i;
+            const int kd = k - (lane - dcur);
+            bool ok = colok && lane >= dcur && kd >= 1;
+            int code = 2;
+            {
+                const int kq = max(kd, 0);
+                const int t = (kq * invC) >> 16;
+                const int kk = kq - t * C;
+                const int wi = kk >> cshift;
+                const int rel = t * CW + wi - wb;
+                ok = ok && (unsigned)rel < 3u;
+                const uint32_t w = rel == 0 ? w0 : rel == 1 ? w1 : w2;
+                const int cc = kk & (cpw - 1);
+                const int ncell = min(cpw, C - (wi << cshift));
+                code = (int)((w >> (2 * (ncell - 1 - cc) + half)) & 3u);
+            }
+            const bool stop = lane >= dcur && (!ok || code != 2);
+            const unsigned ball = __ballot_sync(0xffffffffu, stop);
+            const int f = ball ? __ffs(ball) - 1 : 32;
+            const int steps = f - dcur;                       // diagonal moves (main.cpp:249-250)
+            i -= steps; k -= steps;
+            if (f == 32) continue;                            // ran off the window: refill at the top
+            const int okf = __shfl_sync(0xffffffffu, (int)ok, f);
+            const int codef = __shfl_sync(0xffffffffu, code, f);
+            if (!okf) {
+                if (k >= 1) row0 = -1;                        // cell outside the cached words: force a refill
+                continue;                                     // (k == 0 is handled at the top)
+            }
+            if (codef == 0) { --k; continue; }                // deletion (main.cpp:242-243)
+            if (codef == 1) { --i; continue; }                // insertion (main.cpp:245-246)
+        }
+        // close the alignment (main.cpp:252-262)
+        if (cnt >= n) { cnt = -1; break; }
+        Record rec;
+        rec.row = r; rec.start = i; rec.end = end;
+        if (i == 0) { rec.score = end_score; if (lane == 0) out[cnt] = rec; ++cnt; break; }
+        const JR ji = jr[i];
+        rec.score = end_score - ji.j;
+        if (lane == 0) out[cnt] = rec;
+        ++cnt;
+        end_score = ji.j;
+        r = ji.row;
+        --i;
+        last = a.row_off[r + 1] - a.row_off[r] - 1;
+        k = last; end = i;
+    }
+    if (lane == 0) a.counts[s] = cnt;
 }
 
 // dense[out_off[s] + x] = scratch[seg_rec_off[s] + cnt-1-x]   (reversal of main.cpp:268)
@@ -451,7 +552,10 @@ public:
         t.rows = d_rows_.as<uint8_t>(); t.row_off = d_rowoff_.as<int>();
         t.ins = plan_.sc.ins; t.del = plan_.sc.del; t.mismatch = plan_.sc.mismatch; t.match = plan_.sc.match;
         t.scratch = d_scratch_.as<Record>(); t.seg_rec_off = d_segrec_.as<int64_t>(); t.counts = d_counts_.as<int>();
-        traceback_kernel<<<(nseg_ + 31) / 32, 32, 0, st_>>>(t);
+        t.invC = (65536 + g.C - 1) / g.C;
+        for (int pos = 0; pos < g.C * g.T; ++pos)
+            if (((pos * t.invC) >> 16) != pos / g.C) throw PlanError{"internal: reciprocal division inexact"};
+        traceback_kernel<<<(nseg_ + TB_WARPS - 1) / TB_WARPS, TB_WARPS * 32, 0, st_>>>(t);
         SD_CUDA(cudaGetLastError());
         SD_CUDA(cudaEventRecord(ev_[2], st_));
         SD_CUDA(cudaStreamSynchronize(st_));
