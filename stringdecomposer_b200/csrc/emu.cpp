@@ -23,7 +23,7 @@ void emu_cta(const Plan &p, const Batch &b, int seg_first, int nseg_cta, int nma
     constexpr int SPW = 32 / T;
     const uint32_t deadu = P::splat(p.deadz - 1);
     std::vector<uint32_t> Xall((size_t)NT * C, deadu), PWall((size_t)NT * C, 0u);
-    std::vector<uint32_t> E(NT), carry(NT), prevU(NT);
+    std::vector<uint32_t> E(NT), carry(NT);
     std::vector<int> bref(NS, p.sc.ins), jump0(NS, 0);
     std::vector<int> key(NS, INT_MIN);
     uint32_t (*X)[C] = reinterpret_cast<uint32_t (*)[C]>(Xall.data());
@@ -57,6 +57,7 @@ void emu_cta(const Plan &p, const Batch &b, int seg_first, int nseg_cta, int nma
         if (l.t == T - 1 && L == 1) PW[tid][C - 1] = P::add(PW[tid][C - 1], P::splat(4 * p.sc.del));
         lane_pre<P, C>(X[tid], deadu, PW[tid], deadu, l.t == 0, l.t == T - 1 && L == 1);
     }
+    std::vector<uint32_t> ufirst(NT), uend(NT);
     for (int i = 0;; ++i) {
         for (int tid = 0; tid < NT; ++tid) {
             const LaneId l = lane_id(tid);
@@ -70,23 +71,23 @@ void emu_cta(const Plan &p, const Batch &b, int seg_first, int nseg_cta, int nma
         std::fill(key.begin(), key.end(), INT_MIN);
         for (int tid = 0; tid < NT; ++tid) {
             const LaneId l = lane_id(tid);
-            lane_pass2<P, C>(X[tid], carry[tid], cw, tag_regs<P>());
+            load_profile(tid, l, i + 1);                      // profile of the next column (0-padded past the end)
+            uend[tid] = lane_pass2_pre<P, C>(X[tid], carry[tid], cw, tag_regs<P>(), PW[tid], deadu,
+                                             l.t == T - 1 && p.slot_len[l.slot] == 1, &ufirst[tid]);
             if (l.active && i < l.n)
                 for (int w = 0; w < g.CW; ++w) codes[((size_t)i * NT + tid) * g.CW + w] = cw[w];
             if (l.active && l.t == T - 1) {
-                const uint32_t u = X[tid][C - 1];
+                const uint32_t u = uend[tid];
                 int k0 = make_key(P::lo(u), p.slot_endadd[l.slot], l.slot);
                 if (P::ROWS == 2) k0 = std::max(k0, make_key(P::hi(u), p.slot_endadd[l.slot], g.M + l.slot));
                 key[l.seg_local] = std::max(key[l.seg_local], k0);
             }
         }
-        if (i + 1 < nmax) {
-            for (int tid = 0; tid < NT; ++tid) prevU[tid] = (lane_id(tid).t == 0) ? deadu : X[tid - 1][C - 1];
-            for (int tid = 0; tid < NT; ++tid) {
-                const LaneId l = lane_id(tid);
-                load_profile(tid, l, i + 1);
-                lane_pre<P, C>(X[tid], prevU[tid], PW[tid], deadu, l.t == 0, l.t == T - 1 && p.slot_len[l.slot] == 1);
-            }
+        for (int tid = 0; tid < NT; ++tid) {
+            const LaneId l = lane_id(tid);
+            const uint32_t prevU = (l.t == 0) ? deadu : uend[tid - 1];
+            X[tid][0] = lane_pre_first<P>(prevU, PW[tid][0], ufirst[tid], deadu, l.t == 0,
+                                          C == 1 && l.t == T - 1 && p.slot_len[l.slot] == 1);
         }
         // "barrier": keys visible
         std::vector<int> shift(NS, 0);

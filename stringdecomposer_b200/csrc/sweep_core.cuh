@@ -186,6 +186,39 @@ SD_HD void lane_pass2(uint32_t (&X)[C], uint32_t carryU, uint32_t *codes, TagReg
     }
 }
 
+// Pass 2 fused with pass 1a of the NEXT column.  While the deletion chain of column i runs through the lane
+// (two dependent ALU ops per cell), the J-independent candidates of column i+1 are formed from the fresh U values:
+//   X[kk] <- max(U[kk-1] + pn[kk], U[kk])      kk >= 1        (pn: profile words of column i+1)
+// Cell 0 needs the left lane's last U (a shuffle), so the caller finishes it with lane_pre_first().
+// Returns U[C-1] (row-end value for the jump key and the right neighbour's diagonal); *u_first gets U[0].
+template <class P, int C>
+SD_HD uint32_t lane_pass2_pre(uint32_t (&X)[C], uint32_t carryU, uint32_t *codes, TagRegs tr, const uint32_t (&pn)[C],
+                              uint32_t deadu, bool kill_last, uint32_t *u_first)
+{
+    constexpr int CPW = P::CELLS_PER_WORD;
+    uint32_t ul = carryU, uprev = 0;
+    uint32_t w = 0;
+#pragma unroll
+    for (int kk = 0; kk < C; ++kk) {
+        const uint32_t h = P::addmax(ul, tr.one, X[kk]);
+        ul = (h | tr.mask3) ^ tr.one;
+        w = w * 4u + ul - h;
+        if ((kk + 1) % CPW == 0) { codes[kk / CPW] = w + code_bias<P>(CPW); w = 0; }
+        else if (kk == C - 1) { codes[kk / CPW] = w + code_bias<P>(C % CPW); w = 0; }
+        if (kk == 0) *u_first = ul;
+        else X[kk] = P::addmax(uprev, pn[kk], (kk == C - 1 && kill_last) ? deadu : ul);
+        uprev = ul;
+    }
+    return ul;
+}
+
+template <class P>
+SD_HD uint32_t lane_pre_first(uint32_t prevU, uint32_t pn0, uint32_t u_first, uint32_t deadu, bool kill_first, bool kill_only)
+{
+    // kill_only: C == 1 and the single cell is also the slot's last cell of a length-1 row
+    return P::addmax(prevU, pn0, (kill_first || kill_only) ? deadu : u_first);
+}
+
 // Rebase: shift every register of the lane by -shift4 (packed per half).
 template <class P, int C>
 SD_HD void lane_rebase(uint32_t (&X)[C], int shift4)

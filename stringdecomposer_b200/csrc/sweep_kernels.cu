@@ -130,10 +130,13 @@ __global__ void sweep_kernel(const SweepArgs a)
     int srcl[T > 2 ? T - 2 : 1];
 #pragma unroll
     for (int d = 1; d <= T - 2; ++d) srcl[d - 1] = lane - min(d, t);
-    // FAST: segment s of the CTA owns int4 row s of each key buffer, its warps write one int each
+    // FAST: segment s of the CTA owns int4 row s of each key buffer, its warps write one int each.  Raw shared-space
+    // addresses keep the exchange to one STS / one LDS.128 (no generic-address arithmetic in the loop).
     const int wseg = FAST ? warp / a.wps : 0;
-    int *key_wr = skey + (FAST ? wseg * 4 + (warp - wseg * a.wps) : seg_local);
-    const int *key_rd = skey + (FAST ? wseg * 4 : seg_local);
+    const uint32_t skey_s = (uint32_t)__cvta_generic_to_shared(skey);
+    const uint32_t key_wr_s = skey_s + 4u * (uint32_t)(FAST ? wseg * 4 + (warp - wseg * a.wps) : seg_local);
+    const uint32_t key_rd_s = skey_s + 4u * (uint32_t)(FAST ? wseg * 4 : seg_local);
+    const uint32_t kbytes = 4u * (uint32_t)kstride;
 
     uint32_t X[C], pw[C];
 #pragma unroll
@@ -155,16 +158,20 @@ __global__ void sweep_kernel(const SweepArgs a)
     lane_pre<P, C>(X, deadu, pw, deadu, kill_first, kill_last);
     int jbase = a.ins;            // Bref + i*ins: J[i+1] = vmax + jbase
     int jump0 = 0;                // 4*(B[i] - Bref)
-    int kb = 0;                   // key buffer in use (FAST: 2 buffers alternate; else 3 rotate)
+    uint32_t kboff = 0;           // byte offset of the key buffer in use (FAST: 2 buffers alternate; else 3 rotate)
     int n_store = n_seg;          // columns whose backpointers are still to be written
     int n_j = j_writer ? n_seg : 0;
 #pragma unroll 1
     for (int i = 0; i < nmax; ++i) {
         const uint32_t E = lane_post<P, C>(X, pw, P::splat(jump0 + 1), deadu, tr);
+        // profile of the next column (the symbol buffer is 0-padded, so the round after the last column is harmless);
+        // issued here so that the loads fly during the scan
+        load_profile(*cp++);
         const uint32_t carry = slot_scan<P, T>(E, t, srcl, deadu);
         constexpr int NW = (C + P::CELLS_PER_WORD - 1) / P::CELLS_PER_WORD;
         uint32_t cw[NW];
-        lane_pass2<P, C>(X, carry, cw, tr);
+        uint32_t ufirst;
+        const uint32_t uend = lane_pass2_pre<P, C>(X, carry, cw, tr, pw, deadu, kill_last, &ufirst);
 
         if (n_store > 0) {
             if (NW == 2) *reinterpret_cast<uint2 *>(cptr) = make_uint2(cw[0], cw[1]);
@@ -178,42 +185,38 @@ __global__ void sweep_kernel(const SweepArgs a)
         cptr += cstride;
 
         // row ends -> (score,row) key of the segment: key = (u >> 2) * 4096 + (endadd * 4096 + 4095 - row)
-        const uint32_t u = X[C - 1];
         int key;
         if (P::ROWS == 2) {
-            const int klo = ((int)(u << 16) >> 18) * SD_KEY_ROWS + kc_lo;
-            const int khi = ((int)u >> 18) * SD_KEY_ROWS + kc_hi;
+            const int klo = ((int)(uend << 16) >> 18) * SD_KEY_ROWS + kc_lo;
+            const int khi = ((int)uend >> 18) * SD_KEY_ROWS + kc_hi;
             key = max(klo, khi);
         } else {
-            key = ((int)u >> 2) * SD_KEY_ROWS + kc_lo;
+            key = ((int)uend >> 2) * SD_KEY_ROWS + kc_lo;
         }
         if (!is_end) key = INT_MIN;
-        int *kbuf = skey + kb * kstride;
         if (FAST) {
             const int wk = __reduce_max_sync(0xffffffffu, key);
-            if (lane == 0) key_wr[kb * kstride] = wk;
+            if (lane == 0) asm volatile("st.shared.b32 [%0], %1;" ::"r"(key_wr_s + kboff), "r"(wk) : "memory");
         } else {
-            const int kclr = (kb == 0) ? 2 : kb - 1;                    // buffer read two columns ago
-            if (tid < NS) skey[kclr * kstride + tid] = INT_MIN;
-            if (is_end) atomicMax(&key_wr[kb * kstride], key);
+            const uint32_t kclr = (kboff == 0) ? 2 * kbytes : kboff - kbytes;      // buffer read two columns ago
+            if (tid < NS) asm volatile("st.shared.b32 [%0], %1;" ::"r"(skey_s + kclr + 4u * tid), "r"(INT_MIN) : "memory");
+            if (is_end) atomicMax(reinterpret_cast<int *>(reinterpret_cast<char *>(skey) + kboff) + seg_local, key);
         }
-        (void)kbuf;
-        // J-independent half of the next column, overlapping the barrier wait (the symbol buffer is padded, so
-        // the one extra round after the last column reads a harmless 0)
-        load_profile(*cp++);
+        // first cell of the lane for the next column: needs the left lane's row-end value
         uint32_t prevU = deadu;
-        if (T > 1) { prevU = __shfl_up_sync(0xffffffffu, X[C - 1], 1); if (t == 0) prevU = deadu; }
-        lane_pre<P, C>(X, prevU, pw, deadu, kill_first, kill_last);
+        if (T > 1) { prevU = __shfl_up_sync(0xffffffffu, uend, 1); if (t == 0) prevU = deadu; }
+        X[0] = lane_pre_first<P>(prevU, pw[0], ufirst, deadu, kill_first, C == 1 && kill_last);
 
         __syncthreads();
         int k2;
         if (FAST) {
-            const int4 v = *reinterpret_cast<const int4 *>(key_rd + kb * kstride);
+            int4 v;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(key_rd_s + kboff) : "memory");
             k2 = max(max(v.x, v.y), max(v.z, v.w));
-            kb ^= 1;
+            kboff ^= kbytes;
         } else {
-            k2 = key_rd[kb * kstride];
-            kb = (kb == 2) ? 0 : kb + 1;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(k2) : "r"(key_rd_s + kboff) : "memory");
+            kboff = (kboff == 2 * kbytes) ? 0 : kboff + kbytes;
         }
         const int vmax = k2 >> 12;
         ++jptr;
