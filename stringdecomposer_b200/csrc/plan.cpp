@@ -77,21 +77,26 @@ size_t Plan::smem_bytes(int seg_stride) const
     return prof.size() * 4 + (size_t)g.NS * (size_t)seg_stride + 3 * (size_t)g.NS * 4 + 64;
 }
 
-// Cost model (cycles of one SMSP) used to pick (C, T, NS); constants from tools/int_peak*.cu runs.
-// One warp needs warp_col issue cycles per column and cannot go faster than lat_col (dependent chain +
-// shuffles + the key exchange); w warps resident on an SMSP advance one column each in max(w*warp_col, lat_col).
-static double geometry_cost(int C, int T, int NS, int NT, int64_t nseg, int nmax)
+// Cost model used to pick (C, T, NS), calibrated on B200 runs.  The sweep is bound by the
+// ALU pipe (every DPX/VIMNMX/LOP3 instruction issues at 16 lanes/clk per SM sub-partition): a warp needs
+//   alu = 2 * (4.5*C + 43 + 4*ceil(log2 T))   ALU-pipe cycles per column,
+// a sub-partition hosting w warps advances them one column in max(w*alu/0.75, lat) cycles (0.75: the pipe
+// utilisation reached with the CTA-wide column barrier), and an SM hosts k CTAs (k limited by shared memory --
+// the profile table is per CTA -- and registers).  Small launches are quantised: the slowest SM sets the time.
+static double geometry_cost(int C, int T, int NS, int NT, size_t smem_bytes, int64_t nseg, int nmax)
 {
-    const int lg = (T > 1) ? __builtin_ctz((unsigned)T) : 0;
-    const double per_cell = (T == 1) ? 8.0 : 9.6;
-    const double warp_col = C * per_cell + 120.0 + (T > 1 ? 56.0 * (1 + lg) : 0.0);
-    const double lat_col = C * 8.0 + 220.0 + 60.0 * lg;
-    const int64_t nctas = (nseg + NS - 1) / NS;
-    const double wps = (double)nctas * (NT / 32) / (148.0 * 4.0);
-    const double cap = 8.0;
-    const double waves = std::max(1.0, std::ceil(wps / cap));
-    const double w_res = std::max(1.0, wps / waves);
-    return (double)nmax * waves * std::max(w_res * warp_col, lat_col);
+    const int lg = (T > 1) ? 32 - __builtin_clz((unsigned)(T - 1)) : 0;
+    const int W = NT / 32;
+    const double alu = 2.0 * (4.5 * C + 43.0 + 4.0 * lg);
+    const double lat = 350.0 + 9.0 * C + 30.0 * lg;
+    int kmax = (int)std::min<size_t>((227u * 1024u) / std::max<size_t>(smem_bytes, 1), 32);
+    kmax = std::min(kmax, 65536 / (NT * (2 * C + 40)));       // registers: X[C] + profile[C] + ~40
+    kmax = std::min(kmax, 64 / W);
+    if (kmax < 1) return 1e300;
+    const int64_t ncta = (nseg + NS - 1) / NS;
+    auto col_cost = [&](int k) { return std::max(std::ceil(k * W / 4.0) * alu / 0.75, lat); };
+    if (ncta <= (int64_t)148 * kmax) return (double)nmax * col_cost((int)((ncta + 147) / 148));
+    return (double)nmax * ((double)ncta / (148.0 * kmax)) * col_cost(kmax);
 }
 
 Plan make_plan(const MonomerSet &ms, const Scoring &sc, int max_seg_len, int64_t nseg_hint)
@@ -118,9 +123,13 @@ Plan make_plan(const MonomerSet &ms, const Scoring &sc, int max_seg_len, int64_t
     int bestC = 0, bestT = 0, bestNS = 0, bestNT = 0; double best = 1e300;
     int fC = 0, fT = 0, fNS = 0;
     if (const char *e = getenv("SD_GEOM")) sscanf(e, "%d,%d,%d", &fC, &fT, &fNS);
+    // lanes with more than 24 cells run into register-limited occupancy and long dependent chains (measured);
+    // they are only considered for rows that need them
+    const bool need_big = ms.Lmax > 24 * 32;
     for (int C : kC) for (int T : kT) {
         if (fC && (C != fC || T != fT)) continue;
         if (C * T < ms.Lmax) continue;
+        if (!fC && C > 24 && !need_big) continue;
         int ls = nslots * T;                        // lanes per segment
         if (ls > 1024) continue;
         const int qpc = (C / 4) | 1;
@@ -131,12 +140,12 @@ Plan make_plan(const MonomerSet &ms, const Scoring &sc, int max_seg_len, int64_t
             int NT = (NS * nslots + spw - 1) / spw * 32;
             int lanes = NS * ls;
             if (NT > 1024) break;
-            if ((int64_t)NT * (C + 72) > 65536) continue;       // register file (verified against the real kernel at configure time)
+            if ((int64_t)NT * (2 * C + 40) > 65536) continue;   // register file (verified against the real kernel at configure time)
             size_t smem = prof_bytes + (size_t)NS * ((size_t)max_seg_len + 64) + 256;
             if (smem > kSmemLimit) continue;
-            double util = (double)lanes / NT;
-            double cost = geometry_cost(C, T, NS, NT, std::max<int64_t>(nseg_hint, 1), std::max(max_seg_len, 1)) / util;
-            cost *= 1.0 + 0.02 * (NS - 1);            // mild preference for independent CTAs
+            (void)lanes;
+            double cost = geometry_cost(C, T, NS, NT, smem, std::max<int64_t>(nseg_hint, 1), std::max(max_seg_len, 1));
+            cost *= 1.0 + 0.002 * (NS - 1);           // ties: prefer fewer segments per CTA
             if (cost < best) { best = cost; bestC = C; bestT = T; bestNS = NS; bestNT = NT; }
         }
     }

@@ -142,16 +142,39 @@ SD_HD void lane_pre(uint32_t (&X)[C], uint32_t prevU, const uint32_t (&pw)[C], u
 // Pass 1b ("post"): add the jump candidate 4*(B[i]-Bref) + 4*s'' (tag 0) once J[i] is known.
 // jump0p1 = splat(4*(B[i]-Bref) + 1) (the +1 undoes the -1 folded into the profile words).
 // Returns the lane maximum in tag-2 form: what the lane hands to the lanes on its right (deletion chain).
+// Maximum of n registers as a ternary tree (depth ~log3 n instead of a serial chain of VIMNMX3).
+template <class P, int N> SD_HD uint32_t tree_max(const uint32_t (&v)[N])
+{
+    uint32_t a[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) a[j] = v[j];
+    int n = N;
+#pragma unroll
+    for (int level = 0; level < 6; ++level) {
+        if (n <= 1) break;
+        const int m = (n + 2) / 3;
+#pragma unroll
+        for (int j = 0; j < (N + 2) / 3; ++j) {
+            if (j < m) {
+                const int b = 3 * j;
+                uint32_t r = a[b];
+                if (b + 2 < n) r = P::max3(a[b], a[b + 1], a[b + 2]);
+                else if (b + 1 < n) r = P::max2(a[b], a[b + 1]);
+                a[j] = r;
+            }
+        }
+        n = m;
+    }
+    return a[0];
+}
+
 template <class P, int C>
 SD_HD uint32_t lane_post(uint32_t (&X)[C], const uint32_t (&pw)[C], uint32_t jump0p1, uint32_t deadu, TagRegs tr)
 {
-    uint32_t E = deadu;
+    (void)deadu;
 #pragma unroll
-    for (int kk = 0; kk < C; ++kk) {
-        const uint32_t m2 = P::addmax(pw[kk], jump0p1, X[kk]);
-        X[kk] = m2;
-        E = P::max2(E, m2);
-    }
+    for (int kk = 0; kk < C; ++kk) X[kk] = P::addmax(pw[kk], jump0p1, X[kk]);
+    const uint32_t E = tree_max<P, C>(X);
     return (E | tr.mask3) ^ tr.one;
 }
 

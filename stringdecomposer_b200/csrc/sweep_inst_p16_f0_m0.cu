@@ -1,0 +1,5 @@
+// instantiations of sweep_kernel<Packed16, C, T, FAST=0, MULTI=0>
+#include "sweep_kernel.cuh"
+namespace sdb {
+SD_INSTANTIATE_SWEEP(sweep_lookup_p16_f0_m0, Packed16, false, false)
+}

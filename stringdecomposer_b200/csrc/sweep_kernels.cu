@@ -21,7 +21,7 @@
 #include <string>
 #include <vector>
 
-#include "common.h"
+#include "sweep_kernel.cuh"
 
 namespace sdb {
 
@@ -31,206 +31,6 @@ namespace sdb {
         if (e_ != cudaSuccess) throw PlanError{std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " +  \
                                                __FILE__ + ":" + std::to_string(__LINE__)};                      \
     } while (0)
-
-struct SweepArgs {
-    const uint4 *prof; int prof_u4;                    // [5][nsl][qp] uint4
-    const uint8_t *bases; const int64_t *seg_off;      // seg_off indexed by segment id within the staged wave
-    int nseg;
-    const int *cta_nmax; const int64_t *cta_code_off; const int64_t *seg_j_off;
-    uint32_t *codes; JR *jr;
-    const int *slot_len; const int *slot_endadd;
-    int nslots, M, NS, NT, CW, nsl, qp;
-    int ins, del, deadz;
-    int seg_stride;
-    int wps;                // warps per segment (FAST only, <= 4)
-    int kstride;            // ints per key buffer
-    TagRegs tr;             // TAGMASK / ONE of the policy, passed as run-time values (sweep_core.cuh: TagRegs)
-};
-
-// Exclusive prefix max of the lane maxima over the T lanes of a slot (deletion chain carried across lanes).
-template <class P, int T>
-__device__ __forceinline__ uint32_t slot_scan(uint32_t E, int t, const int (&srcl)[T > 2 ? T - 2 : 1], uint32_t dead)
-{
-    if (T == 1) return dead;
-    uint32_t pv = __shfl_up_sync(0xffffffffu, E, 1);
-    if (t == 0) pv = dead;
-    if (T == 2) return pv;
-    if (T <= 10) {
-        // flat: every lane pulls the (already exclusive) value of each lane further left in one round of independent
-        // shuffles; lanes without such a neighbour re-read lane 0 of their slot, whose value is "dead" (harmless)
-        uint32_t acc = pv;
-#pragma unroll
-        for (int d = 1; d <= T - 2; ++d) acc = P::max2(acc, __shfl_sync(0xffffffffu, pv, srcl[d - 1]));
-        return acc;
-    }
-#pragma unroll
-    for (int d = 1; d < T; d <<= 1) {
-        const uint32_t o = __shfl_up_sync(0xffffffffu, pv, d);
-        if (t >= d) pv = P::max2(pv, o);
-    }
-    return pv;
-}
-
-// FAST: every warp serves exactly one segment and a segment has <= 4 warps: the per-column (score,row) key is
-// reduced with CREDUX inside the warp and exchanged through one aligned int4 row of shared memory.
-// !FAST: arbitrary lane->segment mapping; keys meet in shared-memory atomicMax (three rotating buffers).
-template <class P, int C, int T, bool FAST>
-__global__ void sweep_kernel(const SweepArgs a)
-{
-    extern __shared__ uint4 smem_u4[];
-    uint4 *sprof = smem_u4;
-    int *skey = reinterpret_cast<int *>(sprof + a.prof_u4);             // key buffers, 16-byte aligned rows
-    const int NS = a.NS, NT = a.NT;
-    const int kstride = a.kstride;
-    uint8_t *schar = reinterpret_cast<uint8_t *>(skey + 3 * kstride);
-
-    const int tid = threadIdx.x, cta = blockIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-    constexpr int SPW = 32 / T;
-    const int siw = lane / T, t = lane - siw * T;
-    const bool lane_ok = siw < SPW;
-    const int ginst = warp * SPW + (lane_ok ? siw : 0);
-    int seg_local = ginst / a.nslots;
-    const int slot = ginst - seg_local * a.nslots;
-    const int first = cta * NS;                                         // first segment of the CTA (within the launch)
-    const bool active = lane_ok && seg_local < NS && first + seg_local < a.nseg;
-    if (seg_local >= NS) seg_local = 0;
-    const int nmax = a.cta_nmax[cta];
-    int n_seg = 0;
-    if (active) n_seg = (int)(a.seg_off[first + seg_local + 1] - a.seg_off[first + seg_local]);
-
-    // stage profile, segment symbols and keys
-    for (int x = tid; x < a.prof_u4; x += NT) sprof[x] = a.prof[x];
-    for (int s = 0; s < NS; ++s) {
-        int n = 0; const uint8_t *src = nullptr;
-        if (first + s < a.nseg) {
-            const int64_t o = a.seg_off[first + s];
-            n = (int)(a.seg_off[first + s + 1] - o);
-            src = a.bases + o;
-        }
-        for (int x = tid; x < a.seg_stride; x += NT) schar[s * a.seg_stride + x] = (x < n) ? src[x] : (uint8_t)0;
-    }
-    for (int x = tid; x < 3 * kstride; x += NT) skey[x] = INT_MIN;
-    __syncthreads();
-
-    const int L = a.slot_len[slot];
-    const int endadd = a.slot_endadd[slot];
-    const uint32_t deadu = P::splat(a.deadz - 1);
-    const TagRegs tr = a.tr;
-    const bool kill_first = (t == 0), kill_last = (t == T - 1 && L == 1);
-    const bool j_writer = active && slot == 0 && t == 0;
-    const bool is_end = active && t == T - 1;
-    const int kc_lo = key_const(endadd, slot), kc_hi = key_const(endadd, a.M + slot);
-    JR *jptr = a.jr + (active ? a.seg_j_off[first + seg_local] : 0);
-    uint32_t *cptr = a.codes + a.cta_code_off[cta] + (size_t)tid * a.CW;
-    const size_t cstride = (size_t)NT * a.CW;
-    const uint8_t *cp = schar + seg_local * a.seg_stride;               // symbol of the column being prepared
-    const uint4 *myprof = sprof + (size_t)(slot * T + t) * a.qp;
-    const int sym_stride = a.nsl * a.qp;
-    int srcl[T > 2 ? T - 2 : 1];
-#pragma unroll
-    for (int d = 1; d <= T - 2; ++d) srcl[d - 1] = lane - min(d, t);
-    // FAST: segment s of the CTA owns int4 row s of each key buffer, its warps write one int each.  Raw shared-space
-    // addresses keep the exchange to one STS / one LDS.128 (no generic-address arithmetic in the loop).
-    const int wseg = FAST ? warp / a.wps : 0;
-    const uint32_t skey_s = (uint32_t)__cvta_generic_to_shared(skey);
-    const uint32_t key_wr_s = skey_s + 4u * (uint32_t)(FAST ? wseg * 4 + (warp - wseg * a.wps) : seg_local);
-    const uint32_t key_rd_s = skey_s + 4u * (uint32_t)(FAST ? wseg * 4 : seg_local);
-    const uint32_t kbytes = 4u * (uint32_t)kstride;
-
-    uint32_t X[C], pw[C];
-#pragma unroll
-    for (int kk = 0; kk < C; ++kk) X[kk] = deadu;
-    auto load_profile = [&](int sym) {
-        const uint4 *pp = myprof + sym * sym_stride;
-#pragma unroll
-        for (int q = 0; q < C / 4; ++q) {
-            const uint4 v = pp[q];
-            pw[4 * q] = v.x; pw[4 * q + 1] = v.y; pw[4 * q + 2] = v.z; pw[4 * q + 3] = v.w;
-        }
-    };
-
-    // column 0: everything dead, base B[0] = ins (row-0 rule, main.cpp:180); the k==0 cell is s(0,0) itself
-    // (main.cpp:173-177), i.e. one `del` more than the generic jump candidate
-    load_profile(*cp++);
-    if (t == 0 && L > 1) pw[0] = P::add(pw[0], P::splat(4 * a.del));
-    if (t == T - 1 && L == 1) pw[C - 1] = P::add(pw[C - 1], P::splat(4 * a.del));
-    lane_pre<P, C>(X, deadu, pw, deadu, kill_first, kill_last);
-    int jbase = a.ins;            // Bref + i*ins: J[i+1] = vmax + jbase
-    int jump0 = 0;                // 4*(B[i] - Bref)
-    uint32_t kboff = 0;           // byte offset of the key buffer in use (FAST: 2 buffers alternate; else 3 rotate)
-    int n_store = n_seg;          // columns whose backpointers are still to be written
-    int n_j = j_writer ? n_seg : 0;
-#pragma unroll 1
-    for (int i = 0; i < nmax; ++i) {
-        const uint32_t E = lane_post<P, C>(X, pw, P::splat(jump0 + 1), deadu, tr);
-        // profile of the next column (the symbol buffer is 0-padded, so the round after the last column is harmless);
-        // issued here so that the loads fly during the scan
-        load_profile(*cp++);
-        const uint32_t carry = slot_scan<P, T>(E, t, srcl, deadu);
-        constexpr int NW = (C + P::CELLS_PER_WORD - 1) / P::CELLS_PER_WORD;
-        uint32_t cw[NW];
-        uint32_t ufirst;
-        const uint32_t uend = lane_pass2_pre<P, C>(X, carry, cw, tr, pw, deadu, kill_last, &ufirst);
-
-        if (n_store > 0) {
-            if (NW == 2) *reinterpret_cast<uint2 *>(cptr) = make_uint2(cw[0], cw[1]);
-            else if (NW == 4) *reinterpret_cast<uint4 *>(cptr) = make_uint4(cw[0], cw[1], cw[2], cw[3]);
-            else {
-#pragma unroll
-                for (int w = 0; w < NW; ++w) cptr[w] = cw[w];
-            }
-        }
-        --n_store;
-        cptr += cstride;
-
-        // row ends -> (score,row) key of the segment: key = (u >> 2) * 4096 + (endadd * 4096 + 4095 - row)
-        int key;
-        if (P::ROWS == 2) {
-            const int klo = ((int)(uend << 16) >> 18) * SD_KEY_ROWS + kc_lo;
-            const int khi = ((int)uend >> 18) * SD_KEY_ROWS + kc_hi;
-            key = max(klo, khi);
-        } else {
-            key = ((int)uend >> 2) * SD_KEY_ROWS + kc_lo;
-        }
-        if (!is_end) key = INT_MIN;
-        if (FAST) {
-            const int wk = __reduce_max_sync(0xffffffffu, key);
-            if (lane == 0) asm volatile("st.shared.b32 [%0], %1;" ::"r"(key_wr_s + kboff), "r"(wk) : "memory");
-        } else {
-            const uint32_t kclr = (kboff == 0) ? 2 * kbytes : kboff - kbytes;      // buffer read two columns ago
-            if (tid < NS) asm volatile("st.shared.b32 [%0], %1;" ::"r"(skey_s + kclr + 4u * tid), "r"(INT_MIN) : "memory");
-            if (is_end) atomicMax(reinterpret_cast<int *>(reinterpret_cast<char *>(skey) + kboff) + seg_local, key);
-        }
-        // first cell of the lane for the next column: needs the left lane's row-end value
-        uint32_t prevU = deadu;
-        if (T > 1) { prevU = __shfl_up_sync(0xffffffffu, uend, 1); if (t == 0) prevU = deadu; }
-        X[0] = lane_pre_first<P>(prevU, pw[0], ufirst, deadu, kill_first, C == 1 && kill_last);
-
-        __syncthreads();
-        int k2;
-        if (FAST) {
-            int4 v;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(key_rd_s + kboff) : "memory");
-            k2 = max(max(v.x, v.y), max(v.z, v.w));
-            kboff ^= kbytes;
-        } else {
-            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(k2) : "r"(key_rd_s + kboff) : "memory");
-            kboff = (kboff == 2 * kbytes) ? 0 : kboff + kbytes;
-        }
-        const int vmax = k2 >> 12;
-        ++jptr;
-        if (n_j > 0) *jptr = JR{vmax + jbase, SD_KEY_ROWS - 1 - (k2 & (SD_KEY_ROWS - 1))};
-        --n_j;
-        jbase += a.ins;
-        jump0 = 4 * (vmax + a.del);
-        if (jump0 > SD_REBASE_TH || jump0 < -SD_REBASE_TH) {
-            lane_rebase<P, C>(X, jump0);
-            jbase += jump0 >> 2;
-            jump0 = 0;
-        }
-    }
-}
 
 // ---------------------------------------------------------------------------------------------
 struct TbArgs {
@@ -393,26 +193,11 @@ template <int MODE> __global__ void int_peak_kernel(unsigned *out, unsigned seed
 }
 
 // ---------------------------------------------------------------------------------------------
-template <class P, int C, bool F> static const void *kern_t(int T)
+static const void *kern(int packed, int C, int T, bool fast, bool multi)
 {
-    switch (T) {
-    case 1: return (const void *)sweep_kernel<P, C, 1, F>; case 2: return (const void *)sweep_kernel<P, C, 2, F>;
-    case 4: return (const void *)sweep_kernel<P, C, 4, F>; case 8: return (const void *)sweep_kernel<P, C, 8, F>;
-    case 10: return (const void *)sweep_kernel<P, C, 10, F>;
-    case 16: return (const void *)sweep_kernel<P, C, 16, F>; case 32: return (const void *)sweep_kernel<P, C, 32, F>;
-    }
-    return nullptr;
+    if (packed) return fast ? (multi ? sweep_lookup_p16_f1_m1(C, T) : sweep_lookup_p16_f1_m0(C, T)) : sweep_lookup_p16_f0_m0(C, T);
+    return fast ? (multi ? sweep_lookup_s32_f1_m1(C, T) : sweep_lookup_s32_f1_m0(C, T)) : sweep_lookup_s32_f0_m0(C, T);
 }
-template <class P, bool F> static const void *kern_c(int C, int T)
-{
-    switch (C) {
-    case 8: return kern_t<P, 8, F>(T); case 12: return kern_t<P, 12, F>(T); case 16: return kern_t<P, 16, F>(T);
-    case 20: return kern_t<P, 20, F>(T); case 24: return kern_t<P, 24, F>(T); case 32: return kern_t<P, 32, F>(T);
-    case 48: return kern_t<P, 48, F>(T);
-    }
-    return nullptr;
-}
-template <class P> static const void *kern(int C, int T, bool fast) { return fast ? kern_c<P, true>(C, T) : kern_c<P, false>(C, T); }
 
 namespace {
 
@@ -455,8 +240,9 @@ public:
         plan_ = p; ms_ = ms;
         const Geometry &g = p.g;
         const int spw = 32 / g.T;
-        fast_ = (g.nslots % spw == 0) && (g.nslots / spw <= 4);
-        kernel_ = g.packed ? kern<Packed16>(g.C, g.T, fast_) : kern<Scalar32>(g.C, g.T, fast_);
+        fast_ = (g.nslots % spw == 0) && (g.nslots / spw <= 4) && g.NS <= 15;     // 15 named barriers besides barrier 0
+        if (getenv("SD_NOFAST")) fast_ = false;
+        kernel_ = kern(g.packed, g.C, g.T, fast_, fast_ && g.NS > 1);
         if (!kernel_) throw PlanError{"no sweep kernel compiled for this geometry"};
         cudaFuncAttributes fa;
         SD_CUDA(cudaFuncGetAttributes(&fa, kernel_));
