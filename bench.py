@@ -29,10 +29,10 @@ PART, OVERLAP = 5000, 500
 SCORING = (-1, -1, -1, 1)
 METRIC = "dp_gcups"
 UNIT = "GCUPS"
-# integer-pipe instructions the sweep issues per useful DP cell in the packed s16x2 kernel:
-# per register (2 cells): 2 VIADDMNMX + VIADD.16x2 + 0.5 VIMNMX3 + VIMNMX + LOP3 (ALU pipe), 2 IMAD (FMA pipe) = 7.5 -> 3.75
-OPS_PER_CELL = 3.75
-SURVEY_OPS_PER_CELL = 5.5      # SURVEY.md section 8d planning figure for s16x2
+# ALU-pipe instructions the sweep needs per DP cell in the packed s16x2 kernel: per register
+# (2 cells) 3 VIADDMNMX + 0.5 VIMNMX3 + 1 LOP3 = 4.5 -> 2.25 per cell (the 2 IMAD per register run on the FMA pipe)
+OPS_PER_CELL = {1: 2.25, 0: 4.5}
+SURVEY_OPS_PER_CELL = {1: 5.5, 0: 11.0}      # SURVEY.md section 8d planning figures (s16x2 / s32)
 
 
 def dist_setup(n_gpus):
@@ -79,14 +79,27 @@ def sum_over_ranks(x, ws):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """Samples SM clock and throttle reasons during the timed region: NVML from a thread (10 ms period, no extra
+    process), falling back to the nvidia-smi recipe of B200_PROFILING.md."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu):
-        self.gpu, self.proc, self.lines = gpu, None, []
+        self.gpu, self.proc, self.lines, self.samples, self.stop_flag = gpu, None, [], [], False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu)
+        except Exception:
+            self.nvml = None
 
     def start(self):
+        if self.nvml:
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -95,11 +108,37 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+                mx = n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)
+                try:
+                    r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((sm, mx, r))
+            except Exception:
+                pass
+            time.sleep(0.01)
+
     def _pump(self):
         for ln in self.proc.stdout:
             self.lines.append(ln)
 
     def stop(self):
+        if self.nvml:
+            self.stop_flag = True
+            self.th.join(timeout=1)
+            n = self.nvml
+            names = {"hw_slowdown": getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8), "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+            sm = [s[0] for s in self.samples]
+            reasons = sorted({k for s in self.samples for k, bit in names.items() if s[2] & bit})
+            busy = [x for x in sm if x > 0.5 * max(sm)] if sm else []
+            return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": float(max(s[1] for s in self.samples)) if self.samples else None,
+                    "reasons": reasons, "samples": len(sm), "source": "nvml, 10 ms period during the timed region"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -121,7 +160,7 @@ class ClockSampler:
                     reasons.add(name)
         busy = [x for x in sm if x > 0.5 * max(sm)] if sm else []
         return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 def workload(rank):
@@ -186,7 +225,7 @@ def run_reference_arm(args, ws, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -256,13 +295,16 @@ def main():
         # ---- roofline of the dominant kernel (sweep): integer issue rate --------------------------------
         alu, both, mhz = int_peak(local)
         cells_rank = float(cells_of(segs, mons))
-        ach = cells_rank / (sweep_ms * 1e-3) * OPS_PER_CELL / 1e12
-        peak = both / 1e12
+        opc = OPS_PER_CELL[1 if st["packed"] else 0]
+        ach = cells_rank / (sweep_ms * 1e-3) * opc / 1e12
+        peak = alu / 1e12
         codes_bytes = cells_rank * 0.25
-        roof = {"bound": "int", "achieved": ach, "peak": peak, "unit": "Tlane-op/s", "frac": ach / peak, "traffic": None,
-                "peak_source": "sd_int_peak: VIADDMNMX.S16x2 + IMAD streams on all SMs, this run (ALU pipe alone %.2f)" % (alu / 1e12),
-                "ops_per_cell": OPS_PER_CELL, "kernel": "sweep_kernel", "kernel_ms": sweep_ms, "traceback_ms": tb_ms,
-                "frac_at_survey_5.5_ops_per_cell_vs_alu_peak": cells_rank / (sweep_ms * 1e-3) * SURVEY_OPS_PER_CELL / alu,
+        roof = {"bound": "int_alu", "achieved": ach, "peak": peak, "unit": "Tlane-op/s", "frac": ach / peak,
+                "traffic": TRAFFIC_BYTES_PER_LAUNCH,
+                "peak_source": "measured in this run by sd_int_peak: independent VIADDMNMX.S16x2 streams on all SMs "
+                               "(the integer ALU pipe, 64 lanes/clk/SM); with the FMA pipe (IMAD) in parallel: %.2f" % (both / 1e12),
+                "ops_per_cell": opc, "kernel": "sweep_kernel", "kernel_ms": sweep_ms, "traceback_ms": tb_ms,
+                "frac_with_survey_ops_per_cell": cells_rank / (sweep_ms * 1e-3) * SURVEY_OPS_PER_CELL[1 if st["packed"] else 0] / alu,
                 "hbm": {"achieved_gbs": (codes_bytes + sum(len(s) for s in segs) * 9.0) / (sweep_ms * 1e-3) / 1e9,
                         "peak_gbs": _hbm_peak(), "note": "2-bit backpointers, 0.25 B/cell; not the limiter"}}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
@@ -286,6 +328,10 @@ def main():
         import torch.distributed as dist
         dist.barrier()
         dist.destroy_process_group()
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of one sweep_kernel launch on this workload (ncu --set full, profiles/)
+TRAFFIC_BYTES_PER_LAUNCH = None
 
 
 def sum_len(reads):

@@ -1,6 +1,8 @@
 // api.cpp -- the C ABI declared in include/sd_b200.h.
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
+#include <cstdio>
 #include <mutex>
 #include <unistd.h>
 
@@ -62,14 +64,15 @@ static int to_batch(const char *segments, const int64_t *offsets, int64_t n, Bat
         b.off[(size_t)s] = offsets[s] - base;
         if (s && offsets[s] <= offsets[s - 1]) { err = "segments must be non-empty and offsets increasing"; return SD_ERR_ARG; }
     }
-    const int64_t total = n ? offsets[n] - base : 0;
-    b.bases.resize((size_t)total);
-    for (int64_t x = 0; x < total; ++x) {
-        int c = base_code(segments[base + x]);
-        if (c < 0) { err = "segment contains a symbol outside ACGTN"; return SD_ERR_INPUT; }
-        b.bases[(size_t)x] = (uint8_t)c;
-    }
+    b.text = reinterpret_cast<const uint8_t *>(segments) + base;     // encoded and validated on the device
     return SD_OK;
+}
+
+static int status_of(const std::string &msg)
+{
+    if (msg.find("symbol outside") != std::string::npos) return SD_ERR_INPUT;
+    if (msg.find("CUDA") != std::string::npos) return SD_ERR_CUDA;
+    return SD_ERR_UNSUPPORTED;
 }
 
 static int export_result(const BatchResult &res, sd_record **records, int64_t **rec_offsets)
@@ -116,13 +119,22 @@ int sd_decompose(sd_handle *h, const char *segments, const int64_t *offsets, int
 {
     if (!h || !records || !rec_offsets) return SD_ERR_ARG;
     Batch b;
+    const auto t0 = std::chrono::steady_clock::now();
     int st = to_batch(segments, offsets, n_segments, b, h->err);
     if (st) return st;
+    const auto t1 = std::chrono::steady_clock::now();
     BatchResult res;
     try { h->eng->decompose(b, res); }
-    catch (PlanError &e) { h->err = e.msg; return e.msg.find("CUDA") != std::string::npos ? SD_ERR_CUDA : SD_ERR_UNSUPPORTED; }
+    catch (PlanError &e) { h->err = e.msg; return status_of(e.msg); }
     catch (std::exception &e) { h->err = e.what(); return SD_ERR_INTERNAL; }
-    return export_result(res, records, rec_offsets);
+    const auto t2 = std::chrono::steady_clock::now();
+    st = export_result(res, records, rec_offsets);
+    if (getenv("SD_PROFILE")) {
+        const auto t3 = std::chrono::steady_clock::now();
+        auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        fprintf(stderr, "[sd_b200 profile] sd_decompose: encode %.3f decompose %.3f export %.3f ms\n", ms(t0, t1), ms(t1, t2), ms(t2, t3));
+    }
+    return st;
 }
 
 int sd_stage(sd_handle *h, const char *segments, const int64_t *offsets, int64_t n_segments)
@@ -132,7 +144,7 @@ int sd_stage(sd_handle *h, const char *segments, const int64_t *offsets, int64_t
     int st = to_batch(segments, offsets, n_segments, b, h->err);
     if (st) return st;
     try { h->eng->stage(b); }
-    catch (PlanError &e) { h->err = e.msg; return e.msg.find("CUDA") != std::string::npos ? SD_ERR_CUDA : SD_ERR_UNSUPPORTED; }
+    catch (PlanError &e) { h->err = e.msg; return status_of(e.msg); }
     return SD_OK;
 }
 
@@ -140,7 +152,7 @@ int sd_run_staged(sd_handle *h, double *kernel_ms)
 {
     if (!h) return SD_ERR_ARG;
     try { double ms = h->eng->run_staged(); if (kernel_ms) *kernel_ms = ms; }
-    catch (PlanError &e) { h->err = e.msg; return SD_ERR_CUDA; }
+    catch (PlanError &e) { h->err = e.msg; return status_of(e.msg); }
     return SD_OK;
 }
 

@@ -40,13 +40,22 @@ struct Plan {
     size_t smem_bytes(int seg_stride) const;
 };
 
-// A batch of segments to decompose (symbol codes, concatenated).
+// A batch of segments to decompose: upper-case ACGTN text of all segments back to back.  `text` may point into
+// caller-owned memory (sd_decompose hands the caller's buffer straight to the H2D copy; the symbols are encoded
+// and validated on the device) or into `own`.
 struct Batch {
-    std::vector<uint8_t> bases;          // all segments back to back
-    std::vector<int64_t> off;            // nseg+1
+    const uint8_t *text = nullptr;
+    std::vector<uint8_t> own;
+    std::vector<int64_t> off;            // nseg+1, relative to text
     int nseg() const { return (int)off.size() - 1; }
     int len(int s) const { return (int)(off[s + 1] - off[s]); }
 };
+
+// A C G T N -> 0..4, anything else -> 255; shared by the device staging code and the emulator
+SD_HD int ascii_code(unsigned c)
+{
+    return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : c == 'N' ? 4 : 255;
+}
 
 struct BatchResult {
     std::vector<Record> recs;            // per segment in read order (already reversed), positions segment-relative

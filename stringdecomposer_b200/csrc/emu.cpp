@@ -14,6 +14,8 @@ namespace sdb {
 
 namespace {
 
+bool &bad_symbol() { static thread_local bool f = false; return f; }
+
 template <class P, int C, int T>
 void emu_cta(const Plan &p, const Batch &b, int seg_first, int nseg_cta, int nmax,
              uint32_t *codes, JR *const *jr)
@@ -44,7 +46,8 @@ void emu_cta(const Plan &p, const Batch &b, int seg_first, int nseg_cta, int nma
         return l;
     };
     auto load_profile = [&](int tid, const LaneId &l, int i) {
-        const int sym = (i < l.n) ? b.bases[b.off[seg_first + l.seg_local] + i] : 0;
+        int sym = (i < l.n) ? ascii_code(b.text[b.off[seg_first + l.seg_local] + i]) : 0;
+        if (sym > 4) { bad_symbol() = true; sym = 0; }
         for (int kk = 0; kk < C; ++kk)
             PW[tid][kk] = p.prof[(((size_t)sym * p.nsl + l.sl) * p.qp + kk / 4) * 4 + (kk % 4)];
     };
@@ -152,6 +155,7 @@ public:
         jr_.assign((size_t)lay_.seg_j_off.back(), JR{0, 0});
         const int nseg = s1_ - s0_, nctas = (int)lay_.cta_nmax.size();
         EmuFlags::overflow() = false;
+        bad_symbol() = false;
         for (int c = 0; c < nctas; ++c) {
             int first = c * g.NS, cnt = std::min(g.NS, nseg - first);
             std::vector<JR *> jp(g.NS, nullptr);
@@ -161,6 +165,10 @@ public:
             else pick<Scalar32>(g.C, g.T)(plan_, b, s0_ + first, cnt, lay_.cta_nmax[c], codes, jp.data());
         }
         overflowed_ = g.packed && EmuFlags::overflow();
+        if (bad_symbol()) throw PlanError{"segment contains a symbol outside ACGTN"};
+        // the traceback compares segment and row symbols: bring the rows to the same (ASCII) alphabet
+        rows_ascii_.resize(ms_.rows.size());
+        for (size_t x = 0; x < ms_.rows.size(); ++x) rows_ascii_[x] = (uint8_t)"ACGTN"[ms_.rows[x]];
         launches += 2;
         // traceback
         recs_.assign((size_t)lay_.seg_rec_off.back(), Record{});
@@ -173,7 +181,7 @@ public:
                 return fetch_code(cbase + (size_t)i * g.NT * g.CW, g, seg_local, row, rowlen, k);
             };
             cnt_[s] = traceback_segment(n, jr_.data() + lay_.seg_j_off[s],
-                                        b.bases.data() + b.off[s0_ + s], ms_.rows.data(), ms_.row_off.data(),
+                                        b.text + b.off[s0_ + s], rows_ascii_.data(), ms_.row_off.data(),
                                         plan_.sc.ins, plan_.sc.del, plan_.sc.mismatch, plan_.sc.match, code_at,
                                         recs_.data() + lay_.seg_rec_off[s], n);
         }
@@ -194,7 +202,7 @@ private:
     Plan plan_; MonomerSet ms_;
     const Batch *batch_ = nullptr; int s0_ = 0, s1_ = 0;
     CtaLayout lay_;
-    std::vector<uint32_t> codes_; std::vector<JR> jr_; std::vector<Record> recs_; std::vector<int> cnt_;
+    std::vector<uint32_t> codes_; std::vector<JR> jr_; std::vector<uint8_t> rows_ascii_; std::vector<Record> recs_; std::vector<int> cnt_;
     bool overflowed_ = false;
 };
 

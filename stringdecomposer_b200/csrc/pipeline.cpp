@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstring>
 #include <fstream>
+#include <chrono>
 #include <thread>
 #include <unistd.h>
 
@@ -138,7 +139,11 @@ void Engine::decompose(const Batch &b, BatchResult &out)
             int s0 = bounds[d];
             const int s_end = bounds[d + 1];
             const int64_t budget = dev.wave_budget();
+            const bool prof = getenv("SD_PROFILE") != nullptr;
+            auto now = [] { return std::chrono::steady_clock::now(); };
+            auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
             while (s0 < s_end) {
+                const auto t0 = now();
                 // largest wave that fits the budget: grow geometrically, then shrink by bisection
                 int lo = std::min(s_end, s0 + plan_.g.NS), hi = s_end;
                 if (dev.wave_bytes(b, s0, hi) > budget) {
@@ -149,9 +154,14 @@ void Engine::decompose(const Batch &b, BatchResult &out)
                     }
                     hi = lo;
                 }
+                const auto t1 = now();
                 dev.stage(b, s0, hi);
+                const auto t2 = now();
                 dev.execute();
+                const auto t3 = now();
                 dev.fetch(part[d]);
+                const auto t4 = now();
+                if (prof) fprintf(stderr, "[sd_b200 profile] dev %d wave [%d,%d): plan %.3f stage %.3f execute %.3f fetch %.3f ms\n", d, s0, hi, ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4));
                 s0 = hi;
             }
         } catch (PlanError &e) { errs[d] = e.msg.empty() ? "error" : e.msg; }
@@ -182,6 +192,8 @@ void Engine::stage(const Batch &b)
 {
     if (b.nseg() == 0) throw PlanError{"nothing to stage"};
     staged_ = b;
+    if (staged_.own.empty() && b.nseg()) staged_.own.assign(b.text, b.text + b.off[b.nseg()]);   // outlive the caller's buffer
+    staged_.text = staged_.own.data();
     plan_for(staged_);
     split(staged_, staged_bounds_);
     for (int d = 0; d < ndev(); ++d) {
@@ -289,13 +301,14 @@ int run_files(const std::string &reads_path, const std::string &monomers_path, i
         b.off.reserve(segs.size() + 1); b.off.push_back(0);
         size_t total = 0;
         for (auto &s : segs) total += (size_t)s.second;
-        b.bases.resize(total);
+        b.own.resize(total);
         size_t o = 0;
         for (size_t s = 0; s < segs.size(); ++s) {
             const std::string &r = reads.seqs[seg_read[s]];
-            for (int x = 0; x < segs[s].second; ++x) b.bases[o + x] = (uint8_t)base_code(r[segs[s].first + x]);
+            memcpy(b.own.data() + o, r.data() + segs[s].first, (size_t)segs[s].second);
             o += (size_t)segs[s].second; b.off.push_back((int64_t)o);
         }
+        b.text = b.own.data();
         eng.decompose(b, res);
         if (getenv("SD_VERBOSE")) {
             const EngineStats &s = eng.stats;

@@ -19,6 +19,7 @@ struct SweepArgs {
     int seg_stride;
     int wps;                // warps per segment (FAST only, <= 4)
     int kstride;            // ints per key buffer
+    int *bad_symbol;        // set to 1 when a segment holds a symbol outside ACGTN
     TagRegs tr;             // TAGMASK / ONE of the policy, passed as run-time values (sweep_core.cuh: TagRegs)
 };
 
@@ -84,7 +85,11 @@ __global__ void sweep_kernel(const SweepArgs a)
             n = (int)(a.seg_off[first + s + 1] - o);
             src = a.bases + o;
         }
-        for (int x = tid; x < a.seg_stride; x += NT) schar[s * a.seg_stride + x] = (x < n) ? src[x] : (uint8_t)0;
+        for (int x = tid; x < a.seg_stride; x += NT) {
+            int code = (x < n) ? ascii_code(src[x]) : 0;
+            if (code > 4) { *a.bad_symbol = 1; code = 0; }
+            schar[s * a.seg_stride + x] = (uint8_t)code;
+        }
     }
     for (int x = tid; x < 3 * kstride; x += NT) skey[x] = INT_MIN;
     __syncthreads();

@@ -225,6 +225,9 @@ public:
         for (auto &e : ev_) SD_CUDA(cudaEventCreate(&e));
         SD_CUDA(cudaGetDeviceProperties(&prop_, dev_));
         if (prop_.major < 10) throw PlanError{"CUDA device is not sm_100 class: this library carries sm_100a code only"};
+        size_t fr = 0, tot = 0;
+        SD_CUDA(cudaMemGetInfo(&fr, &tot));
+        budget_ = std::min<int64_t>((int64_t)(fr * 0.85), (int64_t)96 << 30);
     }
     ~CudaBackend() override
     {
@@ -253,7 +256,11 @@ public:
         SD_CUDA(cudaMemcpyAsync(d_slotlen_.p, p.slot_len.data(), p.slot_len.size() * 4, cudaMemcpyHostToDevice, st_));
         SD_CUDA(cudaMemcpyAsync(d_slotend_.p, p.slot_endadd.data(), p.slot_endadd.size() * 4, cudaMemcpyHostToDevice, st_));
         d_rows_.need(ms.rows.size()); d_rowoff_.need(ms.row_off.size() * 4);
-        SD_CUDA(cudaMemcpyAsync(d_rows_.p, ms.rows.data(), ms.rows.size(), cudaMemcpyHostToDevice, st_));
+        rows_ascii_.resize(ms.rows.size());           // the traceback compares row and segment symbols as text
+        for (size_t x = 0; x < ms.rows.size(); ++x) rows_ascii_[x] = (uint8_t)"ACGTN"[ms.rows[x]];
+        SD_CUDA(cudaMemcpyAsync(d_rows_.p, rows_ascii_.data(), rows_ascii_.size(), cudaMemcpyHostToDevice, st_));
+        d_flag_.need(16);
+        SD_CUDA(cudaMemsetAsync(d_flag_.p, 0, 16, st_));
         SD_CUDA(cudaMemcpyAsync(d_rowoff_.p, ms.row_off.data(), ms.row_off.size() * 4, cudaMemcpyHostToDevice, st_));
         SD_CUDA(cudaStreamSynchronize(st_));
     }
@@ -266,11 +273,7 @@ public:
     int64_t wave_budget() const override
     {
         if (const char *e = getenv("SD_WAVE_BYTES")) return atoll(e);
-        size_t fr = 0, tot = 0;
-        cudaSetDevice(dev_);
-        if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) return (int64_t)8 << 30;
-        int64_t pool = (int64_t)(d_codes_.cap + d_scratch_.cap + d_dense_.cap);
-        return std::min<int64_t>((int64_t)((fr + pool) * 0.85), (int64_t)96 << 30);
+        return budget_;        // 85 % of the memory that was free when the backend was created (cudaMemGetInfo costs ms)
     }
 
     void stage(const Batch &b, int s0, int s1) override
@@ -294,7 +297,7 @@ public:
         d_scratch_.need((size_t)lay_.seg_rec_off.back() * sizeof(Record) + 16);
         d_counts_.need((size_t)nseg_ * 4 + 16); d_outoff_.need(((size_t)nseg_ + 1) * 8);
         SD_CUDA(cudaEventRecord(ev_[0], st_));
-        SD_CUDA(cudaMemcpyAsync(d_bases_.p, b.bases.data() + base, nb, cudaMemcpyHostToDevice, st_));
+        SD_CUDA(cudaMemcpyAsync(d_bases_.p, b.text + base, nb, cudaMemcpyHostToDevice, st_));
         SD_CUDA(cudaMemcpyAsync(d_segoff_.p, hoff_.data(), hoff_.size() * 8, cudaMemcpyHostToDevice, st_));
         SD_CUDA(cudaMemcpyAsync(d_ctanmax_.p, lay_.cta_nmax.data(), lay_.cta_nmax.size() * 4, cudaMemcpyHostToDevice, st_));
         SD_CUDA(cudaMemcpyAsync(d_ctacode_.p, lay_.cta_code_off.data(), lay_.cta_code_off.size() * 8, cudaMemcpyHostToDevice, st_));
@@ -318,6 +321,7 @@ public:
         a.nseg = nseg_;
         a.cta_nmax = d_ctanmax_.as<int>(); a.cta_code_off = d_ctacode_.as<int64_t>(); a.seg_j_off = d_segj_.as<int64_t>();
         a.codes = d_codes_.as<uint32_t>(); a.jr = d_jr_.as<JR>();
+        a.bad_symbol = d_flag_.as<int>();
         a.slot_len = d_slotlen_.as<int>(); a.slot_endadd = d_slotend_.as<int>();
         a.nslots = g.nslots; a.M = g.M; a.NS = g.NS; a.NT = g.NT; a.CW = g.CW; a.nsl = plan_.nsl; a.qp = plan_.qp;
         a.ins = plan_.sc.ins; a.del = plan_.sc.del; a.deadz = plan_.deadz;
@@ -347,7 +351,13 @@ public:
         traceback_kernel<<<(nseg_ + TB_WARPS - 1) / TB_WARPS, TB_WARPS * 32, 0, st_>>>(t);
         SD_CUDA(cudaGetLastError());
         SD_CUDA(cudaEventRecord(ev_[2], st_));
+        int flag = 0;
+        SD_CUDA(cudaMemcpyAsync(&flag, d_flag_.p, 4, cudaMemcpyDeviceToHost, st_));
         SD_CUDA(cudaStreamSynchronize(st_));
+        if (flag) {
+            SD_CUDA(cudaMemsetAsync(d_flag_.p, 0, 16, st_));
+            throw PlanError{"segment contains a symbol outside ACGTN"};
+        }
         float ms = 0;
         SD_CUDA(cudaEventElapsedTime(&ms, ev_[0], ev_[1])); sweep_ms += ms;
         SD_CUDA(cudaEventElapsedTime(&ms, ev_[1], ev_[2])); traceback_ms += ms;
@@ -395,9 +405,11 @@ private:
     int s0_ = 0, s1_ = 0, nseg_ = 0, nmax_ = 0;
     std::vector<int64_t> hoff_, houtoff_;
     std::vector<int> hcnt_;
+    std::vector<uint8_t> rows_ascii_;
+    int64_t budget_ = 0;
     DevBuf d_prof_, d_slotlen_, d_slotend_, d_rows_, d_rowoff_;
     DevBuf d_bases_, d_segoff_, d_ctanmax_, d_ctacode_, d_segj_, d_segrec_;
-    DevBuf d_codes_, d_jr_, d_scratch_, d_counts_, d_outoff_, d_dense_;
+    DevBuf d_flag_, d_codes_, d_jr_, d_scratch_, d_counts_, d_outoff_, d_dense_;
 };
 
 } // namespace
