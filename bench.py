@@ -236,6 +236,10 @@ def main():
     ws, rank, local = dist_setup(args.gpus)
     if args.impl == "reference":
         run_reference_arm(args, ws, rank)
+        if ws > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            dist.destroy_process_group()
         return
 
     import torch
