@@ -178,12 +178,18 @@ SD_HD uint32_t lane_post(uint32_t (&X)[C], const uint32_t (&pw)[C], uint32_t jum
     return (E | tr.mask3) ^ tr.one;
 }
 
-// Constant that turns the accumulated (U - h) digits of an n-cell word into the 2-bit codes (U + 1 - h).
-template <class P> constexpr uint32_t code_bias(int ncell)
+// Backpointer words hold the digits (U - h) in {-1..2} accumulated as w = w*4 + digit (mod 2^32); adding this
+// constant turns an n-cell word into the 2-bit codes (U + 1 - h).  The sweep stores the raw word; the decoder adds
+// the bias (one add per decoded cell in the traceback instead of one per word in the sweep).
+SD_HD uint32_t code_bias(int packed, int ncell)
 {
-    uint32_t v = 0;
-    for (int c = 0; c < ncell; ++c) v = v * 4u + 1u;
-    return v * P::ONE;
+    const uint32_t v = 0x55555555u >> (32 - 2 * ncell);       // (4^ncell - 1) / 3, ncell in 1..16
+    return v * (packed ? 0x00010001u : 1u);
+}
+// code of cell c (0-based) of an ncell-cell word; half = 16 for the reverse-complement row of a packed word
+SD_HD int decode_code(uint32_t w, int packed, int ncell, int c, int half)
+{
+    return (int)(((w + code_bias(packed, ncell)) >> (2 * (ncell - 1 - c) + half)) & 3u);
 }
 
 // Pass 2: run the deletion chain (prefix max) through the lane with the carry from the lanes on its left,
@@ -204,8 +210,7 @@ SD_HD void lane_pass2(uint32_t (&X)[C], uint32_t carryU, uint32_t *codes, TagReg
         ul = (h | tr.mask3) ^ tr.one;
         w = w * 4u + ul - h;                     // digits in {-1..2}; biased once per word below
         X[kk] = ul;
-        if ((kk + 1) % CPW == 0) { codes[kk / CPW] = w + code_bias<P>(CPW); w = 0; }
-        else if (kk == C - 1) { codes[kk / CPW] = w + code_bias<P>(C % CPW); w = 0; }
+        if ((kk + 1) % CPW == 0 || kk == C - 1) { codes[kk / CPW] = w; w = 0; }
     }
 }
 
@@ -226,8 +231,7 @@ SD_HD uint32_t lane_pass2_pre(uint32_t (&X)[C], uint32_t carryU, uint32_t *codes
         const uint32_t h = P::addmax(ul, tr.one, X[kk]);
         ul = (h | tr.mask3) ^ tr.one;
         w = w * 4u + ul - h;
-        if ((kk + 1) % CPW == 0) { codes[kk / CPW] = w + code_bias<P>(CPW); w = 0; }
-        else if (kk == C - 1) { codes[kk / CPW] = w + code_bias<P>(C % CPW); w = 0; }
+        if ((kk + 1) % CPW == 0 || kk == C - 1) { codes[kk / CPW] = w; w = 0; }     // unbiased digits; see decode_code()
         if (kk == 0) *u_first = ul;
         else X[kk] = P::addmax(uprev, pn[kk], (kk == C - 1 && kill_last) ? deadu : ul);
         uprev = ul;
@@ -292,8 +296,7 @@ SD_HD int fetch_code(const uint32_t *codes_col, const Geometry &g, int seg_local
     int ncell = g.C - wi * cpw; if (ncell > cpw) ncell = cpw;
     int tid = lane_tid(g.T, seg_local * g.nslots + slot, t);
     uint32_t w = codes_col[(size_t)tid * g.CW + wi];
-    int sh = 2 * (ncell - 1 - c) + ((g.packed && row >= g.M) ? 16 : 0);
-    return (int)((w >> sh) & 3u);
+    return decode_code(w, g.packed, ncell, c, (g.packed && row >= g.M) ? 16 : 0);
 }
 
 // Traceback of one segment from the 2-bit backpointers (reference main.cpp:217-267).

@@ -141,8 +141,6 @@ __global__ void sweep_kernel(const SweepArgs a)
     int jbase = a.ins;            // Bref + i*ins: J[i+1] = vmax + jbase
     int jump0 = 0;                // 4*(B[i] - Bref)
     uint32_t kboff = 0;           // byte offset of the key buffer in use (FAST: 2 buffers alternate; else 3 rotate)
-    int n_store = n_seg;          // columns whose backpointers are still to be written
-    int n_j = j_writer ? n_seg : 0;
 #pragma unroll 1
     for (int i = 0; i < nmax; ++i) {
         const uint32_t E = lane_post<P, C>(X, pw, P::splat(jump0 + 1), deadu, tr);
@@ -155,7 +153,8 @@ __global__ void sweep_kernel(const SweepArgs a)
         uint32_t ufirst;
         const uint32_t uend = lane_pass2_pre<P, C>(X, carry, cw, tr, pw, deadu, kill_last, &ufirst);
 
-        if (n_store > 0) {
+        const bool live = i < n_seg;                          // columns past the end of a shorter segment of the CTA are idle
+        if (live) {
             if (NW == 2) *reinterpret_cast<uint2 *>(cptr) = make_uint2(cw[0], cw[1]);
             else if (NW == 4) *reinterpret_cast<uint4 *>(cptr) = make_uint4(cw[0], cw[1], cw[2], cw[3]);
             else {
@@ -163,7 +162,6 @@ __global__ void sweep_kernel(const SweepArgs a)
                 for (int w = 0; w < NW; ++w) cptr[w] = cw[w];
             }
         }
-        --n_store;
         cptr += cstride;
 
         // row ends -> (score,row) key of the segment: key = (u >> 2) * 4096 + (endadd * 4096 + 4095 - row)
@@ -209,8 +207,7 @@ __global__ void sweep_kernel(const SweepArgs a)
         }
         const int vmax = k2 >> 12;
         ++jptr;
-        if (n_j > 0) *jptr = JR{vmax + jbase, SD_KEY_ROWS - 1 - (k2 & (SD_KEY_ROWS - 1))};
-        --n_j;
+        if (live && j_writer) *jptr = JR{vmax + jbase, SD_KEY_ROWS - 1 - (k2 & (SD_KEY_ROWS - 1))};
         jbase += a.ins;
         jump0 = 4 * (vmax + a.del);
         if (jump0 > SD_REBASE_TH || jump0 < -SD_REBASE_TH) {

@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(TB_WARPS * 32) traceback_kernel(const TbArgs a
                 const uint32_t w = rel == 0 ? w0 : rel == 1 ? w1 : w2;
                 const int cc = kk & (cpw - 1);
                 const int ncell = min(cpw, C - (wi << cshift));
-                code = (int)((w >> (2 * (ncell - 1 - cc) + half)) & 3u);
+                code = decode_code(w, g.packed, ncell, cc, half);
             }
             const bool stop = lane >= dcur && (!ok || code != 2);
             const unsigned ball = __ballot_sync(0xffffffffu, stop);
