@@ -18,10 +18,13 @@ bool &bad_symbol() { static thread_local bool f = false; return f; }
 
 template <class P, int C, int T>
 void emu_cta(const Plan &p, const Batch &b, int seg_first, int nseg_cta, int nmax,
-             uint32_t *codes, JR *const *jr)
+             uint32_t *const *codes, JR *const *jr)
 {
+    // NG == 1: one CTA of NT threads, `codes[0]` its backpointer block.  NG > 1: the NG CTAs that share the segment are
+    // emulated side by side (thread tid belongs to group tid / NT); the only coupling between them is the column key.
     const Geometry &g = p.g;
-    const int NT = g.NT, NS = g.NS;
+    const int NTC = g.NT, NS = g.NS, NG = g.NG;
+    const int NT = NTC * NG;
     constexpr int SPW = 32 / T;
     const uint32_t deadu = P::splat(p.deadz - 1);
     std::vector<uint32_t> Xall((size_t)NT * C, deadu), PWall((size_t)NT * C, 0u);
@@ -34,12 +37,19 @@ void emu_cta(const Plan &p, const Batch &b, int seg_first, int nseg_cta, int nma
     struct LaneId { bool ok; int seg_local, slot, t, sl; bool active; int n; };
     auto lane_id = [&](int tid) {
         LaneId l;
-        const int warp = tid / 32, lane = tid % 32, siw = lane / T;
+        const int grp = tid / NTC, tin = tid % NTC;
+        const int warp = tin / 32, lane = tin % 32, siw = lane / T;
         l.t = lane - siw * T;
         l.ok = siw < SPW;
         const int ginst = warp * SPW + (l.ok ? siw : 0);
-        l.seg_local = ginst / g.nslots; l.slot = ginst % g.nslots;
-        l.active = l.ok && l.seg_local < NS && l.seg_local < nseg_cta;
+        if (NG > 1) {
+            l.seg_local = 0; l.slot = grp * g.SG + ginst;
+            l.active = l.ok && ginst < g.SG && l.slot < g.nslots && nseg_cta > 0;
+            if (l.slot >= g.nslots) l.slot = g.nslots - 1;
+        } else {
+            l.seg_local = ginst / g.nslots; l.slot = ginst % g.nslots;
+            l.active = l.ok && l.seg_local < NS && l.seg_local < nseg_cta;
+        }
         if (l.seg_local >= NS) l.seg_local = 0;
         l.sl = l.slot * T + l.t;
         l.n = (l.seg_local < nseg_cta) ? b.len(seg_first + l.seg_local) : 0;
@@ -78,7 +88,7 @@ void emu_cta(const Plan &p, const Batch &b, int seg_first, int nseg_cta, int nma
             uend[tid] = lane_pass2_pre<P, C>(X[tid], carry[tid], cw, tag_regs<P>(), PW[tid], deadu,
                                              l.t == T - 1 && p.slot_len[l.slot] == 1, &ufirst[tid]);
             if (l.active && i < l.n)
-                for (int w = 0; w < g.CW; ++w) codes[((size_t)i * NT + tid) * g.CW + w] = cw[w];
+                for (int w = 0; w < g.CW; ++w) codes[tid / NTC][((size_t)i * NTC + tid % NTC) * g.CW + w] = cw[w];
             if (l.active && l.t == T - 1) {
                 const uint32_t u = uend[tid];
                 int k0 = make_key(P::lo(u), p.slot_endadd[l.slot], l.slot);
@@ -111,7 +121,7 @@ void emu_cta(const Plan &p, const Batch &b, int seg_first, int nseg_cta, int nma
     }
 }
 
-template <class P> using CtaFn = void (*)(const Plan &, const Batch &, int, int, int, uint32_t *, JR *const *);
+template <class P> using CtaFn = void (*)(const Plan &, const Batch &, int, int, int, uint32_t *const *, JR *const *);
 
 template <class P, int C> CtaFn<P> pick_t(int T)
 {
@@ -156,13 +166,16 @@ public:
         const int nseg = s1_ - s0_, nctas = (int)lay_.cta_nmax.size();
         EmuFlags::overflow() = false;
         bad_symbol() = false;
-        for (int c = 0; c < nctas; ++c) {
-            int first = c * g.NS, cnt = std::min(g.NS, nseg - first);
+        const int nunits = g.NG > 1 ? nseg : nctas;          // group mode: one emulated unit per segment (all its CTAs)
+        for (int c = 0; c < nunits; ++c) {
+            int first = g.NG > 1 ? c : c * g.NS, cnt = g.NG > 1 ? 1 : std::min(g.NS, nseg - first);
             std::vector<JR *> jp(g.NS, nullptr);
             for (int s = 0; s < cnt; ++s) jp[s] = jr_.data() + lay_.seg_j_off[first + s];
-            uint32_t *codes = codes_.data() + lay_.cta_code_off[c];
-            if (g.packed) pick<Packed16>(g.C, g.T)(plan_, b, s0_ + first, cnt, lay_.cta_nmax[c], codes, jp.data());
-            else pick<Scalar32>(g.C, g.T)(plan_, b, s0_ + first, cnt, lay_.cta_nmax[c], codes, jp.data());
+            std::vector<uint32_t *> cp(g.NG);
+            for (int q = 0; q < g.NG; ++q) cp[q] = codes_.data() + lay_.cta_code_off[g.NG > 1 ? c * g.NG + q : c];
+            const int nmax = lay_.cta_nmax[g.NG > 1 ? c * g.NG : c];
+            if (g.packed) pick<Packed16>(g.C, g.T)(plan_, b, s0_ + first, cnt, nmax, cp.data(), jp.data());
+            else pick<Scalar32>(g.C, g.T)(plan_, b, s0_ + first, cnt, nmax, cp.data(), jp.data());
         }
         overflowed_ = g.packed && EmuFlags::overflow();
         if (bad_symbol()) throw PlanError{"segment contains a symbol outside ACGTN"};
@@ -174,11 +187,13 @@ public:
         recs_.assign((size_t)lay_.seg_rec_off.back(), Record{});
         cnt_.assign(nseg, 0);
         for (int s = 0; s < nseg; ++s) {
-            const int cta = s / g.NS, seg_local = s % g.NS, n = b.len(s0_ + s);
+            const int n = b.len(s0_ + s);
             if (n == 0) continue;
-            const uint32_t *cbase = codes_.data() + lay_.cta_code_off[cta];
             auto code_at = [&](int i, int row, int rowlen, int k) {
-                return fetch_code(cbase + (size_t)i * g.NT * g.CW, g, seg_local, row, rowlen, k);
+                const RowPlace pl = place_row(g, g.NG > 1 ? 0 : s % g.NS, row);
+                const int cta = g.NG > 1 ? s * g.NG + pl.grp : s / g.NS;
+                const uint32_t *cbase = codes_.data() + lay_.cta_code_off[cta];
+                return fetch_code(cbase + (size_t)i * g.NT * g.CW, g, pl, rowlen, k);
             };
             cnt_[s] = traceback_segment(n, jr_.data() + lay_.seg_j_off[s],
                                         b.text + b.off[s0_ + s], rows_ascii_.data(), ms_.row_off.data(),

@@ -149,10 +149,33 @@ Plan make_plan(const MonomerSet &ms, const Scoring &sc, int max_seg_len, int64_t
             if (cost < best) { best = cost; bestC = C; bestT = T; bestNS = NS; bestNT = NT; }
         }
     }
-    if (!bestC) throw PlanError{"monomer set does not fit one CTA (rows*lanes > 1024 threads or profile > shared memory); "
-                                "the cluster sweep for large monomer sets is not built yet"};
     Geometry &g = p.g;
+    g.NG = 1;
+    int force_sg = 0;
+    if (const char *e = getenv("SD_GROUP_SLOTS")) force_sg = atoi(e);
+    if (!bestC || force_sg > 0) {
+        // The monomer set does not fit one CTA (threads, registers or the shared-memory profile table): split the slots
+        // into NG groups, one CTA each; the per-column key then meets in global memory (sweep_group_kernel).
+        int gC = 0, gT = 0;
+        for (int C : kC) for (int T : kT) {
+            if (fC && (C != fC || T != fT)) continue;
+            if (C * T < ms.Lmax || (C > 24 && !need_big && !fC)) continue;
+            if (!gC || C * T < gC * gT || (C * T == gC * gT && C > gC)) { gC = C; gT = T; }
+        }
+        if (!gC) throw PlanError{"monomers longer than 1536 bp are not supported by this build"};
+        const int spw = 32 / gT, qpc = (gC / 4) | 1;
+        const size_t per_slot = (size_t)5 * qpc * gT * 16;
+        int sg = (int)std::min<size_t>((size_t)(90 * 1024) / per_slot, (size_t)(384 / 32) * spw);
+        sg = std::max(sg / spw * spw, spw);
+        if (force_sg > 0) sg = std::max(force_sg / spw * spw, spw);
+        sg = std::min(sg, (nslots + spw - 1) / spw * spw);
+        bestC = gC; bestT = gT; bestNS = 1; bestNT = (sg + spw - 1) / spw * 32;
+        g.NG = (nslots + sg - 1) / sg;
+        g.SG = sg;
+        if (g.NG == 1) g.SG = nslots;
+    }
     g.packed = packed; g.C = bestC; g.T = bestT; g.nslots = nslots; g.M = ms.M; g.NS = bestNS; g.NT = bestNT;
+    if (g.NG == 1) g.SG = nslots;
     const int cpw = packed ? 8 : 16;
     g.CW = (g.C + cpw - 1) / cpw;
     p.nsl = nslots * g.T;
@@ -190,14 +213,16 @@ CtaLayout make_cta_layout(const Plan &p, const Batch &b, int seg_begin, int seg_
     CtaLayout l;
     const Geometry &g = p.g;
     const int nseg = seg_end - seg_begin;
-    const int nctas = (nseg + g.NS - 1) / g.NS;
+    // logical CTAs: NG == 1: one per NS segments; NG > 1: CTA seg*NG + grp sweeps slot group grp of segment seg
+    const int nctas = g.NG > 1 ? nseg * g.NG : (nseg + g.NS - 1) / g.NS;
     l.cta_nmax.assign(nctas, 0);
     l.cta_code_off.assign(nctas + 1, 0);
     l.seg_j_off.assign(nseg + 1, 0);
     l.seg_rec_off.assign(nseg + 1, 0);
     for (int s = 0; s < nseg; ++s) {
         int n = b.len(seg_begin + s);
-        l.cta_nmax[s / g.NS] = std::max(l.cta_nmax[s / g.NS], n);
+        if (g.NG > 1) for (int q = 0; q < g.NG; ++q) l.cta_nmax[s * g.NG + q] = n;
+        else l.cta_nmax[s / g.NS] = std::max(l.cta_nmax[s / g.NS], n);
         l.seg_j_off[s + 1] = l.seg_j_off[s] + n + 1;
         l.seg_rec_off[s + 1] = l.seg_rec_off[s] + n;
     }

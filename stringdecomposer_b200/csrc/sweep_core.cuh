@@ -274,6 +274,8 @@ struct Geometry {
     int NS;          // segments per CTA
     int NT;          // threads per CTA
     int CW;          // backpointer words per lane per column
+    int NG;          // CTAs (slot groups) that share one segment; 1 = the whole monomer set fits one CTA
+    int SG;          // slots per group (== nslots when NG == 1)
 };
 
 struct Record { int32_t row, start, end, score; };
@@ -284,19 +286,31 @@ struct JR { int32_t j, row; };      // per column i: J[i] = max_r H[i-1][r][last
 SD_HD int slots_per_warp(int T) { return 32 / T; }
 SD_HD int lane_tid(int T, int ginst, int t) { const int spw = 32 / T; return (ginst / spw) * 32 + (ginst % spw) * T + t; }
 
-// Decode the backpointer of cell k (k>=1... any k inside the row) of `row` in column i of a segment.
-// codes_col points at the first word of column i of the CTA that owns the segment.
-SD_HD int fetch_code(const uint32_t *codes_col, const Geometry &g, int seg_local, int row, int rowlen, int k)
+// Where the backpointers of DP row `row` live: the slot, the group (CTA) that owns it when the monomer set is split
+// over several CTAs, the slot instance inside that CTA, and the half of the packed word.
+struct RowPlace { int grp, ginst, half; };
+SD_HD RowPlace place_row(const Geometry &g, int seg_local, int row)
 {
-    int slot = g.packed ? (row < g.M ? row : row - g.M) : row;
+    RowPlace r;
+    const int slot = g.packed ? (row < g.M ? row : row - g.M) : row;
+    r.half = (g.packed && row >= g.M) ? 16 : 0;
+    r.grp = slot / g.SG;
+    r.ginst = (g.NG > 1) ? slot - r.grp * g.SG : seg_local * g.nslots + slot;
+    return r;
+}
+
+// Decode the backpointer of cell k of a row placed at `pl`; codes_col points at the first word of column i of the
+// CTA that owns the row.
+SD_HD int fetch_code(const uint32_t *codes_col, const Geometry &g, RowPlace pl, int rowlen, int k)
+{
     int pos = (rowlen == 1) ? (g.C * g.T - 1) : k;     // length-1 rows are right-aligned in their slot
     int t = pos / g.C, kk = pos - t * g.C;
     int cpw = g.packed ? 8 : 16;
     int wi = kk / cpw, c = kk - wi * cpw;
     int ncell = g.C - wi * cpw; if (ncell > cpw) ncell = cpw;
-    int tid = lane_tid(g.T, seg_local * g.nslots + slot, t);
+    int tid = lane_tid(g.T, pl.ginst, t);
     uint32_t w = codes_col[(size_t)tid * g.CW + wi];
-    return decode_code(w, g.packed, ncell, c, (g.packed && row >= g.M) ? 16 : 0);
+    return decode_code(w, g.packed, ncell, c, pl.half);
 }
 
 // Traceback of one segment from the 2-bit backpointers (reference main.cpp:217-267).

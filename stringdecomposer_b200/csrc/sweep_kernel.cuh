@@ -219,6 +219,166 @@ __global__ void sweep_kernel(const SweepArgs a)
 }
 
 
+// ---------------------------------------------------------------------------------------------------------------
+// Group sweep: monomer sets that do not fit one CTA (threads, registers, or the shared-memory profile table).
+// The slots are split into NG groups; CTA (gslot, grp) sweeps slot group `grp` of the segments gslot, gslot+ngslots, ...
+// and the NG CTAs of a segment meet once per column in global memory: atomicMax on the (score,row) key, an arrival
+// counter, and a bounded spin.  All CTAs are co-resident (cooperative launch), so the spin cannot deadlock; a
+// time-out raises *error instead of hanging.
+struct GroupArgs {
+    const uint4 *prof; int nsl_total, qp;              // [5][nsl_total][qp] uint4
+    const uint8_t *bases; const int64_t *seg_off; int nseg;
+    const int64_t *cta_code_off; const int64_t *seg_j_off;
+    uint32_t *codes; JR *jr;
+    const int *slot_len; const int *slot_endadd;
+    int nslots, M, NT, CW, NG, SG;
+    int ins, del, deadz;
+    int seg_stride;
+    TagRegs tr;
+    int *bad_symbol;
+    int *gkey; unsigned *gcnt;                          // [ngslots][4]
+    int ngslots;
+    int *error;
+};
+
+template <class P, int C, int T>
+__global__ void sweep_group_kernel(const GroupArgs a)
+{
+    extern __shared__ uint4 smem_u4[];
+    constexpr int SPW = 32 / T;
+    const int NT = a.NT, NG = a.NG;
+    const int sgt = (NT / 32) * SPW * T;                // profile rows kept per CTA (slot lanes)
+    uint4 *sprof = smem_u4;                             // [5][sgt][qp]
+    int *swk = reinterpret_cast<int *>(sprof + (size_t)5 * sgt * a.qp);     // [32] warp keys, [32] = global key
+    uint8_t *schar = reinterpret_cast<uint8_t *>(swk + 36);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = NT >> 5;
+    const int gslot = blockIdx.x / NG, grp = blockIdx.x - gslot * NG;
+    const int siw = lane / T, t = lane - siw * T;
+    const bool lane_ok = siw < SPW;
+    const int ginst = warp * SPW + (lane_ok ? siw : 0);
+    int slot = grp * a.SG + ginst;
+    const bool active = lane_ok && ginst < a.SG && slot < a.nslots;
+    if (slot >= a.nslots) slot = a.nslots - 1;
+
+    // profile slice of this group: rows [grp*SG*T, grp*SG*T + sgt) of every symbol (clamped at the table end)
+    for (int x = tid; x < 5 * sgt * a.qp; x += NT) {
+        const int sym = x / (sgt * a.qp), r = x - sym * (sgt * a.qp);
+        const int row = min(grp * a.SG * T + r / a.qp, a.nsl_total - 1);
+        sprof[x] = a.prof[((size_t)sym * a.nsl_total + row) * a.qp + (r % a.qp)];
+    }
+    const int L = a.slot_len[slot];
+    const int endadd = a.slot_endadd[slot];
+    const uint32_t deadu = P::splat(a.deadz - 1);
+    const TagRegs tr = a.tr;
+    const bool kill_first = (t == 0), kill_last = (t == T - 1 && L == 1);
+    const bool is_end = active && t == T - 1;
+    const bool j_writer = grp == 0 && tid == 0;
+    const int kc_lo = key_const(endadd, slot), kc_hi = key_const(endadd, a.M + slot);
+    const uint4 *myprof = sprof + (size_t)(ginst * T + t) * a.qp;
+    const int sym_stride = sgt * a.qp;
+    int srcl[T > 2 ? T - 2 : 1];
+#pragma unroll
+    for (int d = 1; d <= T - 2; ++d) srcl[d - 1] = lane - min(d, t);
+    int *gkey = a.gkey + gslot * 4;
+    unsigned *gcnt = a.gcnt + gslot * 4;
+    unsigned gcol = 0;                                   // columns this CTA group has exchanged so far
+
+    uint32_t X[C], pw[C];
+    auto load_profile = [&](int sym) {
+        const uint4 *pp = myprof + sym * sym_stride;
+#pragma unroll
+        for (int q = 0; q < C / 4; ++q) {
+            const uint4 v = pp[q];
+            pw[4 * q] = v.x; pw[4 * q + 1] = v.y; pw[4 * q + 2] = v.z; pw[4 * q + 3] = v.w;
+        }
+    };
+
+    for (int seg = gslot; seg < a.nseg; seg += a.ngslots) {
+        const int64_t o = a.seg_off[seg];
+        const int n = (int)(a.seg_off[seg + 1] - o);
+        __syncthreads();                                 // previous segment's symbols no longer needed
+        for (int x = tid; x < a.seg_stride; x += NT) {
+            int code = (x < n) ? ascii_code(a.bases[o + x]) : 0;
+            if (code > 4) { *a.bad_symbol = 1; code = 0; }
+            schar[x] = (uint8_t)code;
+        }
+        __syncthreads();
+        JR *jptr = a.jr + a.seg_j_off[seg];
+        uint32_t *cptr = a.codes + a.cta_code_off[(size_t)seg * NG + grp] + (size_t)tid * a.CW;
+        const size_t cstride = (size_t)NT * a.CW;
+        const uint8_t *cp = schar;
+#pragma unroll
+        for (int kk = 0; kk < C; ++kk) X[kk] = deadu;
+        load_profile(*cp++);
+        if (t == 0 && L > 1) pw[0] = P::add(pw[0], P::splat(4 * a.del));
+        if (t == T - 1 && L == 1) pw[C - 1] = P::add(pw[C - 1], P::splat(4 * a.del));
+        lane_pre<P, C>(X, deadu, pw, deadu, kill_first, kill_last);
+        int jbase = a.ins, jump0 = 0;
+#pragma unroll 1
+        for (int i = 0; i < n; ++i) {
+            const uint32_t E = lane_post<P, C>(X, pw, P::splat(jump0 + 1), deadu, tr);
+            load_profile(*cp++);
+            const uint32_t carry = slot_scan<P, T>(E, t, srcl, deadu);
+            constexpr int NW = (C + P::CELLS_PER_WORD - 1) / P::CELLS_PER_WORD;
+            uint32_t cw[NW];
+            uint32_t ufirst;
+            const uint32_t uend = lane_pass2_pre<P, C>(X, carry, cw, tr, pw, deadu, kill_last, &ufirst);
+            if (active) {
+#pragma unroll
+                for (int w = 0; w < NW; ++w) cptr[w] = cw[w];
+            }
+            cptr += cstride;
+            int key;
+            if (P::ROWS == 2) {
+                const int klo = ((int)(uend << 16) >> 18) * SD_KEY_ROWS + kc_lo;
+                const int khi = ((int)uend >> 18) * SD_KEY_ROWS + kc_hi;
+                key = max(klo, khi);
+            } else {
+                key = ((int)uend >> 2) * SD_KEY_ROWS + kc_lo;
+            }
+            if (!is_end) key = INT_MIN;
+            const int wk = __reduce_max_sync(0xffffffffu, key);
+            if (lane == 0) swk[warp] = wk;
+            uint32_t prevU = deadu;
+            if (T > 1) { prevU = __shfl_up_sync(0xffffffffu, uend, 1); if (t == 0) prevU = deadu; }
+            X[0] = lane_pre_first<P>(prevU, pw[0], ufirst, deadu, kill_first, C == 1 && kill_last);
+#pragma unroll
+            for (int kk = 0; kk < C; ++kk) asm volatile("" ::"r"(X[kk]));
+            __syncthreads();
+            if (tid == 0) {
+                int k = swk[0];
+                for (int w = 1; w < nwarps; ++w) k = max(k, swk[w]);
+                const unsigned b = gcol & 3u;
+                if (grp == 0) { *(volatile int *)(gkey + ((gcol + 2u) & 3u)) = INT_MIN; __threadfence(); }
+                atomicMax(gkey + b, k);
+                __threadfence();
+                atomicAdd(gcnt + b, 1u);
+                const unsigned target = (unsigned)NG * ((gcol >> 2) + 1u);
+                unsigned spins = 0;
+                while (*(volatile unsigned *)(gcnt + b) < target) {
+                    if (++spins > (1u << 21)) { *a.error = 1; break; }
+                }
+                __threadfence();
+                swk[32] = *(volatile int *)(gkey + b);
+            }
+            __syncthreads();
+            const int k2 = swk[32];
+            ++gcol;
+            const int vmax = k2 >> 12;
+            ++jptr;
+            if (j_writer) *jptr = JR{vmax + jbase, SD_KEY_ROWS - 1 - (k2 & (SD_KEY_ROWS - 1))};
+            jbase += a.ins;
+            jump0 = 4 * (vmax + a.del);
+            if (jump0 > SD_REBASE_TH || jump0 < -SD_REBASE_TH) {
+                lane_rebase<P, C>(X, jump0);
+                jbase += jump0 >> 2;
+                jump0 = 0;
+            }
+        }
+    }
+}
+
 // lookup tables of the instantiations, one translation unit per (policy, FAST, MULTI) so that they build in parallel
 const void *sweep_lookup_p16_f1_m0(int C, int T);
 const void *sweep_lookup_p16_f1_m1(int C, int T);
@@ -226,6 +386,8 @@ const void *sweep_lookup_p16_f0_m0(int C, int T);
 const void *sweep_lookup_s32_f1_m0(int C, int T);
 const void *sweep_lookup_s32_f1_m1(int C, int T);
 const void *sweep_lookup_s32_f0_m0(int C, int T);
+const void *sweep_group_lookup_p16(int C, int T);
+const void *sweep_group_lookup_s32(int C, int T);
 
 #define SD_INSTANTIATE_SWEEP(NAME, POLICY, FAST, LL)                                                                 \
     template <int C> static const void *NAME##_t(int T)                                                              \
@@ -238,6 +400,30 @@ const void *sweep_lookup_s32_f0_m0(int C, int T);
         case 10: return (const void *)sweep_kernel<POLICY, C, 10, FAST, LL>;                                          \
         case 16: return (const void *)sweep_kernel<POLICY, C, 16, FAST, LL>;                                          \
         case 32: return (const void *)sweep_kernel<POLICY, C, 32, FAST, LL>;                                          \
+        }                                                                                                             \
+        return nullptr;                                                                                               \
+    }                                                                                                                 \
+    const void *NAME(int C, int T)                                                                                    \
+    {                                                                                                                 \
+        switch (C) {                                                                                                  \
+        case 8: return NAME##_t<8>(T); case 12: return NAME##_t<12>(T); case 16: return NAME##_t<16>(T);              \
+        case 20: return NAME##_t<20>(T); case 24: return NAME##_t<24>(T); case 32: return NAME##_t<32>(T);            \
+        case 48: return NAME##_t<48>(T);                                                                              \
+        }                                                                                                             \
+        return nullptr;                                                                                               \
+    }
+
+#define SD_INSTANTIATE_GROUP(NAME, POLICY)                                                                           \
+    template <int C> static const void *NAME##_t(int T)                                                              \
+    {                                                                                                                 \
+        switch (T) {                                                                                                  \
+        case 1: return (const void *)sweep_group_kernel<POLICY, C, 1>;                                                \
+        case 2: return (const void *)sweep_group_kernel<POLICY, C, 2>;                                                \
+        case 4: return (const void *)sweep_group_kernel<POLICY, C, 4>;                                                \
+        case 8: return (const void *)sweep_group_kernel<POLICY, C, 8>;                                                \
+        case 10: return (const void *)sweep_group_kernel<POLICY, C, 10>;                                              \
+        case 16: return (const void *)sweep_group_kernel<POLICY, C, 16>;                                              \
+        case 32: return (const void *)sweep_group_kernel<POLICY, C, 32>;                                              \
         }                                                                                                             \
         return nullptr;                                                                                               \
     }                                                                                                                 \

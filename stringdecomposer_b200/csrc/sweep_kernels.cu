@@ -58,12 +58,11 @@ __global__ void __launch_bounds__(TB_WARPS * 32) traceback_kernel(const TbArgs a
     if (s >= a.nseg) return;
     const int lane = threadIdx.x & 31;
     const Geometry g = a.g;
-    const int cta = s / g.NS, seg_local = s % g.NS;
+    const int cta0 = g.NG > 1 ? s * g.NG : s / g.NS, seg_local = g.NG > 1 ? 0 : s % g.NS;
     const int64_t o = a.seg_off[s];
     const int n = (int)(a.seg_off[s + 1] - o);
     const uint8_t *seg = a.bases + o;
     const JR *jr = a.jr + a.seg_j_off[s];
-    const uint32_t *cbase = a.codes + a.cta_code_off[cta];
     const size_t cstride = (size_t)g.NT * g.CW;
     const int C = g.C, CW = g.CW, cshift = g.packed ? 3 : 4, cpw = 1 << cshift, invC = a.invC;
     const int maxwl = g.T * CW - 1;
@@ -96,9 +95,10 @@ __global__ void __launch_bounds__(TB_WARPS * 32) traceback_kernel(const TbArgs a
             if (r != row0 || i > i0 || i <= i0 - 32) {
                 // refill: lane d loads the words around cell k-d of column i-d
                 i0 = i; row0 = r;
-                const int slot = g.packed ? (r < g.M ? r : r - g.M) : r;
-                half = (g.packed && r >= g.M) ? 16 : 0;
-                const size_t word0 = (size_t)lane_tid(g.T, seg_local * g.nslots + slot, 0) * CW;
+                const RowPlace pl = place_row(g, seg_local, r);
+                half = pl.half;
+                const uint32_t *cbase = a.codes + a.cta_code_off[cta0 + (g.NG > 1 ? pl.grp : 0)];
+                const size_t word0 = (size_t)lane_tid(g.T, pl.ginst, 0) * CW;
                 const int c = i - lane;
                 colok = c >= 0;
                 if (colok) {
@@ -245,7 +245,8 @@ public:
         const int spw = 32 / g.T;
         fast_ = (g.nslots % spw == 0) && (g.nslots / spw <= 4) && g.NS <= 15;     // 15 named barriers besides barrier 0
         if (getenv("SD_NOFAST")) fast_ = false;
-        kernel_ = kern(g.packed, g.C, g.T, fast_, fast_ && g.NS > 1);
+        kernel_ = g.NG > 1 ? (g.packed ? sweep_group_lookup_p16(g.C, g.T) : sweep_group_lookup_s32(g.C, g.T))
+                           : kern(g.packed, g.C, g.T, fast_, fast_ && g.NS > 1);
         if (!kernel_) throw PlanError{"no sweep kernel compiled for this geometry"};
         cudaFuncAttributes fa;
         SD_CUDA(cudaFuncGetAttributes(&fa, kernel_));
@@ -311,9 +312,8 @@ public:
         (void)g;
     }
 
-    void execute() override
+    void launch_single(int seg_stride)
     {
-        SD_CUDA(cudaSetDevice(dev_));
         const Geometry &g = plan_.g;
         SweepArgs a;
         a.prof = d_prof_.as<uint4>(); a.prof_u4 = (int)(plan_.prof.size() / 4);
@@ -325,23 +325,63 @@ public:
         a.slot_len = d_slotlen_.as<int>(); a.slot_endadd = d_slotend_.as<int>();
         a.nslots = g.nslots; a.M = g.M; a.NS = g.NS; a.NT = g.NT; a.CW = g.CW; a.nsl = plan_.nsl; a.qp = plan_.qp;
         a.ins = plan_.sc.ins; a.del = plan_.sc.del; a.deadz = plan_.deadz;
-        a.seg_stride = (nmax_ + 16) / 16 * 16;
+        a.seg_stride = seg_stride;
         const int spw = 32 / g.T;
         a.wps = fast_ ? g.nslots / spw : 1;
         a.kstride = fast_ ? g.NS * 4 : (g.NS + 3) / 4 * 4;
         a.tr = g.packed ? tag_regs<Packed16>() : tag_regs<Scalar32>();
-        const int kstride = a.kstride;
-        const size_t smem = plan_.prof.size() * 4 + (size_t)3 * kstride * 4 + (size_t)g.NS * a.seg_stride;
+        const size_t smem = plan_.prof.size() * 4 + (size_t)3 * a.kstride * 4 + (size_t)g.NS * a.seg_stride;
         if (smem > (size_t)prop_.sharedMemPerBlockOptin) throw PlanError{"sweep geometry needs more shared memory than the SM has"};
         SD_CUDA(cudaFuncSetAttribute(kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int nctas = (int)lay_.cta_nmax.size();
         void *args[] = {(void *)&a};
-        SD_CUDA(cudaEventRecord(ev_[0], st_));
         SD_CUDA(cudaLaunchKernel(kernel_, dim3(nctas), dim3(g.NT), args, smem, st_));
+    }
+
+    void launch_group(int seg_stride)
+    {
+        const Geometry &g = plan_.g;
+        GroupArgs a;
+        a.prof = d_prof_.as<uint4>(); a.nsl_total = plan_.nsl; a.qp = plan_.qp;
+        a.bases = d_bases_.as<uint8_t>(); a.seg_off = d_segoff_.as<int64_t>(); a.nseg = nseg_;
+        a.cta_code_off = d_ctacode_.as<int64_t>(); a.seg_j_off = d_segj_.as<int64_t>();
+        a.codes = d_codes_.as<uint32_t>(); a.jr = d_jr_.as<JR>();
+        a.slot_len = d_slotlen_.as<int>(); a.slot_endadd = d_slotend_.as<int>();
+        a.nslots = g.nslots; a.M = g.M; a.NT = g.NT; a.CW = g.CW; a.NG = g.NG; a.SG = g.SG;
+        a.ins = plan_.sc.ins; a.del = plan_.sc.del; a.deadz = plan_.deadz;
+        a.seg_stride = seg_stride;
+        a.tr = g.packed ? tag_regs<Packed16>() : tag_regs<Scalar32>();
+        a.bad_symbol = d_flag_.as<int>(); a.error = d_flag_.as<int>() + 1;
+        const int spw = 32 / g.T;
+        const size_t sgt = (size_t)(g.NT / 32) * spw * g.T;
+        const size_t smem = (size_t)5 * sgt * plan_.qp * 16 + 36 * 4 + (size_t)seg_stride;
+        if (smem > (size_t)prop_.sharedMemPerBlockOptin) throw PlanError{"group sweep needs more shared memory than the SM has"};
+        SD_CUDA(cudaFuncSetAttribute(kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        SD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel_, g.NT, smem));
+        const int capacity = per_sm * prop_.multiProcessorCount;
+        if (capacity < g.NG) throw PlanError{"monomer set too large: the CTAs of one segment cannot be co-resident on this GPU"};
+        a.ngslots = std::min(nseg_, capacity / g.NG);
+        d_xchg_.need((size_t)a.ngslots * 4 * 8);
+        a.gkey = d_xchg_.as<int>(); a.gcnt = reinterpret_cast<unsigned *>(d_xchg_.as<int>() + (size_t)a.ngslots * 4);
+        SD_CUDA(cudaMemsetAsync(a.gkey, 0x80, (size_t)a.ngslots * 4 * 4, st_));       // very negative keys
+        SD_CUDA(cudaMemsetAsync(a.gcnt, 0, (size_t)a.ngslots * 4 * 4, st_));
+        void *args[] = {(void *)&a};
+        SD_CUDA(cudaLaunchCooperativeKernel(kernel_, dim3(a.ngslots * g.NG), dim3(g.NT), args, smem, st_));
+    }
+
+    void execute() override
+    {
+        SD_CUDA(cudaSetDevice(dev_));
+        const Geometry &g = plan_.g;
+        const int seg_stride = (nmax_ + 16) / 16 * 16;
+        SD_CUDA(cudaEventRecord(ev_[0], st_));
+        if (g.NG > 1) launch_group(seg_stride); else launch_single(seg_stride);
         SD_CUDA(cudaEventRecord(ev_[1], st_));
         TbArgs t;
-        t.g = g; t.codes = a.codes; t.cta_code_off = a.cta_code_off; t.jr = a.jr; t.seg_j_off = a.seg_j_off;
-        t.bases = a.bases; t.seg_off = a.seg_off; t.nseg = nseg_;
+        t.g = g; t.codes = d_codes_.as<uint32_t>(); t.cta_code_off = d_ctacode_.as<int64_t>(); t.jr = d_jr_.as<JR>();
+        t.seg_j_off = d_segj_.as<int64_t>();
+        t.bases = d_bases_.as<uint8_t>(); t.seg_off = d_segoff_.as<int64_t>(); t.nseg = nseg_;
         t.rows = d_rows_.as<uint8_t>(); t.row_off = d_rowoff_.as<int>();
         t.ins = plan_.sc.ins; t.del = plan_.sc.del; t.mismatch = plan_.sc.mismatch; t.match = plan_.sc.match;
         t.scratch = d_scratch_.as<Record>(); t.seg_rec_off = d_segrec_.as<int64_t>(); t.counts = d_counts_.as<int>();
@@ -351,11 +391,12 @@ public:
         traceback_kernel<<<(nseg_ + TB_WARPS - 1) / TB_WARPS, TB_WARPS * 32, 0, st_>>>(t);
         SD_CUDA(cudaGetLastError());
         SD_CUDA(cudaEventRecord(ev_[2], st_));
-        int flag = 0;
-        SD_CUDA(cudaMemcpyAsync(&flag, d_flag_.p, 4, cudaMemcpyDeviceToHost, st_));
+        int flag[2] = {0, 0};
+        SD_CUDA(cudaMemcpyAsync(flag, d_flag_.p, 8, cudaMemcpyDeviceToHost, st_));
         SD_CUDA(cudaStreamSynchronize(st_));
-        if (flag) {
+        if (flag[0] || flag[1]) {
             SD_CUDA(cudaMemsetAsync(d_flag_.p, 0, 16, st_));
+            if (flag[1]) throw PlanError{"CUDA: group sweep timed out waiting for a partner CTA (internal error)"};
             throw PlanError{"segment contains a symbol outside ACGTN"};
         }
         float ms = 0;
@@ -409,7 +450,7 @@ private:
     int64_t budget_ = 0;
     DevBuf d_prof_, d_slotlen_, d_slotend_, d_rows_, d_rowoff_;
     DevBuf d_bases_, d_segoff_, d_ctanmax_, d_ctacode_, d_segj_, d_segrec_;
-    DevBuf d_flag_, d_codes_, d_jr_, d_scratch_, d_counts_, d_outoff_, d_dense_;
+    DevBuf d_flag_, d_xchg_, d_codes_, d_jr_, d_scratch_, d_counts_, d_outoff_, d_dense_;
 };
 
 } // namespace

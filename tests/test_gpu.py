@@ -173,3 +173,23 @@ def test_multi_gpu_output_identical():
 def test_int_peak_probe():
     alu, both, mhz = int_peak(0)
     assert 5e12 < alu < 4e13 and both >= alu * 0.9 and 500 < mhz < 2500
+
+
+@pytest.mark.parametrize("sg", ["1", "4", "8"])
+def test_group_mode_forced_on_small_sets(sg):
+    picked = [c for c in cases.load_cases() if c["name"] in ("multi_read", "dup_monomers_rev", "short_monomers", "N_in_monomer", "len_5501_default")]
+    for case in picked:
+        cases.check_case(cases.DP_CUDA, case, env={"SD_GROUP_SLOTS": sg})
+    cases.check_case(cases.DP_CUDA, picked[0], env={"SD_GROUP_SLOTS": sg, "SD_FORCE_S32": "1"})
+    st, out, err = sd_oracle.run_cli(cases.DP_CUDA, os.path.join(cases.GOLDEN, "config1_read.fa"), os.path.join(cases.GOLDEN, "DXZ1_star_monomers.fa"))
+    assert st == 0
+
+
+def test_config5_large_monomer_set_sample():
+    # BASELINE config 5 (large monomer set): 160 monomers cannot live in one CTA -> group sweep.  The reference needs
+    # n * sum(L) * 8 B per segment, so parity is checked on a bounded sample (part 2000).
+    rn, reads, mn, mons = synth.config5(n_monomers=160, total=60_000)
+    reads = [r[:9000] for r in reads[:2]]
+    want = sd_oracle.decompose_reads(rn[:2], reads, mn, mons, part_size=2000, overlap=300, threads=4)
+    got = decompose_reads(rn[:2], reads, mn, mons, part_size=2000, overlap=300)
+    assert got == want

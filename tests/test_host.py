@@ -135,3 +135,25 @@ def test_unsupported_inputs_fail_loudly():
     case["argv_tail"] = ["1", "1000", "300", "-1", "-1", "-1", "1", "5"]
     st, out, err = cases.run_case(cases.DP_EMU, case)
     assert st != 0 and out == "" and "ed_thr" in err
+
+
+@pytest.mark.parametrize("sg", ["1", "4", "8"])
+def test_emulated_group_mode_splits_the_monomer_set(sg):
+    # several CTAs per segment (the layout used for monomer sets that do not fit one CTA), forced on small inputs
+    picked = [c for c in cases.load_cases() if c["name"] in ("multi_read", "dup_monomers_rev", "short_monomers", "N_in_monomer")]
+    for case in picked:
+        cases.check_case(cases.DP_EMU, case, env={"SD_GROUP_SLOTS": sg})
+    cases.check_case(cases.DP_EMU, picked[0], env={"SD_GROUP_SLOTS": sg, "SD_FORCE_S32": "1"})
+
+
+def test_emulated_large_monomer_set_needs_groups():
+    rn, reads, mn, mons = synth.config5(n_monomers=70, total=20_000)
+    d = Decomposer(mons, flavour="emu")
+    segs = [reads[0][:600], reads[1][:450]]
+    recs, off = d.decompose(segs)
+    st = d.stats()
+    assert st["NT"] <= 512
+    for j, s in enumerate(segs):
+        want = sd_oracle.align_segment(s, mons)
+        assert [(int(r["row"]), int(r["start"]), int(r["end"]), float(r["score"])) for r in recs[off[j]:off[j + 1]]] == want
+    d.close()
