@@ -165,7 +165,8 @@ Plan make_plan(const MonomerSet &ms, const Scoring &sc, int max_seg_len, int64_t
         if (!gC) throw PlanError{"monomers longer than 1536 bp are not supported by this build"};
         const int spw = 32 / gT, qpc = (gC / 4) | 1;
         const size_t per_slot = (size_t)5 * qpc * gT * 16;
-        int sg = (int)std::min<size_t>((size_t)(90 * 1024) / per_slot, (size_t)(384 / 32) * spw);
+        // large groups win (fewer partners to wait for per column, measured): one CTA per SM, up to 16 warps
+        int sg = (int)std::min<size_t>((size_t)(180 * 1024) / per_slot, (size_t)16 * spw);
         sg = std::max(sg / spw * spw, spw);
         if (force_sg > 0) sg = std::max(force_sg / spw * spw, spw);
         sg = std::min(sg, (nslots + spw - 1) / spw * spw);

@@ -222,8 +222,8 @@ __global__ void sweep_kernel(const SweepArgs a)
 // ---------------------------------------------------------------------------------------------------------------
 // Group sweep: monomer sets that do not fit one CTA (threads, registers, or the shared-memory profile table).
 // The slots are split into NG groups; CTA (gslot, grp) sweeps slot group `grp` of the segments gslot, gslot+ngslots, ...
-// and the NG CTAs of a segment meet once per column in global memory: atomicMax on the (score,row) key, an arrival
-// counter, and a bounded spin.  All CTAs are co-resident (cooperative launch), so the spin cannot deadlock; a
+// and the NG CTAs of a segment meet once per column in global memory: every CTA publishes (epoch, key) in its own
+// slot with a release store and polls the others' slots with acquire loads (no atomics, bounded spin).  All CTAs are co-resident (cooperative launch), so the spin cannot deadlock; a
 // time-out raises *error instead of hanging.
 struct GroupArgs {
     const uint4 *prof; int nsl_total, qp;              // [5][nsl_total][qp] uint4
@@ -236,7 +236,7 @@ struct GroupArgs {
     int seg_stride;
     TagRegs tr;
     int *bad_symbol;
-    int *gkey; unsigned *gcnt;                          // [ngslots][4]
+    unsigned long long *xbuf;                           // [ngslots][2][NG] exchange slots, zeroed before the launch
     int ngslots;
     int *error;
 };
@@ -280,8 +280,7 @@ __global__ void sweep_group_kernel(const GroupArgs a)
     int srcl[T > 2 ? T - 2 : 1];
 #pragma unroll
     for (int d = 1; d <= T - 2; ++d) srcl[d - 1] = lane - min(d, t);
-    int *gkey = a.gkey + gslot * 4;
-    unsigned *gcnt = a.gcnt + gslot * 4;
+    unsigned long long *xbuf = a.xbuf + (size_t)gslot * 2 * NG;     // [2 buffers][NG] (epoch << 32 | key)
     unsigned gcol = 0;                                   // columns this CTA group has exchanged so far
 
     uint32_t X[C], pw[C];
@@ -346,21 +345,33 @@ __global__ void sweep_group_kernel(const GroupArgs a)
 #pragma unroll
             for (int kk = 0; kk < C; ++kk) asm volatile("" ::"r"(X[kk]));
             __syncthreads();
-            if (tid == 0) {
-                int k = swk[0];
-                for (int w = 1; w < nwarps; ++w) k = max(k, swk[w]);
-                const unsigned b = gcol & 3u;
-                if (grp == 0) { *(volatile int *)(gkey + ((gcol + 2u) & 3u)) = INT_MIN; __threadfence(); }
-                atomicMax(gkey + b, k);
-                __threadfence();
-                atomicAdd(gcnt + b, 1u);
-                const unsigned target = (unsigned)NG * ((gcol >> 2) + 1u);
-                unsigned spins = 0;
-                while (*(volatile unsigned *)(gcnt + b) < target) {
-                    if (++spins > (1u << 21)) { *a.error = 1; break; }
+            // Column exchange between the NG CTAs of the segment, without atomics: CTA `grp` publishes (epoch, key) in
+            // its own slot of buffer (gcol & 1); warp 0 polls all NG slots of that buffer until every epoch matches.
+            // Two buffers suffice: a CTA can only be one column ahead of the slowest reader (it needs everybody's key
+            // of column c to leave column c), so the slot of column c is not overwritten before it has been read.
+            if (warp == 0) {
+                const unsigned epoch = gcol + 1u;
+                unsigned long long *buf = xbuf + (size_t)(gcol & 1u) * NG;
+                if (lane == 0) {
+                    int k = swk[0];
+                    for (int w = 1; w < nwarps; ++w) k = max(k, swk[w]);
+                    const unsigned long long v = ((unsigned long long)epoch << 32) | (unsigned)k;
+                    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(buf + grp), "l"(v) : "memory");   // the word is the whole message
                 }
-                __threadfence();
-                swk[32] = *(volatile int *)(gkey + b);
+                int best = INT_MIN;
+                for (int q = lane; q < NG; q += 32) {
+                    unsigned long long v;
+                    unsigned spins = 0;
+                    for (;;) {
+                        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(buf + q) : "memory");
+                        if ((unsigned)(v >> 32) == epoch) break;
+                        if (++spins > (1u << 21)) { *a.error = 1; break; }
+                        if (NG > 8) __nanosleep(40);           // many pollers per slot: back off a little
+                    }
+                    best = max(best, (int)(unsigned)v);
+                }
+                best = __reduce_max_sync(0xffffffffu, best);
+                if (lane == 0) swk[32] = best;
             }
             __syncthreads();
             const int k2 = swk[32];

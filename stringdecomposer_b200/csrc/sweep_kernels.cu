@@ -362,10 +362,9 @@ public:
         const int capacity = per_sm * prop_.multiProcessorCount;
         if (capacity < g.NG) throw PlanError{"monomer set too large: the CTAs of one segment cannot be co-resident on this GPU"};
         a.ngslots = std::min(nseg_, capacity / g.NG);
-        d_xchg_.need((size_t)a.ngslots * 4 * 8);
-        a.gkey = d_xchg_.as<int>(); a.gcnt = reinterpret_cast<unsigned *>(d_xchg_.as<int>() + (size_t)a.ngslots * 4);
-        SD_CUDA(cudaMemsetAsync(a.gkey, 0x80, (size_t)a.ngslots * 4 * 4, st_));       // very negative keys
-        SD_CUDA(cudaMemsetAsync(a.gcnt, 0, (size_t)a.ngslots * 4 * 4, st_));
+        d_xchg_.need((size_t)a.ngslots * 2 * g.NG * 8);
+        a.xbuf = d_xchg_.as<unsigned long long>();
+        SD_CUDA(cudaMemsetAsync(a.xbuf, 0, (size_t)a.ngslots * 2 * g.NG * 8, st_));    // epoch 0 = nothing published
         void *args[] = {(void *)&a};
         SD_CUDA(cudaLaunchCooperativeKernel(kernel_, dim3(a.ngslots * g.NG), dim3(g.NT), args, smem, st_));
     }
