@@ -192,30 +192,14 @@ SD_HD int decode_code(uint32_t w, int packed, int ncell, int c, int half)
     return (int)(((w + code_bias(packed, ncell)) >> (2 * (ncell - 1 - c) + half)) & 3u);
 }
 
-// Pass 2: run the deletion chain (prefix max) through the lane with the carry from the lanes on its left,
-// leave the new U in X and emit the 2-bit backpointers (3 - tag) of the C cells.
+// Pass 2 fused with pass 1a of the NEXT column.  The deletion chain (prefix max) runs through the lane with the carry
+// from the lanes on its left:
 //   h = max(Uleft + 1, m2)      tagged winner (left has tag 3 and wins ties: main.cpp:242 comes first)
 //   U = (h | 3) ^ 1             new state, tag-2 form                 code = U + 1 - h  in {0,1,2,3}
-// Word layout: word wi holds cells [wi*CPW, wi*CPW + ncell); cell c of the word sits at bits 2*(ncell-1-c)
-// (Packed16: forward row in bits 0..15, reverse-complement row in bits 16..31).
-template <class P, int C>
-SD_HD void lane_pass2(uint32_t (&X)[C], uint32_t carryU, uint32_t *codes, TagRegs tr)
-{
-    constexpr int CPW = P::CELLS_PER_WORD;
-    uint32_t ul = carryU;
-    uint32_t w = 0;
-#pragma unroll
-    for (int kk = 0; kk < C; ++kk) {
-        const uint32_t h = P::addmax(ul, tr.one, X[kk]);
-        ul = (h | tr.mask3) ^ tr.one;
-        w = w * 4u + ul - h;                     // digits in {-1..2}; biased once per word below
-        X[kk] = ul;
-        if ((kk + 1) % CPW == 0 || kk == C - 1) { codes[kk / CPW] = w; w = 0; }
-    }
-}
-
-// Pass 2 fused with pass 1a of the NEXT column.  While the deletion chain of column i runs through the lane
-// (two dependent ALU ops per cell), the J-independent candidates of column i+1 are formed from the fresh U values:
+// Backpointer word layout: word wi holds cells [wi*CPW, wi*CPW + ncell); cell c of the word sits at bits 2*(ncell-1-c)
+// (Packed16: forward row in bits 0..15, reverse-complement row in bits 16..31); see decode_code().
+// While the chain runs (two dependent ALU ops per cell), the J-independent candidates of column i+1 are formed from
+// the fresh U values:
 //   X[kk] <- max(U[kk-1] + pn[kk], U[kk])      kk >= 1        (pn: profile words of column i+1)
 // Cell 0 needs the left lane's last U (a shuffle), so the caller finishes it with lane_pre_first().
 // Returns U[C-1] (row-end value for the jump key and the right neighbour's diagonal); *u_first gets U[0].

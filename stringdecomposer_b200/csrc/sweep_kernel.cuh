@@ -101,7 +101,8 @@ __global__ void sweep_kernel(const SweepArgs a)
     const bool kill_first = (t == 0), kill_last = (t == T - 1 && L == 1);
     const bool j_writer = active && slot == 0 && t == 0;
     const bool is_end = active && t == T - 1;
-    const int kc_lo = key_const(endadd, slot), kc_hi = key_const(endadd, a.M + slot);
+    const int kc_lo = is_end ? key_const(endadd, slot) - 0x800 : -(1 << 30);
+    const int kc_hi = is_end ? key_const(endadd, a.M + slot) - 0x800 : -(1 << 30);
     JR *jptr = a.jr + (active ? a.seg_j_off[first + seg_local] : 0);
     uint32_t *cptr = a.codes + a.cta_code_off[cta] + (size_t)tid * a.CW;
     const size_t cstride = (size_t)NT * a.CW;
@@ -153,7 +154,8 @@ __global__ void sweep_kernel(const SweepArgs a)
         uint32_t ufirst;
         const uint32_t uend = lane_pass2_pre<P, C>(X, carry, cw, tr, pw, deadu, kill_last, &ufirst);
 
-        const bool live = i < n_seg;                          // columns past the end of a shorter segment of the CTA are idle
+        // one segment per CTA (FAST without MULTI): every column is live; else a shorter segment idles past its end
+        const bool live = active && ((FAST && !MULTI) || i < n_seg);
         if (live) {
             if (NW == 2) *reinterpret_cast<uint2 *>(cptr) = make_uint2(cw[0], cw[1]);
             else if (NW == 4) *reinterpret_cast<uint4 *>(cptr) = make_uint4(cw[0], cw[1], cw[2], cw[3]);
@@ -165,15 +167,16 @@ __global__ void sweep_kernel(const SweepArgs a)
         cptr += cstride;
 
         // row ends -> (score,row) key of the segment: key = (u >> 2) * 4096 + (endadd * 4096 + 4095 - row)
+        // U = 4*rel + 2, so (half << 10) already is rel*4096 + 0x800: no masking of the low bits is needed for the
+        // forward row; lanes that hold no row end carry a very negative constant instead of a select
         int key;
         if (P::ROWS == 2) {
-            const int klo = ((int)(uend << 16) >> 18) * SD_KEY_ROWS + kc_lo;
-            const int khi = ((int)uend >> 18) * SD_KEY_ROWS + kc_hi;
+            const int klo = ((int)(uend << 16) >> 6) + kc_lo;
+            const int khi = ((int)(uend & 0xffff0000u) >> 6) + kc_hi;
             key = max(klo, khi);
         } else {
-            key = ((int)uend >> 2) * SD_KEY_ROWS + kc_lo;
+            key = ((int)uend << 10) + kc_lo;
         }
-        if (!is_end) key = INT_MIN;
         if (FAST) {
             const int wk = __reduce_max_sync(0xffffffffu, key);
             if (lane == 0) asm volatile("st.shared.b32 [%0], %1;" ::"r"(key_wr_s + kboff), "r"(wk) : "memory");
@@ -186,10 +189,8 @@ __global__ void sweep_kernel(const SweepArgs a)
         uint32_t prevU = deadu;
         if (T > 1) { prevU = __shfl_up_sync(0xffffffffu, uend, 1); if (t == 0) prevU = deadu; }
         X[0] = lane_pre_first<P>(prevU, pw[0], ufirst, deadu, kill_first, C == 1 && kill_last);
-        // pin the next column's J-independent half in front of the barrier (ptxas otherwise sinks it behind the
-        // wait, onto the critical path)
-#pragma unroll
-        for (int kk = 0; kk < C; ++kk) asm volatile("" ::"r"(X[kk]));
+        // (ptxas schedules these J-independent max-plus ops behind the barrier, where they cover the latency of the
+        // key load that follows it)
 
         // FAST: only the warps of this segment meet (named barrier 1 + segment), so the segments that share a CTA
         // (and its profile table) run decoupled; otherwise the whole CTA synchronises
@@ -274,7 +275,8 @@ __global__ void sweep_group_kernel(const GroupArgs a)
     const bool kill_first = (t == 0), kill_last = (t == T - 1 && L == 1);
     const bool is_end = active && t == T - 1;
     const bool j_writer = grp == 0 && tid == 0;
-    const int kc_lo = key_const(endadd, slot), kc_hi = key_const(endadd, a.M + slot);
+    const int kc_lo = is_end ? key_const(endadd, slot) - 0x800 : -(1 << 30);
+    const int kc_hi = is_end ? key_const(endadd, a.M + slot) - 0x800 : -(1 << 30);
     const uint4 *myprof = sprof + (size_t)(ginst * T + t) * a.qp;
     const int sym_stride = sgt * a.qp;
     int srcl[T > 2 ? T - 2 : 1];
@@ -328,22 +330,21 @@ __global__ void sweep_group_kernel(const GroupArgs a)
                 for (int w = 0; w < NW; ++w) cptr[w] = cw[w];
             }
             cptr += cstride;
+            // U = 4*rel + 2, so (half << 10) already is rel*4096 + 0x800: no masking of the low bits is needed for the
+            // forward row; lanes that hold no row end carry a very negative constant instead of a select
             int key;
             if (P::ROWS == 2) {
-                const int klo = ((int)(uend << 16) >> 18) * SD_KEY_ROWS + kc_lo;
-                const int khi = ((int)uend >> 18) * SD_KEY_ROWS + kc_hi;
+                const int klo = ((int)(uend << 16) >> 6) + kc_lo;
+                const int khi = ((int)(uend & 0xffff0000u) >> 6) + kc_hi;
                 key = max(klo, khi);
             } else {
-                key = ((int)uend >> 2) * SD_KEY_ROWS + kc_lo;
+                key = ((int)uend << 10) + kc_lo;
             }
-            if (!is_end) key = INT_MIN;
             const int wk = __reduce_max_sync(0xffffffffu, key);
             if (lane == 0) swk[warp] = wk;
             uint32_t prevU = deadu;
             if (T > 1) { prevU = __shfl_up_sync(0xffffffffu, uend, 1); if (t == 0) prevU = deadu; }
             X[0] = lane_pre_first<P>(prevU, pw[0], ufirst, deadu, kill_first, C == 1 && kill_last);
-#pragma unroll
-            for (int kk = 0; kk < C; ++kk) asm volatile("" ::"r"(X[kk]));
             __syncthreads();
             // Column exchange between the NG CTAs of the segment, without atomics: CTA `grp` publishes (epoch, key) in
             // its own slot of buffer (gcol & 1); warp 0 polls all NG slots of that buffer until every epoch matches.
