@@ -136,7 +136,7 @@ template <class P> CtaFn<P> pick(int C, int T)
 {
     switch (C) {
     case 8: return pick_t<P, 8>(T); case 12: return pick_t<P, 12>(T); case 16: return pick_t<P, 16>(T);
-    case 20: return pick_t<P, 20>(T); case 24: return pick_t<P, 24>(T); case 32: return pick_t<P, 32>(T);
+    case 19: return pick_t<P, 19>(T); case 20: return pick_t<P, 20>(T); case 24: return pick_t<P, 24>(T); case 32: return pick_t<P, 32>(T);
     case 48: return pick_t<P, 48>(T);
     }
     return nullptr;

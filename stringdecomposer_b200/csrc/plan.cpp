@@ -59,7 +59,7 @@ bool packed_range_ok(const MonomerSet &ms, const Scoring &sc, int *deadz, int *p
 }
 
 // Kernel instantiations compiled into the library (sweep_kernels.cu instantiates exactly this table).
-static const int kC[] = {8, 12, 16, 20, 24, 32, 48};
+static const int kC[] = {8, 12, 16, 19, 20, 24, 32, 48};
 static const int kT[] = {1, 2, 4, 8, 10, 16, 32};
 bool geometry_compiled(int packed, int C, int T)
 {
@@ -132,7 +132,7 @@ Plan make_plan(const MonomerSet &ms, const Scoring &sc, int max_seg_len, int64_t
         if (!fC && C > 24 && !need_big) continue;
         int ls = nslots * T;                        // lanes per segment
         if (ls > 1024) continue;
-        const int qpc = (C / 4) | 1;
+        const int qpc = ((C + 3) / 4) | 1;
         size_t prof_bytes = (size_t)5 * qpc * ls * 16;
         for (int NS = 1; NS <= 16; ++NS) {
             if (fNS && NS != fNS) continue;
@@ -163,7 +163,7 @@ Plan make_plan(const MonomerSet &ms, const Scoring &sc, int max_seg_len, int64_t
             if (!gC || C * T < gC * gT || (C * T == gC * gT && C > gC)) { gC = C; gT = T; }
         }
         if (!gC) throw PlanError{"monomers longer than 1536 bp are not supported by this build"};
-        const int spw = 32 / gT, qpc = (gC / 4) | 1;
+        const int spw = 32 / gT, qpc = ((gC + 3) / 4) | 1;
         const size_t per_slot = (size_t)5 * qpc * gT * 16;
         // large groups win (fewer partners to wait for per column, measured): one CTA per SM, up to 16 warps
         int sg = (int)std::min<size_t>((size_t)(180 * 1024) / per_slot, (size_t)16 * spw);
@@ -183,7 +183,7 @@ Plan make_plan(const MonomerSet &ms, const Scoring &sc, int max_seg_len, int64_t
 
     // profile words: prof[sym][sl][q][e] = 4*s''(sym, row cell k) - 1 with k = t*C + 4q + e; pad cells get 4*pad_s - 1.
     const int C = g.C, T = g.T, SL = C * T;
-    p.qp = (C / 4) | 1;
+    p.qp = ((C + 3) / 4) | 1;
     p.prof.assign((size_t)5 * p.nsl * p.qp * 4, 0u);
     p.slot_len.resize(nslots); p.slot_endadd.resize(nslots);
     const int shift = -sc.ins - sc.del;

@@ -125,7 +125,7 @@ constexpr int SD_REBASE_TH = 4096;      // |4*(B[i]-Bref)| above this triggers a
 //   pw       : profile words p = 4*s'' - 1 (packed per half) for this column's read symbol; pad cells very negative
 //   kill_first / kill_last: the cell is a k==0 cell -- no insertion candidate (main.cpp:194)
 template <class P, int C>
-SD_HD void lane_pre(uint32_t (&X)[C], uint32_t prevU, const uint32_t (&pw)[C], uint32_t deadu, bool kill_first, bool kill_last)
+SD_HD void lane_pre(uint32_t (&X)[C], uint32_t prevU, const uint32_t *pw, uint32_t deadu, bool kill_first, bool kill_last)
 {
     uint32_t prev = prevU;
 #pragma unroll
@@ -169,7 +169,7 @@ template <class P, int N> SD_HD uint32_t tree_max(const uint32_t (&v)[N])
 }
 
 template <class P, int C>
-SD_HD uint32_t lane_post(uint32_t (&X)[C], const uint32_t (&pw)[C], uint32_t jump0p1, uint32_t deadu, TagRegs tr)
+SD_HD uint32_t lane_post(uint32_t (&X)[C], const uint32_t *pw, uint32_t jump0p1, uint32_t deadu, TagRegs tr)
 {
     (void)deadu;
 #pragma unroll
@@ -204,7 +204,7 @@ SD_HD int decode_code(uint32_t w, int packed, int ncell, int c, int half)
 // Cell 0 needs the left lane's last U (a shuffle), so the caller finishes it with lane_pre_first().
 // Returns U[C-1] (row-end value for the jump key and the right neighbour's diagonal); *u_first gets U[0].
 template <class P, int C>
-SD_HD uint32_t lane_pass2_pre(uint32_t (&X)[C], uint32_t carryU, uint32_t *codes, TagRegs tr, const uint32_t (&pn)[C],
+SD_HD uint32_t lane_pass2_pre(uint32_t (&X)[C], uint32_t carryU, uint32_t *codes, TagRegs tr, const uint32_t *pn,
                               uint32_t deadu, bool kill_last, uint32_t *u_first)
 {
     constexpr int CPW = P::CELLS_PER_WORD;

@@ -121,13 +121,14 @@ __global__ void sweep_kernel(const SweepArgs a)
     const uint32_t kbytes = 4u * (uint32_t)kstride;
     const int bar_id = 1 + wseg, bar_threads = a.wps * 32;
 
-    uint32_t X[C], pw[C];
+    constexpr int CQ = (C + 3) / 4;                     // uint4 profile loads per lane (the tail words are padding)
+    uint32_t X[C], pw[CQ * 4];
 #pragma unroll
     for (int kk = 0; kk < C; ++kk) X[kk] = deadu;
     auto load_profile = [&](int sym) {
         const uint4 *pp = myprof + sym * sym_stride;
 #pragma unroll
-        for (int q = 0; q < C / 4; ++q) {
+        for (int q = 0; q < CQ; ++q) {
             const uint4 v = pp[q];
             pw[4 * q] = v.x; pw[4 * q + 1] = v.y; pw[4 * q + 2] = v.z; pw[4 * q + 3] = v.w;
         }
@@ -285,11 +286,12 @@ __global__ void sweep_group_kernel(const GroupArgs a)
     unsigned long long *xbuf = a.xbuf + (size_t)gslot * 2 * NG;     // [2 buffers][NG] (epoch << 32 | key)
     unsigned gcol = 0;                                   // columns this CTA group has exchanged so far
 
-    uint32_t X[C], pw[C];
+    constexpr int CQ = (C + 3) / 4;
+    uint32_t X[C], pw[CQ * 4];
     auto load_profile = [&](int sym) {
         const uint4 *pp = myprof + sym * sym_stride;
 #pragma unroll
-        for (int q = 0; q < C / 4; ++q) {
+        for (int q = 0; q < CQ; ++q) {
             const uint4 v = pp[q];
             pw[4 * q] = v.x; pw[4 * q + 1] = v.y; pw[4 * q + 2] = v.z; pw[4 * q + 3] = v.w;
         }
@@ -419,7 +421,8 @@ const void *sweep_group_lookup_s32(int C, int T);
     {                                                                                                                 \
         switch (C) {                                                                                                  \
         case 8: return NAME##_t<8>(T); case 12: return NAME##_t<12>(T); case 16: return NAME##_t<16>(T);              \
-        case 20: return NAME##_t<20>(T); case 24: return NAME##_t<24>(T); case 32: return NAME##_t<32>(T);            \
+        case 19: return NAME##_t<19>(T); case 20: return NAME##_t<20>(T); case 24: return NAME##_t<24>(T);              \
+        case 32: return NAME##_t<32>(T);            \
         case 48: return NAME##_t<48>(T);                                                                              \
         }                                                                                                             \
         return nullptr;                                                                                               \
@@ -443,7 +446,8 @@ const void *sweep_group_lookup_s32(int C, int T);
     {                                                                                                                 \
         switch (C) {                                                                                                  \
         case 8: return NAME##_t<8>(T); case 12: return NAME##_t<12>(T); case 16: return NAME##_t<16>(T);              \
-        case 20: return NAME##_t<20>(T); case 24: return NAME##_t<24>(T); case 32: return NAME##_t<32>(T);            \
+        case 19: return NAME##_t<19>(T); case 20: return NAME##_t<20>(T); case 24: return NAME##_t<24>(T);              \
+        case 32: return NAME##_t<32>(T);            \
         case 48: return NAME##_t<48>(T);                                                                              \
         }                                                                                                             \
         return nullptr;                                                                                               \

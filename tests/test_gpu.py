@@ -44,7 +44,7 @@ def test_edge_cases_through_dp_binary(case):
     cases.check_case(cases.DP_CUDA, case)
 
 
-@pytest.mark.parametrize("geom", ["8,32,1", "16,16,1", "24,8,1", "24,8,2", "32,8,1", "48,4,2", "48,4,3", "12,16,1", "20,10,1", "20,10,2", "12,16,1"])
+@pytest.mark.parametrize("geom", ["8,32,1", "16,16,1", "24,8,1", "24,8,2", "32,8,1", "48,4,2", "48,4,3", "12,16,1", "20,10,1", "20,10,2", "12,16,1", "19,10,1", "19,10,3"])
 @pytest.mark.parametrize("force32", ["0", "1"])
 def test_every_geometry_and_both_widths(geom, force32):
     picked = [c for c in cases.load_cases() if c["name"] in ("multi_read", "scoring_-3_-2_-4_2", "N_in_monomer", "dup_monomers_rev",

@@ -67,7 +67,7 @@ def test_emulated_kernels_match_reference_on_edge_cases(case):
     cases.check_case(cases.DP_EMU, case)
 
 
-@pytest.mark.parametrize("geom", ["8,32,1", "16,16,1", "24,8,1", "24,8,2", "32,8,1", "48,4,2", "48,4,3", "20,10,1", "20,10,2", "12,16,1"])
+@pytest.mark.parametrize("geom", ["8,32,1", "16,16,1", "24,8,1", "24,8,2", "32,8,1", "48,4,2", "48,4,3", "20,10,1", "20,10,2", "12,16,1", "19,10,1", "19,10,3"])
 @pytest.mark.parametrize("force32", ["0", "1"])
 def test_emulated_kernels_every_geometry(geom, force32):
     # same answer whatever the lane layout, packed s16x2 and s32 (the emulator traps 16-bit overflow)
