@@ -1,0 +1,65 @@
+"""Property-based parity (hypothesis): random monomer sets, segments and scorings -- the kernel algebra (host emulator on
+CPU, CUDA on the B200) must reproduce the oracle's records exactly, whatever the launch geometry."""
+import os
+
+import pytest
+from hypothesis import HealthCheck, given, settings, strategies as st
+
+import sd_oracle
+from stringdecomposer_b200 import Decomposer
+
+
+def seq(alphabet, lo, hi):
+    return st.text(alphabet=alphabet, min_size=lo, max_size=hi)
+
+
+@st.composite
+def problems(draw):
+    alphabet = draw(st.sampled_from(["A", "AC", "ACG", "ACGT", "ACGTN"]))
+    monomers = draw(st.lists(seq(alphabet, 1, 70), min_size=1, max_size=6))
+    if draw(st.booleans()) and len(monomers) > 1:
+        monomers[-1] = monomers[0]                       # duplicate rows: arg-max ties (main.cpp:212, :230-236)
+    segments = draw(st.lists(seq(alphabet, 1, 260), min_size=1, max_size=4))
+    scoring = draw(st.sampled_from([(-1, -1, -1, 1), (-2, -2, -3, 1), (-3, -2, -4, 2), (0, -1, -1, 1), (-1, 0, -1, 1),
+                                    (-1, -1, -1, 5), (-7, -25, -3, 2), (1, -1, -1, 1), (-1, -2, 0, 0)]))
+    geom = draw(st.sampled_from(["", "8,32,1", "12,16,2", "19,10,1", "24,8,3", "16,4,2", "8,8,5", "48,2,1"]))
+    group = draw(st.sampled_from(["", "", "1", "4"]))
+    return monomers, segments, scoring, geom, group
+
+
+def run(flavour, problem):
+    monomers, segments, scoring, geom, group = problem
+    lmax = max(len(m) for m in monomers)
+    if geom:
+        c, t, _ = map(int, geom.split(","))
+        if c * t < lmax:
+            geom = ""
+    for k, v in (("SD_GEOM", geom), ("SD_GROUP_SLOTS", group)):
+        if v:
+            os.environ[k] = v
+        else:
+            os.environ.pop(k, None)
+    try:
+        d = Decomposer(monomers, *scoring, flavour=flavour)
+        recs, off = d.decompose(segments)
+        d.close()
+    finally:
+        os.environ.pop("SD_GEOM", None)
+        os.environ.pop("SD_GROUP_SLOTS", None)
+    for j, s in enumerate(segments):
+        want = sd_oracle.align_segment(s, monomers, scoring)
+        got = [(int(r["row"]), int(r["start"]), int(r["end"]), float(r["score"])) for r in recs[off[j]:off[j + 1]]]
+        assert got == want, (monomers, s, scoring, geom, group)
+
+
+@settings(max_examples=120, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
+@given(problems())
+def test_emulated_kernels_match_oracle(problem):
+    run("emu", problem)
+
+
+@pytest.mark.gpu
+@settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
+@given(problems())
+def test_cuda_kernels_match_oracle(problem):
+    run("cuda", problem)
