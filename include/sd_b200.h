@@ -84,6 +84,16 @@ int sd_run_files(const char *reads_path, const char *monomers_path, int32_t thre
                  int32_t overlap, int32_t ins, int32_t del, int32_t mismatch, int32_t match, int32_t ed_thr,
                  int out_fd, int err_fd);
 
+/* Replaces FilterMonomersForRead (main.cpp:135-149), the optional --ed_thr pre-filter: for every segment the DP rows
+ * are sorted by (infix edit distance to the segment, row), the closest row and every row with distance <= ed_thr are
+ * kept, and the DP runs on that re-ordered subset (so arg-max ties follow the new order).  ed_thr < 0 switches it
+ * off (default).  Records keep reporting rows of the full set. */
+int sd_set_ed_thr(sd_handle *h, int32_t ed_thr);
+
+/* Replaces MonomerEditDistance (main.cpp:128-133): infix (edlib "HW") unit-cost edit distance of `query` against the
+ * best substring of `target`; host-side helper (the pre-filter itself runs on the device).  -1 on bad arguments. */
+int32_t sd_hw_distance(const char *query, int32_t query_len, const char *target, int32_t target_len);
+
 int sd_get_stats(sd_handle *h, sd_stats *out);
 void sd_reset_stats(sd_handle *h);
 const char *sd_last_error(sd_handle *h);       /* h may be NULL: error of the last failed sd_create/sd_run_files */

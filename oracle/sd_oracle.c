@@ -13,6 +13,10 @@
  *       into oracle/_ref/dp (full raw TSV incl. score/gap/length columns, many edge cases;
  *       outputs committed as fixtures under tests/golden/ by tests/golden/make_golden.py).
  *
+ * The --ed_thr pre-filter (main.cpp:128-149) is restated too; its edit distance comes from edlib (vendored by the
+ * reference as src/edlib.cpp) and is restated from edlib's published definition of the HW mode as the textbook
+ * infix DP; it is pinned by the reference runs with argc == 11 in tests/golden/edge_cases.json.
+ *
  * Every function cites the reference lines it restates (paths relative to
  * /root/reference/stringdecomposer/src/main.cpp).  This is a restatement in plain C with flat
  * arrays, not a copy: the reference is C++ with nested std::vector and std::string.
@@ -163,6 +167,53 @@ int sdo_align_segment(const char *seg, int n, const char *rows, const int *row_o
 }
 
 /* ---------------------------------------------------------------------------------------
+ * MonomerEditDistance, main.cpp:128-133: edlibAlign(monomer, segment, k = -1, EDLIB_MODE_HW,
+ * EDLIB_TASK_DISTANCE).  edlib (vendored by the reference as src/edlib.cpp, Myers bit-vector) returns the
+ * unit-cost edit distance between the query and the best-matching substring of the target ("infix" / HW
+ * mode: gaps before and after the query's image in the target are free).  Restated here from that published
+ * definition as the textbook O(n*m) dynamic program: D[0][j] = 0, D[i][0] = i, answer = min_j D[m][j].
+ * ------------------------------------------------------------------------------------- */
+int sdo_hw_distance(const char *query, int m, const char *target, int n)
+{
+    int *prev = (int *)malloc(sizeof(int) * (size_t)(n + 1)), *cur = (int *)malloc(sizeof(int) * (size_t)(n + 1));
+    for (int j = 0; j <= n; ++j) prev[j] = 0;
+    for (int i = 1; i <= m; ++i) {
+        cur[0] = i;
+        for (int j = 1; j <= n; ++j) {
+            int a = prev[j - 1] + (query[i - 1] != target[j - 1]);
+            int b = prev[j] + 1, c = cur[j - 1] + 1;
+            cur[j] = a < b ? (a < c ? a : c) : (b < c ? b : c);
+        }
+        int *t = prev; prev = cur; cur = t;
+    }
+    int best = prev[0];
+    for (int j = 1; j <= n; ++j) if (prev[j] < best) best = prev[j];
+    free(prev); free(cur);
+    return best;
+}
+
+/* FilterMonomersForRead, main.cpp:135-149: rows sorted by (distance, index); element 0 is always kept (:142), the
+ * others when distance <= ed_thr (:143-147).  keep[] receives the kept row indices in their new order. */
+typedef struct { int dist, idx; } sdo_di;
+static int cmp_di(const void *a, const void *b)
+{
+    const sdo_di *x = (const sdo_di *)a, *y = (const sdo_di *)b;
+    if (x->dist != y->dist) return x->dist < y->dist ? -1 : 1;
+    return x->idx < y->idx ? -1 : (x->idx > y->idx);
+}
+int sdo_filter_rows(const char *seg, int n, const char *rows, const int *row_off, int R, int ed_thr, int *keep)
+{
+    sdo_di *v = (sdo_di *)malloc(sizeof(sdo_di) * (size_t)R);
+    for (int r = 0; r < R; ++r) { v[r].dist = sdo_hw_distance(rows + row_off[r], row_off[r + 1] - row_off[r], seg, n); v[r].idx = r; }
+    qsort(v, (size_t)R, sizeof(sdo_di), cmp_di);
+    int nk = 0;
+    keep[nk++] = v[0].idx;
+    for (int x = 1; x < R; ++x) if (v[x].dist <= ed_thr) keep[nk++] = v[x].idx;
+    free(v);
+    return nk;
+}
+
+/* ---------------------------------------------------------------------------------------
  * Segmentation of one read, main.cpp:73-79.  The condition at :74 mixes int and size_t; it is
  * evaluated here with the same conversions (size_t arithmetic, int operands converted).
  * Returns the number of segments; offs/lens may be NULL to count only.
@@ -291,7 +342,7 @@ static void buf_add(sdo_buf *b, const char *s, size_t n)
  * parallel loop over all segments.  raw TSV goes to *tsv (malloc'd, caller frees).
  * -------------------------------------------------------------------------------------- */
 int sdo_run_files(const char *reads_path, const char *monomers_path, int threads, int part_size, int overlap,
-                  int ins, int del, int mismatch, int match, char **tsv, size_t *tsv_len, FILE *err)
+                  int ins, int del, int mismatch, int match, int ed_thr, char **tsv, size_t *tsv_len, FILE *err)
 {
     sdo_seqs reads, mons;
     *tsv = NULL; *tsv_len = 0;
@@ -339,7 +390,24 @@ int sdo_run_files(const char *reads_path, const char *monomers_path, int threads
 #endif
         for (int s = 0; s < nseg; ++s) {
             sdo_rec *buf = (sdo_rec *)malloc(sizeof(sdo_rec) * (size_t)(slen[s] + 1));
-            int c = R > 0 ? sdo_align_segment(reads.v[sread[s]].seq + soff[s], slen[s], rows, row_off, R, ins, del, mismatch, match, buf, slen[s] + 1) : 0;
+            const char *segp = reads.v[sread[s]].seq + soff[s];
+            int c = 0;
+            if (R > 0 && ed_thr > -1) {                                              /* main.cpp:91-93 */
+                int *keep = (int *)malloc(sizeof(int) * (size_t)R), *foff = (int *)malloc(sizeof(int) * (size_t)(R + 1));
+                int nk = sdo_filter_rows(segp, slen[s], rows, row_off, R, ed_thr, keep);
+                char *frows = (char *)malloc((size_t)row_off[R] + 1);
+                foff[0] = 0;
+                for (int x = 0; x < nk; ++x) {
+                    int L = row_off[keep[x] + 1] - row_off[keep[x]];
+                    memcpy(frows + foff[x], rows + row_off[keep[x]], (size_t)L);
+                    foff[x + 1] = foff[x] + L;
+                }
+                c = sdo_align_segment(segp, slen[s], frows, foff, nk, ins, del, mismatch, match, buf, slen[s] + 1);
+                for (int x = 0; x < c; ++x) buf[x].row = keep[buf[x].row];            /* back to rows of the full set */
+                free(keep); free(foff); free(frows);
+            } else if (R > 0) {
+                c = sdo_align_segment(segp, slen[s], rows, row_off, R, ins, del, mismatch, match, buf, slen[s] + 1);
+            }
             if (c < 0) {
 #ifdef _OPENMP
 #pragma omp atomic write
@@ -400,9 +468,8 @@ int sdo_cli_main(int argc, char **argv)
     int ed_thr = -1;
     if (argc == 11) ed_thr = atoi(argv[10]);
     fprintf(stderr, "Scores: insertion=%d deletion=%d mismatch=%d match=%d\n", ins, del, mismatch, match);
-    if (ed_thr > -1) { fprintf(stderr, "oracle: ed_thr monomer pre-filter is not restated (SURVEY 8f row f2)\n"); return 2; }
     char *tsv; size_t n;
-    int st = sdo_run_files(argv[1], argv[2], atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), ins, del, mismatch, match, &tsv, &n, stderr);
+    int st = sdo_run_files(argv[1], argv[2], atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), ins, del, mismatch, match, ed_thr, &tsv, &n, stderr);
     if (tsv) { fwrite(tsv, 1, n, stdout); free(tsv); }
     return st;
 }

@@ -16,8 +16,10 @@ int sdo_align_segment(const char *seg, int n, const char *rows, const int *row_o
                       int ins, int del, int mismatch, int match, sdo_rec *out, int cap);
 int sdo_segment_read(long read_len, int part_size, int overlap, int *offs, int *lens, int cap);
 int sdo_postprocess(const sdo_rec *in, int n, sdo_rec *out);
+int sdo_hw_distance(const char *query, int m, const char *target, int n);
+int sdo_filter_rows(const char *seg, int n, const char *rows, const int *row_off, int R, int ed_thr, int *keep);
 int sdo_run_files(const char *reads_path, const char *monomers_path, int threads, int part_size, int overlap,
-                  int ins, int del, int mismatch, int match, char **tsv, size_t *tsv_len, FILE *err);
+                  int ins, int del, int mismatch, int match, int ed_thr, char **tsv, size_t *tsv_len, FILE *err);
 int sdo_cli_main(int argc, char **argv);
 
 #ifdef __cplusplus

@@ -24,7 +24,7 @@ class _Stats(C.Structure):
 
 # every symbol include/sd_b200.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = ["sd_create", "sd_decompose", "sd_stage", "sd_run_staged", "sd_fetch_staged", "sd_segment_read",
-           "sd_postprocess", "sd_run_files", "sd_get_stats", "sd_reset_stats", "sd_last_error", "sd_free",
+           "sd_postprocess", "sd_run_files", "sd_set_ed_thr", "sd_hw_distance", "sd_get_stats", "sd_reset_stats", "sd_last_error", "sd_free",
            "sd_destroy", "sd_device_count", "sd_version", "sd_int_peak"]
 
 _libs = {}
@@ -62,6 +62,10 @@ def load_library(flavour="cuda"):
     lib.sd_postprocess.restype = C.c_int64
     lib.sd_run_files.argtypes = [C.c_char_p, C.c_char_p] + [C.c_int32] * 8 + [C.c_int, C.c_int]
     lib.sd_run_files.restype = C.c_int
+    lib.sd_set_ed_thr.argtypes = [p, C.c_int32]
+    lib.sd_set_ed_thr.restype = C.c_int
+    lib.sd_hw_distance.argtypes = [C.c_char_p, C.c_int32, C.c_char_p, C.c_int32]
+    lib.sd_hw_distance.restype = C.c_int32
     lib.sd_get_stats.argtypes = [p, C.POINTER(_Stats)]
     lib.sd_get_stats.restype = C.c_int
     lib.sd_reset_stats.argtypes = [p]
@@ -170,6 +174,12 @@ class Decomposer:
             self._err(st)
         return self._take(recs, offs, self._staged)
 
+    def set_ed_thr(self, ed_thr):
+        """--ed_thr monomer pre-filter (FilterMonomersForRead, main.cpp:135-149); -1 switches it off."""
+        st = self._lib.sd_set_ed_thr(self._h, ed_thr)
+        if st:
+            self._err(st)
+
     def stats(self):
         s = _Stats()
         self._lib.sd_get_stats(self._h, C.byref(s))
@@ -206,6 +216,11 @@ def run_files(reads_path, monomers_path, threads=1, part_size=5000, overlap=500,
     lib = load_library(flavour)
     return lib.sd_run_files(str(reads_path).encode(), str(monomers_path).encode(), threads, part_size, overlap,
                             scoring[0], scoring[1], scoring[2], scoring[3], ed_thr, out_fd, err_fd)
+
+
+def hw_distance(query, target, flavour="cuda"):
+    """MonomerEditDistance (main.cpp:128-133): infix edit distance of query inside target."""
+    return int(load_library(flavour).sd_hw_distance(query.encode(), len(query), target.encode(), len(target)))
 
 
 def int_peak(device=0):

@@ -206,6 +206,20 @@ int sd_run_files(const char *reads_path, const char *monomers_path, int32_t thre
     return st;
 }
 
+int sd_set_ed_thr(sd_handle *h, int32_t ed_thr)
+{
+    if (!h) return SD_ERR_ARG;
+    try { h->eng->set_ed_thr(ed_thr); }
+    catch (PlanError &e) { h->err = e.msg; return SD_ERR_UNSUPPORTED; }
+    return SD_OK;
+}
+
+int32_t sd_hw_distance(const char *query, int32_t query_len, const char *target, int32_t target_len)
+{
+    if (!query || !target || query_len <= 0 || target_len < 0 || query_len > 64 * SD_HW_BLOCKS) return -1;
+    return hw_distance(reinterpret_cast<const uint8_t *>(query), query_len, reinterpret_cast<const uint8_t *>(target), target_len);
+}
+
 int sd_get_stats(sd_handle *h, sd_stats *o)
 {
     if (!h || !o) return SD_ERR_ARG;

@@ -88,13 +88,20 @@ public:
     virtual void configure(const Plan &p, const MonomerSet &ms) = 0;
     virtual int64_t wave_bytes(const Batch &b, int seg_begin, int seg_end) const = 0;   // device bytes stage() would need
     virtual int64_t wave_budget() const = 0;                                            // bytes one wave may use
+    // --ed_thr pre-filter (FilterMonomersForRead, main.cpp:135-149): -1 = off.  Applied by stage() to every segment.
+    virtual void set_filter(int ed_thr) { ed_thr_ = ed_thr; }
     virtual void stage(const Batch &b, int seg_begin, int seg_end) = 0;
     virtual void execute() = 0;
     virtual void fetch(BatchResult &out) = 0;       // appends to out.recs / out.rec_off (out.rec_off starts as {0})
     double sweep_ms = 0, traceback_ms = 0, h2d_ms = 0, d2h_ms = 0;     // accumulated since reset_stats()
     int64_t h2d_bytes = 0, d2h_bytes = 0, launches = 0;
+    int ed_thr_ = -1;
     void reset_stats() { sweep_ms = traceback_ms = h2d_ms = d2h_ms = 0; h2d_bytes = d2h_bytes = launches = 0; }
 };
+
+// rank tables of the pre-filter for one segment: rows sorted by (distance, row); the first one and every row with
+// distance <= ed_thr are kept (main.cpp:141-147).  rank_of_row[r] = position in the kept list or -1.
+void build_filter_tables(const int *dist, int R, int ed_thr, int *rank_of_row, int *row_of_rank);
 
 Backend *make_cuda_backend(int device_id, std::string &err);    // sweep_kernels.cu (product)
 Backend *make_emu_backend();                                    // emu.cpp (CPU test-suite only; absent from libsd_b200.so)

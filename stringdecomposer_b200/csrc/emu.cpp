@@ -18,8 +18,9 @@ bool &bad_symbol() { static thread_local bool f = false; return f; }
 
 template <class P, int C, int T>
 void emu_cta(const Plan &p, const Batch &b, int seg_first, int nseg_cta, int nmax,
-             uint32_t *const *codes, JR *const *jr)
+             uint32_t *const *codes, JR *const *jr, const int *rank)
 {
+    // rank: pre-filter ranks of the rows of the CTA's segments ([segment][row], -1 = filtered out) or nullptr
     // NG == 1: one CTA of NT threads, `codes[0]` its backpointer block.  NG > 1: the NG CTAs that share the segment are
     // emulated side by side (thread tid belongs to group tid / NT); the only coupling between them is the column key.
     const Geometry &g = p.g;
@@ -91,8 +92,12 @@ void emu_cta(const Plan &p, const Batch &b, int seg_first, int nseg_cta, int nma
                 for (int w = 0; w < g.CW; ++w) codes[tid / NTC][((size_t)i * NTC + tid % NTC) * g.CW + w] = cw[w];
             if (l.active && l.t == T - 1) {
                 const uint32_t u = uend[tid];
-                int k0 = make_key(P::lo(u), p.slot_endadd[l.slot], l.slot);
-                if (P::ROWS == 2) k0 = std::max(k0, make_key(P::hi(u), p.slot_endadd[l.slot], g.M + l.slot));
+                const int R = 2 * g.M;
+                int row_lo = l.slot, row_hi = g.M + l.slot;                  // tie-break index of the two rows of the slot
+                if (rank) { row_lo = rank[l.seg_local * R + row_lo]; row_hi = (P::ROWS == 2) ? rank[l.seg_local * R + row_hi] : -1; }
+                int k0 = INT_MIN;
+                if (row_lo >= 0) k0 = make_key(P::lo(u), p.slot_endadd[l.slot], row_lo);
+                if (P::ROWS == 2 && row_hi >= 0) k0 = std::max(k0, make_key(P::hi(u), p.slot_endadd[l.slot], row_hi));
                 key[l.seg_local] = std::max(key[l.seg_local], k0);
             }
         }
@@ -121,7 +126,7 @@ void emu_cta(const Plan &p, const Batch &b, int seg_first, int nseg_cta, int nma
     }
 }
 
-template <class P> using CtaFn = void (*)(const Plan &, const Batch &, int, int, int, uint32_t *const *, JR *const *);
+template <class P> using CtaFn = void (*)(const Plan &, const Batch &, int, int, int, uint32_t *const *, JR *const *, const int *);
 
 template <class P, int C> CtaFn<P> pick_t(int T)
 {
@@ -156,7 +161,23 @@ public:
         if (const char *e = getenv("SD_WAVE_BYTES")) return atoll(e);
         return (int64_t)1 << 30;
     }
-    void stage(const Batch &b, int s0, int s1) override { batch_ = &b; s0_ = s0; s1_ = s1; lay_ = make_cta_layout(plan_, b, s0, s1); }
+    void stage(const Batch &b, int s0, int s1) override
+    {
+        batch_ = &b; s0_ = s0; s1_ = s1; lay_ = make_cta_layout(plan_, b, s0, s1);
+        rank_.clear(); r2r_.clear();
+        if (ed_thr_ < 0) return;
+        // FilterMonomersForRead (main.cpp:135-149) on the host
+        const int R = ms_.nrows(), nseg = s1 - s0;
+        std::vector<uint8_t> rows((size_t)ms_.rows.size());
+        for (size_t x = 0; x < rows.size(); ++x) rows[x] = (uint8_t)"ACGTN"[ms_.rows[x]];
+        rank_.assign((size_t)nseg * R, -1); r2r_.assign((size_t)nseg * R, -1);
+        std::vector<int> dist((size_t)R);
+        for (int s = 0; s < nseg; ++s) {
+            for (int r = 0; r < R; ++r)
+                dist[(size_t)r] = hw_distance(rows.data() + ms_.row_off[r], ms_.rowlen(r), b.text + b.off[s0 + s], b.len(s0 + s));
+            build_filter_tables(dist.data(), R, ed_thr_, rank_.data() + (size_t)s * R, r2r_.data() + (size_t)s * R);
+        }
+    }
     void execute() override
     {
         const Geometry &g = plan_.g;
@@ -174,8 +195,9 @@ public:
             std::vector<uint32_t *> cp(g.NG);
             for (int q = 0; q < g.NG; ++q) cp[q] = codes_.data() + lay_.cta_code_off[g.NG > 1 ? c * g.NG + q : c];
             const int nmax = lay_.cta_nmax[g.NG > 1 ? c * g.NG : c];
-            if (g.packed) pick<Packed16>(g.C, g.T)(plan_, b, s0_ + first, cnt, nmax, cp.data(), jp.data());
-            else pick<Scalar32>(g.C, g.T)(plan_, b, s0_ + first, cnt, nmax, cp.data(), jp.data());
+            const int *rk = rank_.empty() ? nullptr : rank_.data() + (size_t)first * ms_.nrows();
+            if (g.packed) pick<Packed16>(g.C, g.T)(plan_, b, s0_ + first, cnt, nmax, cp.data(), jp.data(), rk);
+            else pick<Scalar32>(g.C, g.T)(plan_, b, s0_ + first, cnt, nmax, cp.data(), jp.data(), rk);
         }
         overflowed_ = g.packed && EmuFlags::overflow();
         if (bad_symbol()) throw PlanError{"segment contains a symbol outside ACGTN"};
@@ -198,7 +220,8 @@ public:
             cnt_[s] = traceback_segment(n, jr_.data() + lay_.seg_j_off[s],
                                         b.text + b.off[s0_ + s], rows_ascii_.data(), ms_.row_off.data(),
                                         plan_.sc.ins, plan_.sc.del, plan_.sc.mismatch, plan_.sc.match, code_at,
-                                        recs_.data() + lay_.seg_rec_off[s], n);
+                                        recs_.data() + lay_.seg_rec_off[s], n, true,
+                                        r2r_.empty() ? nullptr : r2r_.data() + (size_t)s * ms_.nrows());
         }
     }
     void fetch(BatchResult &out) override
@@ -217,7 +240,7 @@ private:
     Plan plan_; MonomerSet ms_;
     const Batch *batch_ = nullptr; int s0_ = 0, s1_ = 0;
     CtaLayout lay_;
-    std::vector<uint32_t> codes_; std::vector<JR> jr_; std::vector<uint8_t> rows_ascii_; std::vector<Record> recs_; std::vector<int> cnt_;
+    std::vector<uint32_t> codes_; std::vector<JR> jr_; std::vector<uint8_t> rows_ascii_; std::vector<int> rank_, r2r_; std::vector<Record> recs_; std::vector<int> cnt_;
     bool overflowed_ = false;
 };
 

@@ -92,6 +92,12 @@ Engine::Engine(const std::vector<std::string> &forward_monomers, const Scoring &
     if (devs_.empty()) throw PlanError{"no device backend"};
 }
 
+void Engine::set_ed_thr(int ed_thr)
+{
+    if (ed_thr > -1 && ms_.Lmax > 64 * SD_HW_BLOCKS) throw PlanError{"--ed_thr needs monomers of at most 1536 bp"};
+    for (auto &d : devs_) d->set_filter(ed_thr < 0 ? -1 : ed_thr);
+}
+
 void Engine::plan_for(const Batch &b)
 {
     int maxlen = 0;
@@ -270,13 +276,6 @@ int run_files(const std::string &reads_path, const std::string &monomers_path, i
     st = load_fasta(monomers_path, mons, diag);
     err.add(diag); err.flush();
     if (st) return st;
-    if (ed_thr > -1) {
-        // FilterMonomersForRead (main.cpp:135-149) re-orders the rows per segment; running the unfiltered DP
-        // instead would silently change the output, so refuse.
-        error = "the --ed_thr monomer pre-filter is not implemented in this build (ed_thr must be -1)";
-        err.add("ERROR: " + error + "\n");
-        return 3;
-    }
     if (part_size <= 0) { error = "part-size must be positive"; err.add("ERROR: " + error + "\n"); return 1; }
 
     // segmentation of all reads, in read order (main.cpp:70-81)
@@ -297,6 +296,7 @@ int run_files(const std::string &reads_path, const std::string &monomers_path, i
     BatchResult res;
     try {
         Engine eng(mons.seqs, sc, std::move(devs));
+        eng.set_ed_thr(ed_thr);          // FilterMonomersForRead (main.cpp:91-93,135-149) when ed_thr > -1
         Batch b;
         b.off.reserve(segs.size() + 1); b.off.push_back(0);
         size_t total = 0;

@@ -35,6 +35,7 @@ public:
     void stage(const Batch &b);                                 // whole batch resident, one wave per device
     double run_staged();                                        // returns kernel ms (max over devices)
     void fetch_staged(BatchResult &out);
+    void set_ed_thr(int ed_thr);                                // --ed_thr monomer pre-filter, -1 = off (main.cpp:135-149)
     const MonomerSet &monomers() const { return ms_; }
     EngineStats stats;
     int ndev() const { return (int)devs_.size(); }

@@ -209,6 +209,17 @@ Plan make_plan(const MonomerSet &ms, const Scoring &sc, int max_seg_len, int64_t
     return p;
 }
 
+void build_filter_tables(const int *dist, int R, int ed_thr, int *rank_of_row, int *row_of_rank)
+{
+    std::vector<std::pair<int, int>> v((size_t)R);
+    for (int r = 0; r < R; ++r) v[(size_t)r] = {dist[r], r};
+    std::sort(v.begin(), v.end());
+    int nf = 0;
+    for (int r = 0; r < R; ++r) { rank_of_row[r] = -1; row_of_rank[r] = -1; }
+    for (int x = 0; x < R; ++x)
+        if (x == 0 || v[(size_t)x].first <= ed_thr) { rank_of_row[v[(size_t)x].second] = nf; row_of_rank[nf] = v[(size_t)x].second; ++nf; }
+}
+
 CtaLayout make_cta_layout(const Plan &p, const Batch &b, int seg_begin, int seg_end)
 {
     CtaLayout l;

@@ -297,6 +297,51 @@ SD_HD int fetch_code(const uint32_t *codes_col, const Geometry &g, RowPlace pl, 
     return decode_code(w, g.packed, ncell, c, pl.half);
 }
 
+// Infix ("HW") edit distance of a DP row against a segment: unit-cost edit distance between the row and the best
+// substring of the segment.  This is what the reference's --ed_thr pre-filter asks edlib for
+// (MonomerEditDistance, main.cpp:128-133: edlibAlign(monomer, segment, k=-1, EDLIB_MODE_HW, EDLIB_TASK_DISTANCE)); the
+// distance is unique, so any exact algorithm agrees with edlib.  Myers/Hyyro bit-vector algorithm, 64 rows per word,
+// rows of up to 64*SD_HW_BLOCKS symbols.
+constexpr int SD_HW_BLOCKS = 24;
+SD_HD int hw_distance(const uint8_t *pat, int m, const uint8_t *text, int n, int (*code_of)(unsigned) = nullptr)
+{
+    (void)code_of;
+    const int B = (m + 63) / 64;
+    unsigned long long peq[5][SD_HW_BLOCKS], pv[SD_HW_BLOCKS], mv[SD_HW_BLOCKS];
+    for (int b = 0; b < B; ++b) { pv[b] = ~0ull; mv[b] = 0ull; for (int c = 0; c < 5; ++c) peq[c][b] = 0ull; }
+    for (int i = 0; i < m; ++i) {
+        const unsigned ch = pat[i];
+        const int c = ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : 4;
+        peq[c][i >> 6] |= 1ull << (i & 63);
+    }
+    const unsigned long long last_bit = 1ull << ((m - 1) & 63);
+    int score = m, best = m;
+    for (int j = 0; j < n; ++j) {
+        const unsigned ch = text[j];
+        const int c = ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : 4;
+        int hin = 0;                                     // row 0 of the HW table is all zeros: no horizontal delta
+        for (int b = 0; b < B; ++b) {
+            unsigned long long eq = peq[c][b];
+            const unsigned long long p = pv[b], mm = mv[b];
+            const unsigned long long xv = eq | mm;
+            if (hin < 0) eq |= 1ull;
+            const unsigned long long xh = (((eq & p) + p) ^ p) | eq;
+            unsigned long long ph = mm | ~(xh | p);
+            unsigned long long mh = p & xh;
+            const unsigned long long top = (b == B - 1) ? last_bit : (1ull << 63);
+            const int hout = (ph & top) ? 1 : ((mh & top) ? -1 : 0);
+            ph <<= 1; mh <<= 1;
+            if (hin < 0) mh |= 1ull; else if (hin > 0) ph |= 1ull;
+            pv[b] = mh | ~(xv | ph);
+            mv[b] = ph & xv;
+            hin = hout;
+        }
+        score += hin;
+        if (score < best) best = score;
+    }
+    return best;
+}
+
 // Traceback of one segment from the 2-bit backpointers (reference main.cpp:217-267).
 //   jr[i], i=1..n : J[i] = max_r H[i-1][r][last] (jr[n].j is the final score) and its lowest row.
 //   k == 0 cells are decided here from J and the two symbols involved (main.cpp:245 tests the insertion
@@ -305,12 +350,14 @@ SD_HD int fetch_code(const uint32_t *codes_col, const Geometry &g, RowPlace pl, 
 template <class CodeAt>
 SD_HD int traceback_segment(int n, const JR *jr, const uint8_t *seg, const uint8_t *rows,
                             const int *row_off, int ins, int del, int mismatch, int match,
-                            CodeAt code_at, Record *out, int cap, bool writer = true)
+                            CodeAt code_at, Record *out, int cap, bool writer = true, const int *rank2row = nullptr)
 {
+    // rank2row: with the --ed_thr pre-filter the DP rows of a segment are a re-ordered subset (main.cpp:135-149) and
+    // jr[].row holds the position in that list; rank2row maps it back to the row of the full set
     (void)del;
     int cnt = 0;
     int i = n - 1;
-    int r = jr[n].row;
+    int r = rank2row ? rank2row[jr[n].row] : jr[n].row;
     int last = row_off[r + 1] - row_off[r] - 1;
     int k = last;
     int end = i;
@@ -340,7 +387,7 @@ SD_HD int traceback_segment(int n, const JR *jr, const uint8_t *seg, const uint8
         if (writer) out[cnt] = rec;
         ++cnt;
         end_score = jr[i].j;
-        r = jr[i].row;
+        r = rank2row ? rank2row[jr[i].row] : jr[i].row;
         --i;
         last = row_off[r + 1] - row_off[r] - 1;
         k = last; end = i;

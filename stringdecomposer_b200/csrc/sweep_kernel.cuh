@@ -19,6 +19,7 @@ struct SweepArgs {
     int seg_stride;
     int wps;                // warps per segment (FAST only, <= 4)
     int kstride;            // ints per key buffer
+    const int *rank;        // --ed_thr pre-filter: [segment][row] position in the filtered list, -1 = filtered out; or null
     int *bad_symbol;        // set to 1 when a segment holds a symbol outside ACGTN
     TagRegs tr;             // TAGMASK / ONE of the policy, passed as run-time values (sweep_core.cuh: TagRegs)
 };
@@ -101,8 +102,14 @@ __global__ void sweep_kernel(const SweepArgs a)
     const bool kill_first = (t == 0), kill_last = (t == T - 1 && L == 1);
     const bool j_writer = active && slot == 0 && t == 0;
     const bool is_end = active && t == T - 1;
-    const int kc_lo = is_end ? key_const(endadd, slot) - 0x800 : -(1 << 30);
-    const int kc_hi = is_end ? key_const(endadd, a.M + slot) - 0x800 : -(1 << 30);
+    // tie-break index of the slot's rows: the row itself, or its position in the segment's filtered list (main.cpp:141-147)
+    int tb_lo = slot, tb_hi = a.M + slot;
+    if (a.rank && active) {
+        const int *rk = a.rank + (size_t)(first + seg_local) * (2 * a.M);
+        tb_lo = rk[slot]; tb_hi = (P::ROWS == 2) ? rk[a.M + slot] : -1;
+    }
+    const int kc_lo = (is_end && tb_lo >= 0) ? key_const(endadd, tb_lo) - 0x800 : -(1 << 30);
+    const int kc_hi = (is_end && tb_hi >= 0) ? key_const(endadd, tb_hi) - 0x800 : -(1 << 30);
     JR *jptr = a.jr + (active ? a.seg_j_off[first + seg_local] : 0);
     uint32_t *cptr = a.codes + a.cta_code_off[cta] + (size_t)tid * a.CW;
     const size_t cstride = (size_t)NT * a.CW;
@@ -239,6 +246,7 @@ struct GroupArgs {
     TagRegs tr;
     int *bad_symbol;
     unsigned long long *xbuf;                           // [ngslots][2][NG] exchange slots, zeroed before the launch
+    const int *rank;                                    // --ed_thr pre-filter ranks [segment][row] or null
     int ngslots;
     int *error;
 };
@@ -276,8 +284,6 @@ __global__ void sweep_group_kernel(const GroupArgs a)
     const bool kill_first = (t == 0), kill_last = (t == T - 1 && L == 1);
     const bool is_end = active && t == T - 1;
     const bool j_writer = grp == 0 && tid == 0;
-    const int kc_lo = is_end ? key_const(endadd, slot) - 0x800 : -(1 << 30);
-    const int kc_hi = is_end ? key_const(endadd, a.M + slot) - 0x800 : -(1 << 30);
     const uint4 *myprof = sprof + (size_t)(ginst * T + t) * a.qp;
     const int sym_stride = sgt * a.qp;
     int srcl[T > 2 ? T - 2 : 1];
@@ -307,6 +313,13 @@ __global__ void sweep_group_kernel(const GroupArgs a)
             schar[x] = (uint8_t)code;
         }
         __syncthreads();
+        int tb_lo = slot, tb_hi = a.M + slot;
+        if (a.rank && active) {
+            const int *rk = a.rank + (size_t)seg * (2 * a.M);
+            tb_lo = rk[slot]; tb_hi = (P::ROWS == 2) ? rk[a.M + slot] : -1;
+        }
+        const int kc_lo = (is_end && tb_lo >= 0) ? key_const(endadd, tb_lo) - 0x800 : -(1 << 30);
+        const int kc_hi = (is_end && tb_hi >= 0) ? key_const(endadd, tb_hi) - 0x800 : -(1 << 30);
         JR *jptr = a.jr + a.seg_j_off[seg];
         uint32_t *cptr = a.codes + a.cta_code_off[(size_t)seg * NG + grp] + (size_t)tid * a.CW;
         const size_t cstride = (size_t)NT * a.CW;

@@ -41,6 +41,7 @@ struct TbArgs {
     const uint8_t *rows; const int *row_off;
     int ins, del, mismatch, match;
     Record *scratch; const int64_t *seg_rec_off; int *counts;
+    const int *rank2row;    // --ed_thr pre-filter: [segment][rank] -> row of the full set, or null
     int invC;               // ceil(65536 / C): pos / C == (pos * invC) >> 16 for every pos < C*T (checked on the host)
 };
 
@@ -69,8 +70,9 @@ __global__ void __launch_bounds__(TB_WARPS * 32) traceback_kernel(const TbArgs a
     Record *out = a.scratch + a.seg_rec_off[s];
 
     // walk state (warp-uniform)
+    const int *r2r = a.rank2row ? a.rank2row + (size_t)s * (2 * g.M) : nullptr;
     int i = n - 1;
-    int r = jr[n].row;
+    int r = r2r ? r2r[jr[n].row] : jr[n].row;
     int last = a.row_off[r + 1] - a.row_off[r] - 1;
     int k = last, end = i, end_score = jr[n].j, cnt = 0;
     // window (per lane)
@@ -151,12 +153,22 @@ __global__ void __launch_bounds__(TB_WARPS * 32) traceback_kernel(const TbArgs a
         if (lane == 0) out[cnt] = rec;
         ++cnt;
         end_score = ji.j;
-        r = ji.row;
+        r = r2r ? r2r[ji.row] : ji.row;
         --i;
         last = a.row_off[r + 1] - a.row_off[r] - 1;
         k = last; end = i;
     }
     if (lane == 0) a.counts[s] = cnt;
+}
+
+// --ed_thr pre-filter: infix edit distance of every DP row against every staged segment (one thread per pair)
+__global__ void hw_distance_kernel(const uint8_t *bases, const int64_t *seg_off, int nseg, const uint8_t *rows, const int *row_off,
+                                   int R, int *dist)
+{
+    const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= (int64_t)nseg * R) return;
+    const int s = (int)(x / R), r = (int)(x - (int64_t)s * R);
+    dist[x] = hw_distance(rows + row_off[r], row_off[r + 1] - row_off[r], bases + seg_off[s], (int)(seg_off[s + 1] - seg_off[s]));
 }
 
 // dense[out_off[s] + x] = scratch[seg_rec_off[s] + cnt-1-x]   (reversal of main.cpp:268)
@@ -309,6 +321,25 @@ public:
         float ms = 0; SD_CUDA(cudaEventElapsedTime(&ms, ev_[0], ev_[1]));
         h2d_ms += ms;
         h2d_bytes += (int64_t)(nb + hoff_.size() * 8 + lay_.cta_nmax.size() * 4 + lay_.cta_code_off.size() * 8 + lay_.seg_j_off.size() * 16);
+        filter_on_ = ed_thr_ >= 0;
+        if (filter_on_) {
+            // FilterMonomersForRead (main.cpp:135-149): distances on the device, (distance,row) sort on the host
+            const int R = ms_.nrows();
+            const size_t np = (size_t)nseg_ * R;
+            d_dist_.need(np * 4); d_rank_.need(np * 4); d_r2r_.need(np * 4);
+            hw_distance_kernel<<<(unsigned)((np + 63) / 64), 64, 0, st_>>>(d_bases_.as<uint8_t>(), d_segoff_.as<int64_t>(), nseg_,
+                                                                        d_rows_.as<uint8_t>(), d_rowoff_.as<int>(), R, d_dist_.as<int>());
+            SD_CUDA(cudaGetLastError());
+            hdist_.resize(np); hrank_.resize(np); hr2r_.resize(np);
+            SD_CUDA(cudaMemcpyAsync(hdist_.data(), d_dist_.p, np * 4, cudaMemcpyDeviceToHost, st_));
+            SD_CUDA(cudaStreamSynchronize(st_));
+            for (int s = 0; s < nseg_; ++s)
+                build_filter_tables(hdist_.data() + (size_t)s * R, R, ed_thr_, hrank_.data() + (size_t)s * R, hr2r_.data() + (size_t)s * R);
+            SD_CUDA(cudaMemcpyAsync(d_rank_.p, hrank_.data(), np * 4, cudaMemcpyHostToDevice, st_));
+            SD_CUDA(cudaMemcpyAsync(d_r2r_.p, hr2r_.data(), np * 4, cudaMemcpyHostToDevice, st_));
+            SD_CUDA(cudaStreamSynchronize(st_));
+            launches += 1;
+        }
         (void)g;
     }
 
@@ -322,6 +353,7 @@ public:
         a.cta_nmax = d_ctanmax_.as<int>(); a.cta_code_off = d_ctacode_.as<int64_t>(); a.seg_j_off = d_segj_.as<int64_t>();
         a.codes = d_codes_.as<uint32_t>(); a.jr = d_jr_.as<JR>();
         a.bad_symbol = d_flag_.as<int>();
+        a.rank = filter_on_ ? d_rank_.as<int>() : nullptr;
         a.slot_len = d_slotlen_.as<int>(); a.slot_endadd = d_slotend_.as<int>();
         a.nslots = g.nslots; a.M = g.M; a.NS = g.NS; a.NT = g.NT; a.CW = g.CW; a.nsl = plan_.nsl; a.qp = plan_.qp;
         a.ins = plan_.sc.ins; a.del = plan_.sc.del; a.deadz = plan_.deadz;
@@ -352,6 +384,7 @@ public:
         a.seg_stride = seg_stride;
         a.tr = g.packed ? tag_regs<Packed16>() : tag_regs<Scalar32>();
         a.bad_symbol = d_flag_.as<int>(); a.error = d_flag_.as<int>() + 1;
+        a.rank = filter_on_ ? d_rank_.as<int>() : nullptr;
         const int spw = 32 / g.T;
         const size_t sgt = (size_t)(g.NT / 32) * spw * g.T;
         const size_t smem = (size_t)5 * sgt * plan_.qp * 16 + 36 * 4 + (size_t)seg_stride;
@@ -384,6 +417,7 @@ public:
         t.rows = d_rows_.as<uint8_t>(); t.row_off = d_rowoff_.as<int>();
         t.ins = plan_.sc.ins; t.del = plan_.sc.del; t.mismatch = plan_.sc.mismatch; t.match = plan_.sc.match;
         t.scratch = d_scratch_.as<Record>(); t.seg_rec_off = d_segrec_.as<int64_t>(); t.counts = d_counts_.as<int>();
+        t.rank2row = filter_on_ ? d_r2r_.as<int>() : nullptr;
         t.invC = (65536 + g.C - 1) / g.C;
         for (int pos = 0; pos < g.C * g.T; ++pos)
             if (((pos * t.invC) >> 16) != pos / g.C) throw PlanError{"internal: reciprocal division inexact"};
@@ -446,10 +480,12 @@ private:
     std::vector<int64_t> hoff_, houtoff_;
     std::vector<int> hcnt_;
     std::vector<uint8_t> rows_ascii_;
+    std::vector<int> hdist_, hrank_, hr2r_;
+    bool filter_on_ = false;
     int64_t budget_ = 0;
     DevBuf d_prof_, d_slotlen_, d_slotend_, d_rows_, d_rowoff_;
     DevBuf d_bases_, d_segoff_, d_ctanmax_, d_ctacode_, d_segj_, d_segrec_;
-    DevBuf d_flag_, d_xchg_, d_codes_, d_jr_, d_scratch_, d_counts_, d_outoff_, d_dense_;
+    DevBuf d_flag_, d_xchg_, d_dist_, d_rank_, d_r2r_, d_codes_, d_jr_, d_scratch_, d_counts_, d_outoff_, d_dense_;
 };
 
 } // namespace

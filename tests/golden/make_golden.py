@@ -101,6 +101,19 @@ def main():
     p = subprocess.run([REF, "a", "b", "1"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     cases.append({"name": "argc_lt_5", "note": "usage on stdout, status 255 (main.cpp:375-379)", "reads_fa": None, "monomers_fa": None,
                   "argv_raw": ["a", "b", "1"], "status": p.returncode, "stdout": p.stdout.decode(), "stderr": p.stderr.decode()})
+    # --ed_thr pre-filter (FilterMonomersForRead, main.cpp:135-149): argc == 11, scores ignored, rows re-ordered per segment
+    for thr in (0, 5, 12, 30, 200):
+        add("ed_thr_%d" % thr, fasta(["e1", "e2"], [read[10000:14000], read[47000:49500]]), mono_txt, [2, 1000, 300, -1, -1, -1, 1, thr],
+            "argc == 11 with ed_thr = %d" % thr)
+    add("ed_thr_dups", fasta(["d"], [read[60000:63000]]), fasta(["X3", "B", "X2", "X1"], [ms[0], ms[1], ms[0], ms[0]]), [2, 1000, 300, -1, -1, -1, 1, 20],
+        "duplicate monomers: equal distances are ordered by row index")
+    add("ed_thr_short_monomers", fasta(["sm"], ["".join(rnd.choice("ACGT") for _ in range(700))]),
+        fasta(["m1", "m2", "m3", "m4"], ["A", "AC", "GTT", "ACGTACG"]), [1, 300, 100, -1, -1, -1, 1, 1])
+    for seed in range(12):
+        al = ["AT", "AC", "ACGT", "ACGTN"][seed % 4]
+        rnn, rr, mnn, mm = synth.random_case(2000 + seed, alphabet=al)
+        add("ed_thr_fuzz_%02d_%s" % (seed, al), fasta(rnn, rr), fasta(mnn, mm), [2, [50, 120, 300][seed % 3], [10, 30, 100][seed % 3], -1, -1, -1, 1, [0, 1, 2, 4, 8, 16][seed % 6]],
+            "random case seed %d with the pre-filter" % (2000 + seed))
     # random fuzz cases (tiny alphabets, duplicates, odd scoring)
     scorings = [(-1, -1, -1, 1), (-2, -2, -3, 1), (-3, -2, -4, 2), (0, -1, -1, 1), (-1, 0, -2, 2), (-4, -1, -1, 1), (-1, -4, -1, 2)]
     geoms = [(50, 10), (120, 30), (300, 100), (5000, 500)]

@@ -130,30 +130,41 @@ def test_unsupported_inputs_fail_loudly():
     with pytest.raises(SdError):
         d.decompose(["ACGT", ""])
     d.close()
-    # ed_thr pre-filter is not built: the CLI must refuse instead of silently running the unfiltered DP
-    case = dict(cases.load_cases()[0])
-    case["argv_tail"] = ["1", "1000", "300", "-1", "-1", "-1", "1", "5"]
-    st, out, err = cases.run_case(cases.DP_EMU, case)
-    assert st != 0 and out == "" and "ed_thr" in err
 
 
-@pytest.mark.parametrize("sg", ["1", "4", "8"])
-def test_emulated_group_mode_splits_the_monomer_set(sg):
-    # several CTAs per segment (the layout used for monomer sets that do not fit one CTA), forced on small inputs
-    picked = [c for c in cases.load_cases() if c["name"] in ("multi_read", "dup_monomers_rev", "short_monomers", "N_in_monomer")]
-    for case in picked:
-        cases.check_case(cases.DP_EMU, case, env={"SD_GROUP_SLOTS": sg})
-    cases.check_case(cases.DP_EMU, picked[0], env={"SD_GROUP_SLOTS": sg, "SD_FORCE_S32": "1"})
+def test_hw_distance_against_plain_dp():
+    # the bit-vector infix edit distance of the --ed_thr pre-filter (main.cpp:128-133) vs the textbook DP
+    from stringdecomposer_b200 import hw_distance
+    rng = np.random.default_rng(11)
+    for trial in range(150):
+        al = list("ACGTN"[:int(rng.integers(1, 6))])
+        m = int(rng.integers(1, 64 if trial % 3 else 400)); n = int(rng.integers(1, 500))
+        pat = "".join(rng.choice(al, m)); txt = "".join(rng.choice(al, n))
+        if trial % 4 == 0 and n > m:                      # plant a noisy copy so that small distances occur
+            k = int(rng.integers(0, n - m))
+            txt = txt[:k] + pat + txt[k + m:]
+        prev = [0] * (n + 1)
+        for i in range(1, m + 1):
+            cur = [i] + [0] * n
+            for j in range(1, n + 1):
+                cur[j] = min(prev[j - 1] + (pat[i - 1] != txt[j - 1]), prev[j] + 1, cur[j - 1] + 1)
+            prev = cur
+        assert hw_distance(pat, txt, flavour="emu") == min(prev)
+        assert hw_distance(pat, txt, flavour="cuda") == min(prev)
 
 
-def test_emulated_large_monomer_set_needs_groups():
-    rn, reads, mn, mons = synth.config5(n_monomers=70, total=20_000)
+def test_ed_thr_filter_through_the_api():
+    names, mons = synth.load_dxz1()
+    seg = synth.hor_array(mons, 1200, 0.03, seed=3)
     d = Decomposer(mons, flavour="emu")
-    segs = [reads[0][:600], reads[1][:450]]
-    recs, off = d.decompose(segs)
-    st = d.stats()
-    assert st["NT"] <= 512
-    for j, s in enumerate(segs):
-        want = sd_oracle.align_segment(s, mons)
-        assert [(int(r["row"]), int(r["start"]), int(r["end"]), float(r["score"])) for r in recs[off[j]:off[j + 1]]] == want
+    base, _ = d.decompose([seg])
+    d.set_ed_thr(10 ** 6)                                  # nothing filtered, but rows re-ordered by distance
+    allr, _ = d.decompose([seg])
+    d.set_ed_thr(0)                                        # only the closest row survives
+    one, _ = d.decompose([seg])
+    d.set_ed_thr(-1)
+    again, _ = d.decompose([seg])
+    assert (again == base).all()
+    assert len(set(one["row"])) == 1
+    assert allr["start"][0] == 0 and allr["end"][-1] == len(seg) - 1
     d.close()
