@@ -75,9 +75,23 @@ __global__ void __launch_bounds__(TB_WARPS * 32) traceback_kernel(const TbArgs a
     int r = r2r ? r2r[jr[n].row] : jr[n].row;
     int last = a.row_off[r + 1] - a.row_off[r] - 1;
     int k = last, end = i, end_score = jr[n].j, cnt = 0;
-    // window (per lane)
+    // window (per lane) and the prefetched next window (columns i0-32-lane along the same diagonal)
     int i0 = -1000, row0 = -1, half = 0;
     uint32_t w0 = 0, w1 = 0, w2 = 0; int wb = 0; bool colok = false;
+    uint32_t n0 = 0, n1 = 0, n2 = 0; int nwb = 0; bool ncolok = false; int ni0 = -2000;
+    const uint32_t *rowbase = nullptr;                  // first word of the current row's slot in column 0
+    auto load_window = [&](int iw, int kw, uint32_t &x0, uint32_t &x1, uint32_t &x2, int &xb, bool &xok) {
+        const int c = iw - lane;
+        xok = c >= 0;
+        if (xok) {
+            const int kp = max(kw - lane, 0);
+            const int t = (kp * invC) >> 16;
+            const int wl = t * CW + ((kp - t * C) >> cshift);
+            xb = min(max(wl - 1, 0), max(maxwl - 2, 0));
+            const uint32_t *col = rowbase + (size_t)c * cstride;
+            x0 = col[xb]; x1 = col[min(xb + 1, maxwl)]; x2 = col[min(xb + 2, maxwl)];
+        }
+    };
 
     for (;;) {
         if (k == 0) {
@@ -95,22 +109,20 @@ __global__ void __launch_bounds__(TB_WARPS * 32) traceback_kernel(const TbArgs a
             if (ins_move) { --i; continue; }
         } else {
             if (r != row0 || i > i0 || i <= i0 - 32) {
-                // refill: lane d loads the words around cell k-d of column i-d
-                i0 = i; row0 = r;
-                const RowPlace pl = place_row(g, seg_local, r);
-                half = pl.half;
-                const uint32_t *cbase = a.codes + a.cta_code_off[cta0 + (g.NG > 1 ? pl.grp : 0)];
-                const size_t word0 = (size_t)lane_tid(g.T, pl.ginst, 0) * CW;
-                const int c = i - lane;
-                colok = c >= 0;
-                if (colok) {
-                    const int kp = max(k - lane, 0);
-                    const int t = (kp * invC) >> 16;
-                    const int wl = t * CW + ((kp - t * C) >> cshift);
-                    wb = min(max(wl - 1, 0), max(maxwl - 2, 0));
-                    const uint32_t *col = cbase + (size_t)c * cstride + word0;
-                    w0 = col[wb]; w1 = col[min(wb + 1, maxwl)]; w2 = col[min(wb + 2, maxwl)];
+                if (r == row0 && i == ni0) {
+                    // the walk ran straight into the prefetched window: adopt it (if the path drifted out of its three
+                    // words the decode below notices and forces a reload) and prefetch the one after it
+                    i0 = ni0; w0 = n0; w1 = n1; w2 = n2; wb = nwb; colok = ncolok;
+                } else {
+                    // refill: lane d loads the words around cell k-d of column i-d
+                    i0 = i; row0 = r;
+                    const RowPlace pl = place_row(g, seg_local, r);
+                    half = pl.half;
+                    rowbase = a.codes + a.cta_code_off[cta0 + (g.NG > 1 ? pl.grp : 0)] + (size_t)lane_tid(g.T, pl.ginst, 0) * CW;
+                    load_window(i, k, w0, w1, w2, wb, colok);
                 }
+                ni0 = i0 - 32;
+                load_window(ni0, k - 32, n0, n1, n2, nwb, ncolok);
             }
             const int dcur = i0 - i;
             const int kd = k - (lane - dcur);
