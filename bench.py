@@ -335,7 +335,7 @@ def main():
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one sweep_kernel launch on this workload (ncu --set full, profiles/)
-TRAFFIC_BYTES_PER_LAUNCH = None
+TRAFFIC_BYTES_PER_LAUNCH = 3.62e9     # profiles/r01_sweep_r1_final.md: 0.288 GB read + 3.335 GB written (2.26 GB algorithmic)
 
 
 def sum_len(reads):

@@ -8,17 +8,20 @@
 // Shift every cell by its position, Hh[i][k] = H[i][k] - i*ins - k*del, and the moves become
 //   left: Hh[i][k-1]          up: Hh[i-1][k]          diag: Hh[i-1][k-1] + s''
 //   jump: B[i] + s''          with s'' = s - ins - del and B[i] = J[i] - (i-1)*ins + del,
-// i.e. the deletion chain is a pure prefix-max and the insertion move is free.  Cells are stored
-// relative to the column base B[i] (so the jump operand is the constant 0) and multiplied by 4 with
-// a 2-bit priority tag in the low bits (left/del=3 > up/ins=2 > diag=1 > jump=0), so that a plain
+// i.e. the deletion chain is a pure prefix-max and the insertion move is free.  Values are multiplied by 4 and
+// carry a 2-bit priority tag in the low bits (left/del=3 > up/ins=2 > diag=1 > jump=0), so that a plain
 // integer max reproduces the reference's traceback priority del > ins > diag > jump
 // (main.cpp:242-253) and the backpointer is (3 - tag) = reference code {0:del,1:ins,2:diag,3:jump}.
 // State registers hold U = 4*rel + 2 ("tag-2 form": already the insertion candidate of the next column);
 // rel is relative to a per-segment reference base Bref that is moved ("rebase") only when the jump operand
 // 4*(B[i]-Bref) leaves +-SD_REBASE_TH, so no per-column renormalisation work is needed.
-// Per cell and column the sweep issues: 2 VIADDMNMX (one of them independent of J[i], so it runs before the
-// column barrier), 0.5 VIMNMX3 (lane maximum for the cross-lane scan), VIMNMX + LOP3 (deletion chain), and three
-// plain integer ops that ptxas places on the FMA pipe (IMAD.IADD / IMAD): backpointer extraction and re-tagging.
+// Per register (two DP cells when packed) and column the sweep issues, on the integer ALU pipe:
+//   VIADDMNMX  m = max(U[k-1] + p[k], U[k])      diag vs up; independent of J[i]  (lane_pre / lane_pass2_pre)
+//   VIADDMNMX  m = max(p[k] + j, m)              jump candidate                    (lane_post)
+//   1/2 VIMNMX3                                  lane maximum for the cross-lane scan
+//   VIADDMNMX  h = max(Uleft + 1, m)             deletion chain, left wins ties    (lane_pass2_pre)
+//   LOP3       U = (h | 3) ^ 1                   re-tag
+// and on the FMA pipe IMAD + IMAD.IADD for the backpointer digits w = w*4 + U - h.
 #pragma once
 #include <stdint.h>
 
@@ -79,8 +82,6 @@ struct Packed16 {
         return emu_pack(emu_lo(a) + emu_lo(b), emu_hi(a) + emu_hi(b));
 #endif
     }
-    static SD_HD uint32_t tag3(uint32_t a) { return a | TAGMASK; }
-    static SD_HD uint32_t tag2(uint32_t a) { return (a | TAGMASK) ^ ONE; }     // one LOP3
 };
 
 // One DP row per 32-bit register; used when the score range does not provably fit 14+2 bits.
@@ -108,8 +109,6 @@ struct Scalar32 {
 #endif
     }
     static SD_HD uint32_t add(uint32_t a, uint32_t b) { return a + b; }
-    static SD_HD uint32_t tag3(uint32_t a) { return a | 3u; }
-    static SD_HD uint32_t tag2(uint32_t a) { return (a | 3u) ^ 1u; }
 };
 
 // TAGMASK and ONE as run-time register values: ptxas then folds (h | TAGMASK) ^ ONE into one three-register LOP3
