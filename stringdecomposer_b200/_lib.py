@@ -31,9 +31,12 @@ _libs = {}
 
 
 def library_path(flavour="cuda"):
-    """Path of the in-tree shared library.  ``flavour="emu"`` is the host emulator used by the CPU tests only."""
-    name = {"cuda": "libsd_b200.so", "emu": "libsd_emu.so"}[flavour]
-    return os.path.join(_HERE, name)
+    """Path of the in-tree product library (CUDA, sm_100a).  Any other value of ``flavour`` is taken as the path of a
+    library with the same C ABI -- the CPU test-suite passes its host emulator (tests/emu) this way; the package itself
+    ships no CPU implementation."""
+    if flavour == "cuda":
+        return os.path.join(_HERE, "libsd_b200.so")
+    return str(flavour)
 
 
 def load_library(flavour="cuda"):

@@ -1,4 +1,4 @@
-// emu.cpp -- host emulation of the sweep and traceback kernels.  CPU TEST-SUITE ONLY.
+// tests/emu/emu.cpp -- host emulation of the sweep and traceback kernels.  CPU TEST-SUITE ONLY (built by tests/emu/Makefile).
 //
 // Runs the very same per-lane functions as the sm_100a kernels (sweep_core.cuh) with the CTA-level
 // choreography (shuffles, prefix-max scan across the lanes of a slot, key exchange, barrier) replaced by

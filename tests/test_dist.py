@@ -17,11 +17,12 @@ WORKER = textwrap.dedent("""
     from stringdecomposer_b200 import synth, Decomposer
     from stringdecomposer_b200.hostpipe import segment_reads
     import sd_oracle
+    EMU = %r
     names, mons = synth.load_dxz1()
     arr = synth.hor_array(mons, 6000, 0.02, seed=40)          # same array everywhere; ranks take alternating shards
-    segs, where = segment_reads([arr], 1000, 300, flavour="emu")
+    segs, where = segment_reads([arr], 1000, 300, flavour=EMU)
     mine = [s for i, s in enumerate(segs) if i %% ws == rank]
-    d = Decomposer(mons, flavour="emu")
+    d = Decomposer(mons, flavour=EMU)
     recs, off = d.decompose(mine)
     ok = 1
     for j, s in enumerate(mine):
@@ -39,7 +40,7 @@ WORKER = textwrap.dedent("""
 
 def test_two_rank_sharding_gloo(tmp_path):
     script = tmp_path / "worker.py"
-    script.write_text(WORKER % (cases.ROOT, os.path.join(cases.ROOT, "oracle")))
+    script.write_text(WORKER % (cases.ROOT, os.path.join(cases.ROOT, "oracle"), cases.EMU_LIB))
     p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29517", str(script)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
     assert p.returncode == 0, p.stderr.decode()[-2000:]
@@ -56,8 +57,8 @@ def test_multi_device_engine_split_is_exact():
     names, mons = synth.load_dxz1()
     arr = synth.hor_array(mons, 5000, 0.02, seed=41)
     from stringdecomposer_b200.hostpipe import segment_reads
-    segs, _ = segment_reads([arr], 700, 200, flavour="emu")
-    d = Decomposer(mons, flavour="emu")
+    segs, _ = segment_reads([arr], 700, 200, flavour=cases.EMU_LIB)
+    d = Decomposer(mons, flavour=cases.EMU_LIB)
     whole, woff = d.decompose(segs)
     a, aoff = d.decompose(segs[:3])
     b, boff = d.decompose(segs[3:])

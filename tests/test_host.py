@@ -43,7 +43,7 @@ def test_product_library_has_no_cpu_path():
                                        (1301, 1000, 300), (94871, 5000, 500), (5499, 5000, 500), (5500, 5000, 500), (5501, 5000, 500),
                                        (10000, 5000, 500), (700, 700, 50), (20000, 20000, 500), (123456, 777, 1000)])
 def test_segmentation_matches_oracle(L, part, ov):
-    assert segment_read(L, part, ov, flavour="emu") == sd_oracle.segment_read(L, part, ov)
+    assert segment_read(L, part, ov, flavour=cases.EMU_LIB) == sd_oracle.segment_read(L, part, ov)
     assert segment_read(L, part, ov, flavour="cuda") == sd_oracle.segment_read(L, part, ov)
 
 
@@ -57,7 +57,7 @@ def test_postprocess_matches_oracle():
         recs["end"] = starts + rng.integers(0, 400, n)
         recs["row"] = rng.integers(0, 24, n)
         recs["score"] = rng.integers(-50, 200, n)
-        got = postprocess(recs, flavour="emu")
+        got = postprocess(recs, flavour=cases.EMU_LIB)
         want = sd_oracle.postprocess([(int(r["row"]), int(r["start"]), int(r["end"]), float(r["score"])) for r in recs])
         assert [(int(r["row"]), int(r["start"]), int(r["end"]), float(r["score"])) for r in got] == want
 
@@ -84,7 +84,7 @@ def test_emulated_kernels_small_slots(geom):
         want = sd_oracle.decompose_reads(rn, rr, mn, mm, part_size=150, overlap=40)
         os.environ["SD_GEOM"] = geom
         try:
-            got = decompose_reads(rn, rr, mn, mm, part_size=150, overlap=40, flavour="emu")
+            got = decompose_reads(rn, rr, mn, mm, part_size=150, overlap=40, flavour=cases.EMU_LIB)
         finally:
             del os.environ["SD_GEOM"]
         assert got == want
@@ -102,7 +102,7 @@ def test_waves_do_not_change_the_result():
     want = sd_oracle.decompose_reads(rn, rr, mn, mm, part_size=300, overlap=100)
     os.environ["SD_WAVE_BYTES"] = "200000"
     try:
-        got = decompose_reads(rn, rr, mn, mm, part_size=300, overlap=100, flavour="emu")
+        got = decompose_reads(rn, rr, mn, mm, part_size=300, overlap=100, flavour=cases.EMU_LIB)
     finally:
         del os.environ["SD_WAVE_BYTES"]
     assert got == want
@@ -113,7 +113,7 @@ def test_score_range_switch():
     names, mons = synth.load_dxz1()
     seg = synth.hor_array(mons, 1500, 0.05, seed=9)
     for sc, packed in (((-1, -1, -1, 1), 1), ((-2, -2, -3, 1), 1), ((-9, -30, -9, 2), 0), ((1, -1, -1, 1), 0)):
-        d = Decomposer(mons, *sc, flavour="emu")
+        d = Decomposer(mons, *sc, flavour=cases.EMU_LIB)
         recs, off = d.decompose([seg])
         assert d.stats()["packed"] == packed
         want = sd_oracle.align_segment(seg, mons, sc)
@@ -123,8 +123,8 @@ def test_score_range_switch():
 
 def test_unsupported_inputs_fail_loudly():
     with pytest.raises(SdError):
-        Decomposer(["ACGU"], flavour="emu")
-    d = Decomposer(["ACGT"], flavour="emu")
+        Decomposer(["ACGU"], flavour=cases.EMU_LIB)
+    d = Decomposer(["ACGT"], flavour=cases.EMU_LIB)
     with pytest.raises(SdError):
         d.decompose(["ACGTX"])
     with pytest.raises(SdError):
@@ -149,14 +149,14 @@ def test_hw_distance_against_plain_dp():
             for j in range(1, n + 1):
                 cur[j] = min(prev[j - 1] + (pat[i - 1] != txt[j - 1]), prev[j] + 1, cur[j - 1] + 1)
             prev = cur
-        assert hw_distance(pat, txt, flavour="emu") == min(prev)
+        assert hw_distance(pat, txt, flavour=cases.EMU_LIB) == min(prev)
         assert hw_distance(pat, txt, flavour="cuda") == min(prev)
 
 
 def test_ed_thr_filter_through_the_api():
     names, mons = synth.load_dxz1()
     seg = synth.hor_array(mons, 1200, 0.03, seed=3)
-    d = Decomposer(mons, flavour="emu")
+    d = Decomposer(mons, flavour=cases.EMU_LIB)
     base, _ = d.decompose([seg])
     d.set_ed_thr(10 ** 6)                                  # nothing filtered, but rows re-ordered by distance
     allr, _ = d.decompose([seg])

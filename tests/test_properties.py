@@ -5,6 +5,7 @@ import os
 import pytest
 from hypothesis import HealthCheck, given, settings, strategies as st
 
+import cases
 import sd_oracle
 from stringdecomposer_b200 import Decomposer
 
@@ -55,7 +56,7 @@ def run(flavour, problem):
 @settings(max_examples=120, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
 @given(problems())
 def test_emulated_kernels_match_oracle(problem):
-    run("emu", problem)
+    run(cases.EMU_LIB, problem)
 
 
 @pytest.mark.gpu
