@@ -165,12 +165,17 @@ Plan make_plan(const MonomerSet &ms, const Scoring &sc, int max_seg_len, int64_t
         if (!gC) throw PlanError{"monomers longer than 1536 bp are not supported by this build"};
         const int spw = 32 / gT, qpc = ((gC + 3) / 4) | 1;
         const size_t per_slot = (size_t)5 * qpc * gT * 16;
-        // large groups win (fewer partners to wait for per column, measured): one CTA per SM, up to 16 warps
-        int sg = (int)std::min<size_t>((size_t)(180 * 1024) / per_slot, (size_t)16 * spw);
+        // The per-column exchange costs ~1-2 us whatever the CTA computes and grows with the number of partner CTAs, so
+        // groups are large (8 warps per segment) and a CTA sweeps its group for two segments at once (they share the
+        // profile slice).  Measured on 1000 monomers: 8 warps x 2 segments 1.11 TCUPS, 12 x 1 1.07, 5 x 3 0.70.
+        int sg = (int)std::min<size_t>((size_t)(140 * 1024) / per_slot, (size_t)8 * spw);
         sg = std::max(sg / spw * spw, spw);
         if (force_sg > 0) sg = std::max(force_sg / spw * spw, spw);
         sg = std::min(sg, (nslots + spw - 1) / spw * spw);
-        bestC = gC; bestT = gT; bestNS = 1; bestNT = (sg + spw - 1) / spw * 32;
+        bestC = gC; bestT = gT; bestNT = (sg + spw - 1) / spw * 32;
+        bestNS = std::max(1, std::min({2, 65536 / (bestNT * 112), 256 / ((nslots + sg - 1) / sg)}));   // registers; <= 256 exchange slots
+        if (fNS) bestNS = std::min(fNS, 1024 / bestNT);
+        bestNS = (int)std::max<int64_t>(1, std::min<int64_t>(bestNS, nseg_hint));
         g.NG = (nslots + sg - 1) / sg;
         g.SG = sg;
         if (g.NG == 1) g.SG = nslots;

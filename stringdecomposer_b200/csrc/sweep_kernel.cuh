@@ -230,22 +230,23 @@ __global__ void sweep_kernel(const SweepArgs a)
 
 // ---------------------------------------------------------------------------------------------------------------
 // Group sweep: monomer sets that do not fit one CTA (threads, registers, or the shared-memory profile table).
-// The slots are split into NG groups; CTA (gslot, grp) sweeps slot group `grp` of the segments gslot, gslot+ngslots, ...
-// and the NG CTAs of a segment meet once per column in global memory: every CTA publishes (epoch, key) in its own
-// slot with a release store and polls the others' slots with acquire loads (no atomics, bounded spin).  All CTAs are co-resident (cooperative launch), so the spin cannot deadlock; a
-// time-out raises *error instead of hanging.
+// The slots are split into NG groups.  CTA (gslot, grp) holds the profile slice of group `grp` and sweeps that group
+// for NS segments at a time (segment blocks gslot, gslot+ngslots, ...; the NS segments share the profile slice and the
+// column exchange, which amortises its latency).  The NG CTAs of a block meet once per column in global memory:
+// every CTA publishes (epoch, key) per segment in its own slots with relaxed 64-bit stores and warp 0 polls the
+// NG*NS slots of the current buffer (no atomics, two buffers, bounded spin).  All CTAs are co-resident (cooperative
+// launch), so the spin cannot deadlock; a time-out raises *error instead of hanging.
 struct GroupArgs {
     const uint4 *prof; int nsl_total, qp;              // [5][nsl_total][qp] uint4
     const uint8_t *bases; const int64_t *seg_off; int nseg;
     const int64_t *cta_code_off; const int64_t *seg_j_off;
     uint32_t *codes; JR *jr;
     const int *slot_len; const int *slot_endadd;
-    int nslots, M, NT, CW, NG, SG;
+    int nslots, M, NT, CW, NG, SG, NS;                 // NT: threads per (segment, group) = layout stride; block = NS*NT
     int ins, del, deadz;
-    int seg_stride;
     TagRegs tr;
     int *bad_symbol;
-    unsigned long long *xbuf;                           // [ngslots][2][NG] exchange slots, zeroed before the launch
+    unsigned long long *xbuf;                           // [ngslots][2][NG][NS] exchange slots, zeroed before the launch
     const int *rank;                                    // --ed_thr pre-filter ranks [segment][row] or null
     int ngslots;
     int *error;
@@ -256,23 +257,25 @@ __global__ void sweep_group_kernel(const GroupArgs a)
 {
     extern __shared__ uint4 smem_u4[];
     constexpr int SPW = 32 / T;
-    const int NT = a.NT, NG = a.NG;
-    const int sgt = (NT / 32) * SPW * T;                // profile rows kept per CTA (slot lanes)
-    uint4 *sprof = smem_u4;                             // [5][sgt][qp]
-    int *swk = reinterpret_cast<int *>(sprof + (size_t)5 * sgt * a.qp);     // [32] warp keys, [32] = global key
-    uint8_t *schar = reinterpret_cast<uint8_t *>(swk + 36);
+    const int NT = a.NT, NG = a.NG, NS = a.NS;
+    const int wps = NT >> 5;                             // warps per segment in this CTA
+    const int sgt = wps * SPW * T;                       // profile rows kept per CTA (slot lanes)
+    uint4 *sprof = smem_u4;                              // [5][sgt][qp]
+    int *swk = reinterpret_cast<int *>(sprof + (size_t)5 * sgt * a.qp);     // [NS][wps] warp keys
+    int *sres = swk + NS * wps;                          // [NS] block-wide keys of the column
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = NT >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int gslot = blockIdx.x / NG, grp = blockIdx.x - gslot * NG;
+    const int seg_local = warp / wps, wseg = warp - seg_local * wps;
     const int siw = lane / T, t = lane - siw * T;
     const bool lane_ok = siw < SPW;
-    const int ginst = warp * SPW + (lane_ok ? siw : 0);
+    const int ginst = wseg * SPW + (lane_ok ? siw : 0);
     int slot = grp * a.SG + ginst;
-    const bool active = lane_ok && ginst < a.SG && slot < a.nslots;
+    const bool slot_ok = lane_ok && ginst < a.SG && slot < a.nslots;
     if (slot >= a.nslots) slot = a.nslots - 1;
 
     // profile slice of this group: rows [grp*SG*T, grp*SG*T + sgt) of every symbol (clamped at the table end)
-    for (int x = tid; x < 5 * sgt * a.qp; x += NT) {
+    for (int x = tid; x < 5 * sgt * a.qp; x += NS * NT) {
         const int sym = x / (sgt * a.qp), r = x - sym * (sgt * a.qp);
         const int row = min(grp * a.SG * T + r / a.qp, a.nsl_total - 1);
         sprof[x] = a.prof[((size_t)sym * a.nsl_total + row) * a.qp + (r % a.qp)];
@@ -282,15 +285,14 @@ __global__ void sweep_group_kernel(const GroupArgs a)
     const uint32_t deadu = P::splat(a.deadz - 1);
     const TagRegs tr = a.tr;
     const bool kill_first = (t == 0), kill_last = (t == T - 1 && L == 1);
-    const bool is_end = active && t == T - 1;
-    const bool j_writer = grp == 0 && tid == 0;
     const uint4 *myprof = sprof + (size_t)(ginst * T + t) * a.qp;
     const int sym_stride = sgt * a.qp;
     int srcl[T > 2 ? T - 2 : 1];
 #pragma unroll
     for (int d = 1; d <= T - 2; ++d) srcl[d - 1] = lane - min(d, t);
-    unsigned long long *xbuf = a.xbuf + (size_t)gslot * 2 * NG;     // [2 buffers][NG] (epoch << 32 | key)
+    unsigned long long *xbuf = a.xbuf + (size_t)gslot * 2 * NG * NS;
     unsigned gcol = 0;                                   // columns this CTA group has exchanged so far
+    __syncthreads();
 
     constexpr int CQ = (C + 3) / 4;
     uint32_t X[C], pw[CQ * 4];
@@ -302,17 +304,21 @@ __global__ void sweep_group_kernel(const GroupArgs a)
             pw[4 * q] = v.x; pw[4 * q + 1] = v.y; pw[4 * q + 2] = v.z; pw[4 * q + 3] = v.w;
         }
     };
-
-    for (int seg = gslot; seg < a.nseg; seg += a.ngslots) {
-        const int64_t o = a.seg_off[seg];
-        const int n = (int)(a.seg_off[seg + 1] - o);
-        __syncthreads();                                 // previous segment's symbols no longer needed
-        for (int x = tid; x < a.seg_stride; x += NT) {
-            int code = (x < n) ? ascii_code(a.bases[o + x]) : 0;
-            if (code > 4) { *a.bad_symbol = 1; code = 0; }
-            schar[x] = (uint8_t)code;
+    const int nblocks = (a.nseg + NS - 1) / NS;
+    for (int blk = gslot; blk < nblocks; blk += a.ngslots) {
+        // the NS segments of the block advance in lockstep; a shorter (or missing) one idles past its end
+        const int seg = blk * NS + seg_local;
+        const bool seg_ok = seg < a.nseg;
+        const int64_t o = seg_ok ? a.seg_off[seg] : 0;
+        const int n = seg_ok ? (int)(a.seg_off[seg + 1] - o) : 0;
+        int nmax = 0;
+        for (int q = 0; q < NS; ++q) {
+            const int sq = blk * NS + q;
+            if (sq < a.nseg) nmax = max(nmax, (int)(a.seg_off[sq + 1] - a.seg_off[sq]));
         }
-        __syncthreads();
+        const bool active = slot_ok && seg_ok;
+        const bool is_end = active && t == T - 1;
+        const bool j_writer = seg_ok && grp == 0 && wseg == 0 && lane == 0;
         int tb_lo = slot, tb_hi = a.M + slot;
         if (a.rank && active) {
             const int *rk = a.rank + (size_t)seg * (2 * a.M);
@@ -320,27 +326,36 @@ __global__ void sweep_group_kernel(const GroupArgs a)
         }
         const int kc_lo = (is_end && tb_lo >= 0) ? key_const(endadd, tb_lo) - 0x800 : -(1 << 30);
         const int kc_hi = (is_end && tb_hi >= 0) ? key_const(endadd, tb_hi) - 0x800 : -(1 << 30);
-        JR *jptr = a.jr + a.seg_j_off[seg];
-        uint32_t *cptr = a.codes + a.cta_code_off[(size_t)seg * NG + grp] + (size_t)tid * a.CW;
+        JR *jptr = a.jr + (seg_ok ? a.seg_j_off[seg] : 0);
+        uint32_t *cptr = a.codes + (seg_ok ? a.cta_code_off[(size_t)seg * NG + grp] : 0) + (size_t)(wseg * 32 + lane) * a.CW;
         const size_t cstride = (size_t)NT * a.CW;
-        const uint8_t *cp = schar;
+        // symbols are streamed from global memory (one byte per column, the same for all lanes of the segment)
+        const uint8_t *src = a.bases + o;
+        auto symbol = [&](int i) {
+            int code = (i < n) ? ascii_code(__ldg(src + i)) : 0;
+            if (code > 4) { *a.bad_symbol = 1; code = 0; }
+            return code;
+        };
 #pragma unroll
         for (int kk = 0; kk < C; ++kk) X[kk] = deadu;
-        load_profile(*cp++);
+        load_profile(symbol(0));
         if (t == 0 && L > 1) pw[0] = P::add(pw[0], P::splat(4 * a.del));
         if (t == T - 1 && L == 1) pw[C - 1] = P::add(pw[C - 1], P::splat(4 * a.del));
         lane_pre<P, C>(X, deadu, pw, deadu, kill_first, kill_last);
         int jbase = a.ins, jump0 = 0;
+        int sym_next = symbol(1);
 #pragma unroll 1
-        for (int i = 0; i < n; ++i) {
+        for (int i = 0; i < nmax; ++i) {
             const uint32_t E = lane_post<P, C>(X, pw, P::splat(jump0 + 1), deadu, tr);
-            load_profile(*cp++);
+            load_profile(sym_next);
+            sym_next = symbol(i + 2);
             const uint32_t carry = slot_scan<P, T>(E, t, srcl, deadu);
             constexpr int NW = (C + P::CELLS_PER_WORD - 1) / P::CELLS_PER_WORD;
             uint32_t cw[NW];
             uint32_t ufirst;
             const uint32_t uend = lane_pass2_pre<P, C>(X, carry, cw, tr, pw, deadu, kill_last, &ufirst);
-            if (active) {
+            const bool live = active && i < n;
+            if (live) {
 #pragma unroll
                 for (int w = 0; w < NW; ++w) cptr[w] = cw[w];
             }
@@ -356,47 +371,55 @@ __global__ void sweep_group_kernel(const GroupArgs a)
                 key = ((int)uend << 10) + kc_lo;
             }
             const int wk = __reduce_max_sync(0xffffffffu, key);
-            if (lane == 0) swk[warp] = wk;
+            if (lane == 0) swk[seg_local * wps + wseg] = wk;
             uint32_t prevU = deadu;
             if (T > 1) { prevU = __shfl_up_sync(0xffffffffu, uend, 1); if (t == 0) prevU = deadu; }
             X[0] = lane_pre_first<P>(prevU, pw[0], ufirst, deadu, kill_first, C == 1 && kill_last);
             __syncthreads();
-            // Column exchange between the NG CTAs of the segment, without atomics: CTA `grp` publishes (epoch, key) in
-            // its own slot of buffer (gcol & 1); warp 0 polls all NG slots of that buffer until every epoch matches.
-            // Two buffers suffice: a CTA can only be one column ahead of the slowest reader (it needs everybody's key
-            // of column c to leave column c), so the slot of column c is not overwritten before it has been read.
+            // Column exchange between the NG CTAs of the block (see the comment above the kernel).  Two buffers
+            // suffice: a CTA can only be one column ahead of the slowest reader, because it needs everybody's key of
+            // column c to leave column c.
             if (warp == 0) {
                 const unsigned epoch = gcol + 1u;
-                unsigned long long *buf = xbuf + (size_t)(gcol & 1u) * NG;
-                if (lane == 0) {
-                    int k = swk[0];
-                    for (int w = 1; w < nwarps; ++w) k = max(k, swk[w]);
+                unsigned long long *buf = xbuf + (size_t)(gcol & 1u) * NG * NS;
+                if (lane < NS) {
+                    int k = swk[lane * wps];
+                    for (int w = 1; w < wps; ++w) k = max(k, swk[lane * wps + w]);
                     const unsigned long long v = ((unsigned long long)epoch << 32) | (unsigned)k;
-                    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(buf + grp), "l"(v) : "memory");   // the word is the whole message
+                    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(buf + grp * NS + lane), "l"(v) : "memory");
+                    sres[lane] = INT_MIN;
                 }
-                int best = INT_MIN;
-                for (int q = lane; q < NG; q += 32) {
-                    unsigned long long v;
-                    unsigned spins = 0;
-                    for (;;) {
-                        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(buf + q) : "memory");
-                        if ((unsigned)(v >> 32) == epoch) break;
-                        if (++spins > (1u << 21)) { *a.error = 1; break; }
-                        if (NG > 8) __nanosleep(40);           // many pollers per slot: back off a little
-                    }
-                    best = max(best, (int)(unsigned)v);
+                __syncwarp();
+                // every lane owns the slots lane, lane+32, ...; the loads of one polling round are issued back to back
+                // so that a round costs one L2 round trip however many slots a lane owns
+                const int nx = NG * NS;
+                unsigned pending = 0;                            // bit j: slot lane + 32*j not seen yet
+                for (int j = 0; lane + 32 * j < nx; ++j) pending |= 1u << j;
+                unsigned spins = 0;
+                while (__any_sync(0xffffffffu, pending != 0)) {
+                    unsigned long long v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (pending & (1u << j))
+                            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v[j]) : "l"(buf + lane + 32 * j) : "memory");
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if ((pending & (1u << j)) && (unsigned)(v[j] >> 32) == epoch) {
+                            atomicMax(&sres[(lane + 32 * j) % NS], (int)(unsigned)v[j]);
+                            pending &= ~(1u << j);
+                        }
+                    if (++spins > (1u << 21)) { *a.error = 1; break; }
                 }
-                best = __reduce_max_sync(0xffffffffu, best);
-                if (lane == 0) swk[32] = best;
             }
             __syncthreads();
-            const int k2 = swk[32];
+            const int k2 = sres[seg_local];
             ++gcol;
             const int vmax = k2 >> 12;
             ++jptr;
-            if (j_writer) *jptr = JR{vmax + jbase, SD_KEY_ROWS - 1 - (k2 & (SD_KEY_ROWS - 1))};
+            if (j_writer && i < n) *jptr = JR{vmax + jbase, SD_KEY_ROWS - 1 - (k2 & (SD_KEY_ROWS - 1))};
             jbase += a.ins;
             jump0 = 4 * (vmax + a.del);
+            if (i >= n) jump0 = 0;                       // an idle segment keeps its registers bounded
             if (jump0 > SD_REBASE_TH || jump0 < -SD_REBASE_TH) {
                 lane_rebase<P, C>(X, jump0);
                 jbase += jump0 >> 2;

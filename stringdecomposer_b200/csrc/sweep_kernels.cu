@@ -274,7 +274,7 @@ public:
         if (!kernel_) throw PlanError{"no sweep kernel compiled for this geometry"};
         cudaFuncAttributes fa;
         SD_CUDA(cudaFuncGetAttributes(&fa, kernel_));
-        if ((int64_t)fa.numRegs * g.NT > 65536) throw PlanError{"sweep geometry exceeds the register file (regs*threads > 64K)"};
+        if ((int64_t)fa.numRegs * g.NT * (g.NG > 1 ? g.NS : 1) > 65536) throw PlanError{"sweep geometry exceeds the register file (regs*threads > 64K)"};
         d_prof_.need(p.prof.size() * 4);
         SD_CUDA(cudaMemcpyAsync(d_prof_.p, p.prof.data(), p.prof.size() * 4, cudaMemcpyHostToDevice, st_));
         d_slotlen_.need(p.slot_len.size() * 4); d_slotend_.need(p.slot_endadd.size() * 4);
@@ -384,6 +384,7 @@ public:
 
     void launch_group(int seg_stride)
     {
+        (void)seg_stride;
         const Geometry &g = plan_.g;
         GroupArgs a;
         a.prof = d_prof_.as<uint4>(); a.nsl_total = plan_.nsl; a.qp = plan_.qp;
@@ -391,27 +392,28 @@ public:
         a.cta_code_off = d_ctacode_.as<int64_t>(); a.seg_j_off = d_segj_.as<int64_t>();
         a.codes = d_codes_.as<uint32_t>(); a.jr = d_jr_.as<JR>();
         a.slot_len = d_slotlen_.as<int>(); a.slot_endadd = d_slotend_.as<int>();
-        a.nslots = g.nslots; a.M = g.M; a.NT = g.NT; a.CW = g.CW; a.NG = g.NG; a.SG = g.SG;
+        a.nslots = g.nslots; a.M = g.M; a.NT = g.NT; a.CW = g.CW; a.NG = g.NG; a.SG = g.SG; a.NS = g.NS;
         a.ins = plan_.sc.ins; a.del = plan_.sc.del; a.deadz = plan_.deadz;
-        a.seg_stride = seg_stride;
         a.tr = g.packed ? tag_regs<Packed16>() : tag_regs<Scalar32>();
         a.bad_symbol = d_flag_.as<int>(); a.error = d_flag_.as<int>() + 1;
         a.rank = filter_on_ ? d_rank_.as<int>() : nullptr;
-        const int spw = 32 / g.T;
-        const size_t sgt = (size_t)(g.NT / 32) * spw * g.T;
-        const size_t smem = (size_t)5 * sgt * plan_.qp * 16 + 36 * 4 + (size_t)seg_stride;
+        const int spw = 32 / g.T, wps = g.NT / 32;
+        const size_t sgt = (size_t)wps * spw * g.T;
+        const size_t smem = (size_t)5 * sgt * plan_.qp * 16 + ((size_t)g.NS * wps + g.NS + 8) * 4;
         if (smem > (size_t)prop_.sharedMemPerBlockOptin) throw PlanError{"group sweep needs more shared memory than the SM has"};
         SD_CUDA(cudaFuncSetAttribute(kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
-        SD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel_, g.NT, smem));
+        SD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel_, g.NS * g.NT, smem));
         const int capacity = per_sm * prop_.multiProcessorCount;
         if (capacity < g.NG) throw PlanError{"monomer set too large: the CTAs of one segment cannot be co-resident on this GPU"};
-        a.ngslots = std::min(nseg_, capacity / g.NG);
-        d_xchg_.need((size_t)a.ngslots * 2 * g.NG * 8);
+        const int nblocks = (nseg_ + g.NS - 1) / g.NS;
+        a.ngslots = std::min(nblocks, capacity / g.NG);
+        const size_t xwords = (size_t)a.ngslots * 2 * g.NG * g.NS;
+        d_xchg_.need(xwords * 8);
         a.xbuf = d_xchg_.as<unsigned long long>();
-        SD_CUDA(cudaMemsetAsync(a.xbuf, 0, (size_t)a.ngslots * 2 * g.NG * 8, st_));    // epoch 0 = nothing published
+        SD_CUDA(cudaMemsetAsync(a.xbuf, 0, xwords * 8, st_));    // epoch 0 = nothing published
         void *args[] = {(void *)&a};
-        SD_CUDA(cudaLaunchCooperativeKernel(kernel_, dim3(a.ngslots * g.NG), dim3(g.NT), args, smem, st_));
+        SD_CUDA(cudaLaunchCooperativeKernel(kernel_, dim3(a.ngslots * g.NG), dim3(g.NS * g.NT), args, smem, st_));
     }
 
     void execute() override
