@@ -156,11 +156,16 @@ Plan make_plan(const MonomerSet &ms, const Scoring &sc, int max_seg_len, int64_t
     if (!bestC || force_sg > 0) {
         // The monomer set does not fit one CTA (threads, registers or the shared-memory profile table): split the slots
         // into NG groups, one CTA each; the per-column key then meets in global memory (sweep_group_kernel).
-        int gC = 0, gT = 0;
+        // fewest partner CTAs per segment first (the exchange latency grows with them), then least padding
+        int gC = 0, gT = 0, gNG = 1 << 30;
         for (int C : kC) for (int T : kT) {
             if (fC && (C != fC || T != fT)) continue;
             if (C * T < ms.Lmax || (C > 24 && !need_big && !fC)) continue;
-            if (!gC || C * T < gC * gT || (C * T == gC * gT && C > gC)) { gC = C; gT = T; }
+            const int spw_c = 32 / T, qp_c = ((C + 3) / 4) | 1;
+            int sg_c = (int)std::min<size_t>((size_t)(140 * 1024) / ((size_t)5 * qp_c * T * 16), (size_t)8 * spw_c);
+            sg_c = std::max(sg_c / spw_c * spw_c, spw_c);
+            const int ng_c = (nslots + sg_c - 1) / sg_c;
+            if (ng_c < gNG || (ng_c == gNG && C * T < gC * gT)) { gC = C; gT = T; gNG = ng_c; }
         }
         if (!gC) throw PlanError{"monomers longer than 1536 bp are not supported by this build"};
         const int spw = 32 / gT, qpc = ((gC + 3) / 4) | 1;
@@ -172,16 +177,27 @@ Plan make_plan(const MonomerSet &ms, const Scoring &sc, int max_seg_len, int64_t
         sg = std::max(sg / spw * spw, spw);
         if (force_sg > 0) sg = std::max(force_sg / spw * spw, spw);
         sg = std::min(sg, (nslots + spw - 1) / spw * spw);
-        bestC = gC; bestT = gT; bestNT = (sg + spw - 1) / spw * 32;
-        bestNS = std::max(1, std::min({2, 65536 / (bestNT * 112), 256 / ((nslots + sg - 1) / sg)}));   // registers; <= 256 exchange slots
-        if (fNS) bestNS = std::min(fNS, 1024 / bestNT);
-        bestNS = (int)std::max<int64_t>(1, std::min<int64_t>(bestNS, nseg_hint));
-        g.NG = (nslots + sg - 1) / sg;
-        g.SG = sg;
-        if (g.NG == 1) g.SG = nslots;
+        const int ng = (nslots + sg - 1) / sg;
+        if (ng > 1) {
+            bestC = gC; bestT = gT; bestNT = (sg + spw - 1) / spw * 32;
+            bestNS = std::max(1, std::min({2, 65536 / (bestNT * 112), 256 / ng}));   // registers; <= 256 exchange slots
+            if (fNS) bestNS = std::min(fNS, 1024 / bestNT);
+            bestNS = (int)std::max<int64_t>(1, std::min<int64_t>(bestNS, nseg_hint));
+            g.NG = ng;
+            g.SG = sg;
+        } else if (!bestC) {
+            throw PlanError{"internal: no launch geometry for this monomer set"};
+        }                                    // a forced group size that covers every slot is the ordinary single-CTA sweep
     }
     g.packed = packed; g.C = bestC; g.T = bestT; g.nslots = nslots; g.M = ms.M; g.NS = bestNS; g.NT = bestNT;
     if (g.NG == 1) g.SG = nslots;
+    {
+        // the lanes of a CTA must cover its slots: NS*nslots slot instances (single CTA) or SG (group sweep)
+        const int spw = 32 / g.T;
+        const int need = g.NG > 1 ? (g.SG + spw - 1) / spw * 32 : (g.NS * nslots + spw - 1) / spw * 32;
+        if (g.NT < need || g.NT * (g.NG > 1 ? g.NS : 1) > 1024 || g.C * g.T < ms.Lmax)
+            throw PlanError{"internal: inconsistent launch geometry"};
+    }
     const int cpw = packed ? 8 : 16;
     g.CW = (g.C + cpw - 1) / cpw;
     p.nsl = nslots * g.T;
