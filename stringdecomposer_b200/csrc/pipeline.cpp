@@ -268,6 +268,10 @@ int run_files(const std::string &reads_path, const std::string &monomers_path, i
     err.add("Scores: insertion=" + std::to_string(sc.ins) + " deletion=" + std::to_string(sc.del) + " mismatch=" +
             std::to_string(sc.mismatch) + " match=" + std::to_string(sc.match) + "\n");                  // main.cpp:393
     err.flush();
+    const bool prof = getenv("SD_PROFILE") != nullptr;
+    auto tnow = [] { return std::chrono::steady_clock::now(); };
+    auto tms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    const auto t_begin = tnow();
     FastaSet reads, mons;
     std::string diag;
     int st = load_fasta(reads_path, reads, diag);
@@ -293,9 +297,12 @@ int run_files(const std::string &reads_path, const std::string &monomers_path, i
     if (segs.empty()) return 0;
     if (mons.seqs.empty()) { error = "no monomers"; err.add("ERROR: " + error + "\n"); return 1; }
 
+    const auto t_loaded = tnow();
+    auto t_engine = t_loaded, t_batch = t_loaded, t_done = t_loaded;
     BatchResult res;
     try {
         Engine eng(mons.seqs, sc, std::move(devs));
+        t_engine = tnow();
         eng.set_ed_thr(ed_thr);          // FilterMonomersForRead (main.cpp:91-93,135-149) when ed_thr > -1
         Batch b;
         b.off.reserve(segs.size() + 1); b.off.push_back(0);
@@ -309,7 +316,9 @@ int run_files(const std::string &reads_path, const std::string &monomers_path, i
             o += (size_t)segs[s].second; b.off.push_back((int64_t)o);
         }
         b.text = b.own.data();
+        t_batch = tnow();
         eng.decompose(b, res);
+        t_done = tnow();
         if (getenv("SD_VERBOSE")) {
             const EngineStats &s = eng.stats;
             char line[512];
@@ -353,6 +362,13 @@ int run_files(const std::string &reads_path, const std::string &monomers_path, i
             prev_end = r.end;
             if (outw.buf.size() > (1 << 20)) outw.flush();
         }
+    }
+    outw.flush();
+    if (prof) {
+        char line[256];
+        snprintf(line, sizeof line, "[sd_b200 profile] run_files: fasta %.1f engine %.1f batch %.1f decompose %.1f output %.1f ms\n",
+                 tms(t_begin, t_loaded), tms(t_loaded, t_engine), tms(t_engine, t_batch), tms(t_batch, t_done), tms(t_done, tnow()));
+        err.add(line);
     }
     return 0;
 }
