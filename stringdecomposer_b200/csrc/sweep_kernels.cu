@@ -297,7 +297,7 @@ public:
     }
     int64_t wave_budget() const override
     {
-        if (const char *e = getenv("SD_WAVE_BYTES")) return atoll(e);
+        if (const char *e = getenv("SD_WAVE_BYTES")) if (atoll(e) > 0) return atoll(e);
         return budget_;        // 85 % of the memory that was free when the backend was created (cudaMemGetInfo costs ms)
     }
 

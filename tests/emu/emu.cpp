@@ -158,7 +158,7 @@ public:
     }
     int64_t wave_budget() const override
     {
-        if (const char *e = getenv("SD_WAVE_BYTES")) return atoll(e);
+        if (const char *e = getenv("SD_WAVE_BYTES")) if (atoll(e) > 0) return atoll(e);
         return (int64_t)1 << 30;
     }
     void stage(const Batch &b, int s0, int s1) override
