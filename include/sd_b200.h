@@ -94,6 +94,25 @@ int sd_set_ed_thr(sd_handle *h, int32_t ed_thr);
  * best substring of `target`; host-side helper (the pre-filter itself runs on the device).  -1 on bad arguments. */
 int32_t sd_hw_distance(const char *query, int32_t query_len, const char *target, int32_t target_len);
 
+/* Replaces edist / aai (stringdecomposer/main.py:29-60), the per-alignment `edlib.align(interval, monomer, mode="NW",
+ * task="path")` of the final-TSV stage (convert_read, main.py:107-147): for every (query, target) pair the unit-cost
+ * global alignment edlib would report -- its edit distance, the number of '=' columns and the alignment length, so
+ * that identity = 100 * matches / columns -- computed on `device` for the whole batch at once.
+ *   queries / targets   concatenated bytes (compared verbatim, like edlib's default equality) + n+1 offsets
+ *   pair_query/_target  n_pairs index pairs; both NULL: every query against every target, query-major
+ *                       (n_pairs must then be n_queries * n_targets)
+ *   matches, columns    caller-allocated [n_pairs]; distance may be NULL.  A pair with an empty side gets
+ *                       matches = columns = 0, distance = -1 (main.py:30-33 -> identity 0)
+ *   hirschberg_pairs    optional: number of pairs so large that edlib would leave its traceback for Hirschberg
+ *                       splitting (edlib.cpp:1187-1191) and might report another optimal path; they are still
+ *                       computed with the traceback rule.  Lengths above 16383 are refused (SD_ERR_UNSUPPORTED).
+ *   kernel_ms           optional: device time of the kernel */
+int sd_identity(const char *queries, const int64_t *query_offsets, int64_t n_queries,
+                const char *targets, const int64_t *target_offsets, int64_t n_targets,
+                const int32_t *pair_query, const int32_t *pair_target, int64_t n_pairs,
+                int32_t *matches, int32_t *columns, int32_t *distance,
+                int32_t device, int64_t *hirschberg_pairs, double *kernel_ms);
+
 int sd_get_stats(sd_handle *h, sd_stats *out);
 void sd_reset_stats(sd_handle *h);
 const char *sd_last_error(sd_handle *h);       /* h may be NULL: error of the last failed sd_create/sd_run_files */

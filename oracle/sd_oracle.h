@@ -21,6 +21,9 @@ int sdo_filter_rows(const char *seg, int n, const char *rows, const int *row_off
 int sdo_run_files(const char *reads_path, const char *monomers_path, int threads, int part_size, int overlap,
                   int ins, int del, int mismatch, int match, int ed_thr, char **tsv, size_t *tsv_len, FILE *err);
 int sdo_cli_main(int argc, char **argv);
+/* identity rescoring (sd_identity_oracle.c; main.py:29-60) */
+int sdo_nw_path_counts(const char *q, int qlen, const char *t, int tlen, int *matches, int *columns);
+int sdo_nw_uses_traceback(int qlen, int tlen);
 
 #ifdef __cplusplus
 }

@@ -102,3 +102,45 @@ def decompose_reads(read_names, reads, monomer_names, monomers, part_size=5000, 
         if st != 0:
             raise RuntimeError("oracle dp exited with %d: %s" % (st, err.decode()[-300:]))
         return out.decode()
+
+
+# ---- identity rescoring: sd_identity_oracle.c and the reference's own edlib ----------------
+REF_EDLIB = os.path.join(HERE, "_ref", "libedlib_ref.so")
+_ref_edlib = None
+
+
+def _counts(fn, q, t):
+    qb, tb = q.encode(), t.encode()
+    m, c = C.c_int(), C.c_int()
+    d = fn(qb, len(qb), tb, len(tb), C.byref(m), C.byref(c))
+    return d, m.value, c.value
+
+
+def nw_path_counts(q, t):
+    """(edit distance, '=' columns, alignment columns) of edlib's NW path; distance -1 when either is empty."""
+    f = lib().sdo_nw_path_counts
+    f.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    return _counts(f, q, t)
+
+
+def nw_uses_traceback(qlen, tlen):
+    return bool(lib().sdo_nw_uses_traceback(int(qlen), int(tlen)))
+
+
+def ref_nw_path_counts(q, t):
+    """The same triple from the reference's vendored edlib.cpp (oracle/_ref/libedlib_ref.so); non-empty inputs only."""
+    global _ref_edlib
+    if _ref_edlib is None:
+        _ref_edlib = C.CDLL(REF_EDLIB)
+        _ref_edlib.ref_nw_path_counts.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    return _counts(_ref_edlib.ref_nw_path_counts, q, t)
+
+
+def identity(q, t):
+    """aai of main.py:36-60: percent of '=' columns in edlib's NW alignment; 0 when either string is empty."""
+    q = q[:-1] if q.endswith("*") else q                      # main.py:38-41
+    t = t[:-1] if t.endswith("*") else t
+    d, m, c = nw_path_counts(q, t)
+    if d == -1:
+        return 0
+    return m / c * 100

@@ -6,7 +6,7 @@ and the drop-in ``build/bin/dp`` binary.  This package is the thin Python host m
 GPU raises.
 """
 from ._lib import (Decomposer, SdError, load_library, segment_read, postprocess, run_files, int_peak,  # noqa: F401
-                   library_path, device_count, hw_distance, RECORD_DTYPE)
+                   library_path, device_count, hw_distance, nw_identity, RECORD_DTYPE)
 from .hostpipe import decompose_reads, read_fasta, format_raw_tsv  # noqa: F401
 
 __version__ = "0.1.0"

@@ -25,7 +25,7 @@ class _Stats(C.Structure):
 # every symbol include/sd_b200.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = ["sd_create", "sd_decompose", "sd_stage", "sd_run_staged", "sd_fetch_staged", "sd_segment_read",
            "sd_postprocess", "sd_run_files", "sd_set_ed_thr", "sd_hw_distance", "sd_get_stats", "sd_reset_stats", "sd_last_error", "sd_free",
-           "sd_destroy", "sd_device_count", "sd_version", "sd_int_peak"]
+           "sd_destroy", "sd_device_count", "sd_version", "sd_int_peak", "sd_identity"]
 
 _libs = {}
 
@@ -83,6 +83,10 @@ def load_library(flavour="cuda"):
     lib.sd_version.restype = C.c_char_p
     lib.sd_int_peak.argtypes = [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.sd_int_peak.restype = C.c_int
+    i32p, i64p = C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+    lib.sd_identity.argtypes = [C.c_char_p, i64p, C.c_int64, C.c_char_p, i64p, C.c_int64, i32p, i32p, C.c_int64,
+                                i32p, i32p, i32p, C.c_int32, i64p, C.POINTER(C.c_double)]
+    lib.sd_identity.restype = C.c_int
     _libs[flavour] = lib
     return lib
 
@@ -234,3 +238,40 @@ def int_peak(device=0):
     if st:
         raise SdError(st, (lib.sd_last_error(None) or b"").decode())
     return a.value, b.value, m.value
+
+
+def nw_identity(queries, targets, pairs=None, device=0, flavour="cuda"):
+    """Batched edist/aai of the reference (main.py:29-60): for every (query, target) pair the edit distance, the number
+    of '=' columns and the alignment length of edlib's global ("NW") alignment path.
+
+    queries / targets: lists of str/bytes, or ``(blob, int64 offsets)`` tuples.  pairs: ``(query index array, target
+    index array)`` or None for all queries x all targets (query-major).  Returns a dict of int32 arrays ``matches``,
+    ``columns``, ``distance`` plus ``kernel_ms`` and ``hirschberg_pairs``; identity = 100 * matches / columns
+    (0 where columns == 0)."""
+    lib = load_library(flavour)
+    qb, qo = queries if isinstance(queries, tuple) else _pack(queries)
+    tb, to = targets if isinstance(targets, tuple) else _pack(targets)
+    qo = np.ascontiguousarray(qo, dtype=np.int64)
+    to = np.ascontiguousarray(to, dtype=np.int64)
+    nq, nt = len(qo) - 1, len(to) - 1
+    i32p, i64p = C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+    if pairs is None:
+        n, pq, pt = nq * nt, None, None
+    else:
+        pq = np.ascontiguousarray(pairs[0], dtype=np.int32)
+        pt = np.ascontiguousarray(pairs[1], dtype=np.int32)
+        if pq.shape != pt.shape:
+            raise SdError(1, "pairs: index arrays of different length")
+        n = len(pq)
+    m = np.zeros(n, dtype=np.int32)
+    c = np.zeros(n, dtype=np.int32)
+    d = np.zeros(n, dtype=np.int32)
+    hb, ms = C.c_int64(0), C.c_double(0)
+    st = lib.sd_identity(bytes(qb), qo.ctypes.data_as(i64p), nq, bytes(tb), to.ctypes.data_as(i64p), nt,
+                         pq.ctypes.data_as(i32p) if pq is not None else None,
+                         pt.ctypes.data_as(i32p) if pt is not None else None, n,
+                         m.ctypes.data_as(i32p), c.ctypes.data_as(i32p), d.ctypes.data_as(i32p), device,
+                         C.byref(hb), C.byref(ms))
+    if st:
+        raise SdError(st, (lib.sd_last_error(None) or b"").decode())
+    return {"matches": m, "columns": c, "distance": d, "kernel_ms": ms.value, "hirschberg_pairs": hb.value}

@@ -1,4 +1,6 @@
 // api.cpp -- the C ABI declared in include/sd_b200.h.
+#include <algorithm>
+#include <climits>
 #include <cstdlib>
 #include <cstring>
 #include <chrono>
@@ -8,6 +10,7 @@
 
 #include "../../include/sd_b200.h"
 #include "pipeline.h"
+#include "identity_core.cuh"
 
 using namespace sdb;
 
@@ -31,7 +34,11 @@ static void set_global_error(const std::string &e) { std::lock_guard<std::mutex>
 namespace sdb { Backend *make_emu_backend() { return nullptr; } }
 int cuda_device_count();
 int cuda_int_peak(int device, double *alu, double *both, double *mhz, std::string &err);
+namespace sdb { int cuda_identity(const IdentityArgs &h, int max_qlen, int max_tlen, int device, double *kernel_ms, std::string &err); }
+static int run_identity(const IdentityArgs &h, int mq, int mt, int device, double *ms, std::string &err) { return cuda_identity(h, mq, mt, device, ms, err); }
 #else
+namespace sdb { int emu_identity(const IdentityArgs &h, int max_qlen, int max_tlen, double *kernel_ms, std::string &err); }
+static int run_identity(const IdentityArgs &h, int mq, int mt, int, double *ms, std::string &err) { return emu_identity(h, mq, mt, ms, err); }
 namespace sdb { Backend *make_cuda_backend(int, std::string &err) { err = "emulator build"; return nullptr; } }
 static int cuda_device_count() { return 1; }
 static int cuda_int_peak(int, double *, double *, double *, std::string &err) { err = "emulator build has no device"; return SD_ERR_NO_DEVICE; }
@@ -218,6 +225,48 @@ int32_t sd_hw_distance(const char *query, int32_t query_len, const char *target,
 {
     if (!query || !target || query_len <= 0 || target_len < 0 || query_len > 64 * SD_HW_BLOCKS) return -1;
     return hw_distance(reinterpret_cast<const uint8_t *>(query), query_len, reinterpret_cast<const uint8_t *>(target), target_len);
+}
+
+int sd_identity(const char *queries, const int64_t *qoff, int64_t nq, const char *targets, const int64_t *toff, int64_t nt,
+                const int32_t *pair_q, const int32_t *pair_t, int64_t npairs, int32_t *matches, int32_t *columns,
+                int32_t *distance, int32_t device, int64_t *hirschberg_pairs, double *kernel_ms)
+{
+    std::string err;
+    auto fail = [&](int st, const char *msg) { set_global_error(msg); return st; };
+    if (nq < 0 || nt < 0 || npairs < 0 || !qoff || !toff || (npairs > 0 && (!matches || !columns))) return fail(SD_ERR_ARG, "sd_identity: bad arguments");
+    if ((pair_q == nullptr) != (pair_t == nullptr)) return fail(SD_ERR_ARG, "sd_identity: pair_query and pair_target go together");
+    if (!pair_q && npairs != nq * nt) return fail(SD_ERR_ARG, "sd_identity: n_pairs must be n_queries * n_targets without a pair list");
+    if (nq > INT32_MAX || nt > INT32_MAX) return fail(SD_ERR_ARG, "sd_identity: too many sequences");
+    int max_q = 0, max_t = 0;
+    for (int64_t i = 0; i < nq; ++i) {
+        const int64_t l = qoff[i + 1] - qoff[i];
+        if (l < 0) return fail(SD_ERR_ARG, "sd_identity: query offsets must not decrease");
+        if (l > SD_NW_MAXLEN) return fail(SD_ERR_UNSUPPORTED, "sd_identity: sequence longer than 16383");
+        max_q = std::max<int>(max_q, (int)l);
+    }
+    for (int64_t i = 0; i < nt; ++i) {
+        const int64_t l = toff[i + 1] - toff[i];
+        if (l < 0) return fail(SD_ERR_ARG, "sd_identity: target offsets must not decrease");
+        if (l > SD_NW_MAXLEN) return fail(SD_ERR_UNSUPPORTED, "sd_identity: sequence longer than 16383");
+        max_t = std::max<int>(max_t, (int)l);
+    }
+    if ((qoff[nq] > qoff[0] && !queries) || (toff[nt] > toff[0] && !targets) || qoff[0] != 0 || toff[0] != 0) return fail(SD_ERR_ARG, "sd_identity: bad text buffers");
+    int64_t hb = 0;
+    for (int64_t p = 0; p < npairs; ++p) {
+        const int64_t qi = pair_q ? pair_q[p] : p / nt, ti = pair_q ? pair_t[p] : p % nt;
+        if (qi < 0 || qi >= nq || ti < 0 || ti >= nt) return fail(SD_ERR_ARG, "sd_identity: pair index out of range");
+        if (!nw_edlib_traceback_domain((int)(qoff[qi + 1] - qoff[qi]), (int)(toff[ti + 1] - toff[ti]))) ++hb;
+    }
+    if (hirschberg_pairs) *hirschberg_pairs = hb;
+    if (kernel_ms) *kernel_ms = 0;
+    if (npairs == 0) return SD_OK;
+    if (!kEmu && (device < 0 || device >= cuda_device_count())) return fail(SD_ERR_NO_DEVICE, "sd_identity: no such CUDA device (libsd_b200 has no CPU path)");
+    IdentityArgs a{};
+    a.qtext = queries; a.qoff = qoff; a.nq = nq; a.ttext = targets; a.toff = toff; a.nt = nt;
+    a.pair_q = pair_q; a.pair_t = pair_t; a.npairs = npairs; a.matches = matches; a.columns = columns; a.distance = distance;
+    const int st = run_identity(a, max_q, max_t, device, kernel_ms, err);
+    if (st) { set_global_error(err); return st == 2 ? SD_ERR_NO_DEVICE : SD_ERR_CUDA; }
+    return SD_OK;
 }
 
 int sd_get_stats(sd_handle *h, sd_stats *o)

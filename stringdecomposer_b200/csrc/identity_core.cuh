@@ -1,0 +1,96 @@
+// identity_core.cuh -- per-lane algebra of the identity rescoring kernel, shared by the CUDA kernel
+// (identity_kernels.cu) and the host emulator of the CPU test-suite (tests/emu/emu.cpp).
+//
+// Replaces edist/aai of the reference (stringdecomposer/main.py:29-60): edlib.align(interval, monomer, mode="NW",
+// task="path"), identity = '=' columns / alignment columns.  edlib walks its unit-cost matrix back from the
+// bottom-right cell taking, at every cell, the first move that explains the value: up (query character alone),
+// then left (target character alone), then the diagonal (vendored edlib.cpp:1036-1133).  The number of '='
+// columns on that walk obeys a forward recurrence over the same matrix,
+//     pred(i,j) = up if D[i-1][j]+1 == D[i][j], else left if D[i][j-1]+1 == D[i][j], else diagonal
+//     M[i][j]   = M[pred(i,j)] + (diagonal taken and q[i] == t[j]),      columns = M + D at the last cell,
+// so no traceback state is stored at all.  One 32-bit word per cell carries both: D in bits 18..31, M in bits
+// 0..15; bits 16..17 hold the move priority inside the three candidates only, so ONE unsigned minimum picks the
+// smallest distance and, among equal distances, edlib's preferred move, and drags that move's M along.
+#pragma once
+#include <cstdint>
+#if defined(__CUDACC__)
+#define SDI_HD __host__ __device__ __forceinline__
+#else
+#define SDI_HD inline
+#endif
+
+namespace sdb {
+
+constexpr int SD_NW_MAXLEN = 16383;                 // D < 2^14 and M < 2^16
+constexpr uint32_t NW_DSHIFT = 18;
+constexpr uint32_t NW_K_UP = 1u << 18;                              // +1, priority 0
+constexpr uint32_t NW_K_LEFT = (1u << 18) | (1u << 16);             // +1, priority 1
+constexpr uint32_t NW_K_DIAG_EQ = (2u << 16) + 1u;                  // +0, priority 2, one more '=' column
+constexpr uint32_t NW_K_DIAG_NE = (1u << 18) | (2u << 16);          // +1, priority 2
+constexpr uint32_t NW_CLEAR = ~(3u << 16);
+constexpr uint32_t NW_NOCHAR = 0xffffu;                             // query padding: equals no target byte
+
+SDI_HD uint32_t nw_addmin(uint32_t a, uint32_t b, uint32_t c)       // min(a + b, c)     VIADDMNMX.U32
+{
+#if defined(__CUDA_ARCH__)
+    return __viaddmin_u32(a, b, c);
+#else
+    const uint32_t s = a + b;
+    return s < c ? s : c;
+#endif
+}
+
+// The R consecutive query rows one lane owns, at the column it finished last.
+template <int R>
+struct NwLane {
+    uint32_t left[R];      // cells of the previous column
+    uint32_t qc[R];        // query characters (NW_NOCHAR beyond the end)
+    uint32_t up_prev;      // cell above the first row, previous column
+};
+
+template <int R>
+SDI_HD void nw_lane_init(NwLane<R> &st, const char *q, int qlen, int row0)
+{
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        st.qc[r] = row0 + r < qlen ? (uint32_t)(uint8_t)q[row0 + r] : NW_NOCHAR;
+        st.left[r] = (uint32_t)(row0 + r + 1) << NW_DSHIFT;         // D[i][-1] = i + 1
+    }
+    st.up_prev = (uint32_t)row0 << NW_DSHIFT;                       // D[row0-1][-1] = row0
+}
+
+// One column for this lane: `top` is the cell above the first row in this column, tc the target character.
+template <int R>
+SDI_HD uint32_t nw_lane_step(NwLane<R> &st, uint32_t top, uint32_t tc)
+{
+    uint32_t diag = st.up_prev, up = top;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const uint32_t cd = diag + (st.qc[r] == tc ? NW_K_DIAG_EQ : NW_K_DIAG_NE);
+        const uint32_t v = nw_addmin(up, NW_K_UP, nw_addmin(st.left[r], NW_K_LEFT, cd)) & NW_CLEAR;
+        diag = st.left[r];
+        st.left[r] = v;
+        up = v;
+    }
+    st.up_prev = top;
+    return up;              // bottom cell of the strip
+}
+
+SDI_HD int nw_rows_per_lane(int max_qlen) { return max_qlen <= 64 ? 2 : max_qlen <= 128 ? 4 : max_qlen <= 192 ? 6 : 8; }
+
+// Above 1 MiB of traceback state edlib switches to Hirschberg splitting (edlib.cpp:1187-1191), whose path may differ.
+SDI_HD bool nw_edlib_traceback_domain(int qlen, int tlen)
+{
+    const long long blocks = (qlen + 63) / 64;
+    return 20ll * blocks * tlen + 8ll * tlen < 1024ll * 1024ll;
+}
+
+struct IdentityArgs {
+    const char *qtext; const int64_t *qoff; int64_t nq;
+    const char *ttext; const int64_t *toff; int64_t nt;
+    const int32_t *pair_q, *pair_t; int64_t npairs;        // pair_q == nullptr: all queries x all targets, query-major
+    int32_t *matches, *columns, *distance;                 // distance may be nullptr
+    uint32_t *scratch; int64_t scratch_stride;             // one row of max target length per warp (tiled queries)
+};
+
+} // namespace sdb

@@ -9,6 +9,7 @@
 #include <cstring>
 
 #include "common.h"
+#include "identity_core.cuh"
 
 namespace sdb {
 
@@ -247,5 +248,58 @@ private:
 } // namespace
 
 Backend *make_emu_backend() { return new EmuBackend(); }
+
+// Host emulation of identity_kernel (identity_kernels.cu): the same strips, tiles, wavefront steps and spill row,
+// with the 32 lanes of the warp walked in descending order so that lane l reads lane l-1's bottom cell of the
+// previous step, exactly what the SHFL.UP delivers on the device.
+template <int R>
+static void emu_identity_pair(const char *q, int qlen, const char *t, int tlen, std::vector<uint32_t> &scratch, int &m, int &d)
+{
+    const int ntiles = (qlen + 32 * R - 1) / (32 * R);
+    NwLane<R> st[32];
+    uint32_t bottom[32];
+    for (int tile = 0; tile < ntiles; ++tile) {
+        const int base = tile * 32 * R;
+        for (int l = 0; l < 32; ++l) { nw_lane_init<R>(st[l], q, qlen, base + l * R); bottom[l] = 0; }
+        const int nl = std::min(32, (qlen - base + R - 1) / R);
+        const bool spill = tile + 1 < ntiles;
+        for (int s = 0; s < tlen + nl - 1; ++s)
+            for (int l = 31; l >= 0; --l) {
+                uint32_t top = bottom[l ? l - 1 : 0];
+                const int j = s - l;
+                if (j < 0 || j >= tlen) continue;
+                if (l == 0) top = tile == 0 ? (uint32_t)(j + 1) << NW_DSHIFT : scratch[j];
+                bottom[l] = nw_lane_step<R>(st[l], top, (uint32_t)(uint8_t)t[j]);
+                if (spill && l == 31) scratch[j] = bottom[l];
+            }
+    }
+    const int fr = qlen - 1 - (ntiles - 1) * 32 * R;
+    const uint32_t v = st[fr / R].left[fr % R];
+    d = (int)(v >> NW_DSHIFT); m = (int)(v & 0xffffu);
+}
+
+int emu_identity(const IdentityArgs &a, int max_qlen, int max_tlen, double *kernel_ms, std::string &)
+{
+    const int R = nw_rows_per_lane(max_qlen);
+    std::vector<uint32_t> scratch((size_t)max_tlen + 32);
+    for (int64_t p = 0; p < a.npairs; ++p) {
+        const int64_t qi = a.pair_q ? a.pair_q[p] : p / a.nt, ti = a.pair_q ? a.pair_t[p] : p % a.nt;
+        const char *q = a.qtext + a.qoff[qi], *t = a.ttext + a.toff[ti];
+        const int qlen = (int)(a.qoff[qi + 1] - a.qoff[qi]), tlen = (int)(a.toff[ti + 1] - a.toff[ti]);
+        int m = 0, d = -1;
+        if (qlen > 0 && tlen > 0) {
+            switch (R) {
+            case 2: emu_identity_pair<2>(q, qlen, t, tlen, scratch, m, d); break;
+            case 4: emu_identity_pair<4>(q, qlen, t, tlen, scratch, m, d); break;
+            case 6: emu_identity_pair<6>(q, qlen, t, tlen, scratch, m, d); break;
+            default: emu_identity_pair<8>(q, qlen, t, tlen, scratch, m, d); break;
+            }
+        }
+        a.matches[p] = m; a.columns[p] = d < 0 ? 0 : m + d;
+        if (a.distance) a.distance[p] = d;
+    }
+    if (kernel_ms) *kernel_ms = 0;
+    return 0;
+}
 
 } // namespace sdb
