@@ -197,18 +197,11 @@ int sd_run_files(const char *reads_path, const char *monomers_path, int32_t thre
 {
     if (!reads_path || !monomers_path) return SD_ERR_ARG;
     std::string err;
-    std::vector<std::unique_ptr<Backend>> devs;
     int32_t ndev = 0;
     if (const char *e = getenv("SD_DEVICES")) ndev = (strcmp(e, "all") == 0) ? -1 : atoi(e);
-    int st = make_backends(nullptr, ndev, devs, err);
-    if (st) {
-        set_global_error(err);
-        std::string m = "ERROR: " + err + "\n";
-        if (::write(err_fd, m.data(), m.size()) < 0) {}
-        return st;
-    }
+    auto open_devices = [ndev](std::vector<std::unique_ptr<Backend>> &devs, std::string &e) { return make_backends(nullptr, ndev, devs, e); };
     Scoring sc; sc.ins = ins; sc.del = del; sc.mismatch = mismatch; sc.match = match;
-    st = run_files(reads_path, monomers_path, threads, part_size, overlap, sc, ed_thr, std::move(devs), out_fd, err_fd, err);
+    int st = run_files(reads_path, monomers_path, threads, part_size, overlap, sc, ed_thr, open_devices, out_fd, err_fd, err);
     if (!err.empty()) set_global_error(err);
     return st;
 }

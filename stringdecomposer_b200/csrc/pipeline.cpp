@@ -5,7 +5,9 @@
 #include <cstring>
 #include <fstream>
 #include <chrono>
+#include <future>
 #include <thread>
+#include <sys/stat.h>
 #include <unistd.h>
 
 #include "pipeline.h"
@@ -20,30 +22,45 @@ namespace sdb {
 int load_fasta(const std::string &path, FastaSet &out, std::string &diag)
 {
     out.names.clear(); out.seqs.clear();
-    std::ifstream f(path, std::ios::in | std::ios::binary);
-    std::string line;
-    while (std::getline(f, line)) {
-        if (!line.empty() && line[0] == '>') {
-            size_t a = 1;
-            auto ws = [](char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\n' || c == '\v' || c == '\f'; };
-            while (a < line.size() && ws(line[a])) ++a;
-            size_t b = a;
-            while (b < line.size() && !ws(line[b])) ++b;
-            out.names.emplace_back(line.substr(a, b - a));
-            out.seqs.emplace_back();
-        } else if (!out.seqs.empty()) {
-            out.seqs.back() += line;
-        }
+    // whole file in one read, lines found with memchr: at GPU speed the reference's getline loop would dominate
+    std::string buf;
+    if (FILE *f = fopen(path.c_str(), "rb")) {
+        char chunk[1 << 16];
+        struct stat sb;
+        if (fstat(fileno(f), &sb) == 0 && sb.st_size > 0) buf.reserve((size_t)sb.st_size);
+        size_t got;
+        while ((got = fread(chunk, 1, sizeof chunk, f)) > 0) buf.append(chunk, got);
+        fclose(f);
     }
+    auto ws = [](char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\n' || c == '\v' || c == '\f'; };
     bool has_n = false;
-    for (size_t i = 0; i < out.seqs.size(); ++i)
-        for (char c : out.seqs[i]) {
-            if (base_code(c) < 0) {
-                diag += "ERROR: Sequence " + out.names[i] + " contains undefined symbol (not ACGT): " + std::string(1, c) + "\n";
-                return 255;
-            }
-            if (c == 'N') has_n = true;
+    int bad_seq = -1; char bad_char = 0;
+    const char *p = buf.data(), *end = p + buf.size();
+    while (p < end) {
+        const char *nl = static_cast<const char *>(memchr(p, '\n', (size_t)(end - p)));
+        const char *le = nl ? nl : end;                     // the line is [p, le), like getline
+        if (le > p && *p == '>') {                         // name = first token (main.cpp:321-325)
+            const char *a = p + 1;
+            while (a < le && ws(*a)) ++a;
+            const char *b = a;
+            while (b < le && !ws(*b)) ++b;
+            out.names.emplace_back(a, b);
+            out.seqs.emplace_back();
+        } else if (!out.seqs.empty()) {                     // lines appended raw (main.cpp:327), checked at :330-341
+            if (bad_seq < 0)
+                for (const char *c = p; c < le; ++c) {
+                    if (base_code(*c) < 0) { bad_seq = (int)out.seqs.size() - 1; bad_char = *c; break; }
+                    has_n |= *c == 'N';
+                }
+            out.seqs.back().append(p, le);
         }
+        p = nl ? nl + 1 : end;
+    }
+    if (bad_seq >= 0) {
+        // the reference reports the first offending sequence in file order, and in it the first offending symbol
+        diag += "ERROR: Sequence " + out.names[bad_seq] + " contains undefined symbol (not ACGT): " + std::string(1, bad_char) + "\n";
+        return 255;
+    }
     if (has_n) diag += "WARNING: sequences in " + path + " contain N symbol. It will be counted as a separate symbol in scoring!\n";
     return 0;
 }
@@ -250,7 +267,7 @@ namespace {
 struct FdWriter {
     int fd; std::string buf;
     explicit FdWriter(int f) : fd(f) { buf.reserve(1 << 20); }
-    void flush() { size_t o = 0; while (o < buf.size()) { ssize_t w = ::write(fd, buf.data() + o, buf.size() - o); if (w <= 0) break; o += (size_t)w; } buf.clear(); }
+    void flush() { if (fd < 0) return; size_t o = 0; while (o < buf.size()) { ssize_t w = ::write(fd, buf.data() + o, buf.size() - o); if (w <= 0) break; o += (size_t)w; } buf.clear(); }
     void add(const std::string &s) { buf += s; if (buf.size() > (1 << 20)) flush(); }
     void add_int(long v) { char t[24]; int n = 0; bool neg = v < 0; unsigned long u = neg ? 0ul - (unsigned long)v : (unsigned long)v;
         do { t[n++] = (char)('0' + u % 10); u /= 10; } while (u); if (neg) t[n++] = '-'; while (n) buf.push_back(t[--n]); }
@@ -260,11 +277,13 @@ struct FdWriter {
 } // namespace
 
 int run_files(const std::string &reads_path, const std::string &monomers_path, int threads, int part_size, int overlap,
-              const Scoring &sc, int ed_thr, std::vector<std::unique_ptr<Backend>> devs, int out_fd, int err_fd,
-              std::string &error)
+              const Scoring &sc, int ed_thr, DeviceOpener open_devices, int out_fd, int err_fd, std::string &error)
 {
     (void)threads;     // OpenMP width in the reference (main.cpp:85,88); the output does not depend on it
     FdWriter err(err_fd);
+    std::vector<std::unique_ptr<Backend>> devs;
+    std::string dev_error;
+    std::future<int> dev_ready = std::async(std::launch::async, [&] { return open_devices(devs, dev_error); });
     err.add("Scores: insertion=" + std::to_string(sc.ins) + " deletion=" + std::to_string(sc.del) + " mismatch=" +
             std::to_string(sc.mismatch) + " match=" + std::to_string(sc.match) + "\n");                  // main.cpp:393
     err.flush();
@@ -298,14 +317,10 @@ int run_files(const std::string &reads_path, const std::string &monomers_path, i
     if (mons.seqs.empty()) { error = "no monomers"; err.add("ERROR: " + error + "\n"); return 1; }
 
     const auto t_loaded = tnow();
-    auto t_engine = t_loaded, t_batch = t_loaded, t_done = t_loaded;
-    BatchResult res;
-    try {
-        Engine eng(mons.seqs, sc, std::move(devs));
-        t_engine = tnow();
-        eng.set_ed_thr(ed_thr);          // FilterMonomersForRead (main.cpp:91-93,135-149) when ed_thr > -1
-        Batch b;
-        b.off.reserve(segs.size() + 1); b.off.push_back(0);
+    // pack the segments while the devices are still being opened
+    Batch b;
+    b.off.reserve(segs.size() + 1); b.off.push_back(0);
+    {
         size_t total = 0;
         for (auto &s : segs) total += (size_t)s.second;
         b.own.resize(total);
@@ -316,14 +331,27 @@ int run_files(const std::string &reads_path, const std::string &monomers_path, i
             o += (size_t)segs[s].second; b.off.push_back((int64_t)o);
         }
         b.text = b.own.data();
-        t_batch = tnow();
-        eng.decompose(b, res);
+    }
+    const auto t_batch = tnow();
+    auto t_engine = t_batch, t_done = t_batch;
+    if (int dst = dev_ready.get()) {                 // no usable device: fail loudly, there is no CPU path
+        error = dev_error;
+        err.add("ERROR: " + error + "\n");
+        return dst;
+    }
+    BatchResult res;
+    std::unique_ptr<Engine> eng;
+    try {
+        eng.reset(new Engine(mons.seqs, sc, std::move(devs)));
+        t_engine = tnow();
+        eng->set_ed_thr(ed_thr);          // FilterMonomersForRead (main.cpp:91-93,135-149) when ed_thr > -1
+        eng->decompose(b, res);
         t_done = tnow();
         if (getenv("SD_VERBOSE")) {
-            const EngineStats &s = eng.stats;
+            const EngineStats &s = eng->stats;
             char line[512];
             snprintf(line, sizeof line, "[sd_b200] devices=%d geometry packed=%d C=%d T=%d NS=%d NT=%d segments=%ld cells=%ld sweep=%.3f ms traceback=%.3f ms -> %.1f GCUPS (kernels)\n",
-                     eng.ndev(), s.g.packed, s.g.C, s.g.T, s.g.NS, s.g.NT, (long)s.segments, (long)s.cells, s.sweep_ms, s.traceback_ms,
+                     eng->ndev(), s.g.packed, s.g.C, s.g.T, s.g.NS, s.g.NT, (long)s.segments, (long)s.cells, s.sweep_ms, s.traceback_ms,
                      s.cells / ((s.sweep_ms + s.traceback_ms) * 1e6 + 1e-9));
             err.add(line);
         }
@@ -332,42 +360,64 @@ int run_files(const std::string &reads_path, const std::string &monomers_path, i
         err.add("ERROR: " + error + "\n");
         return 3;
     }
+    // The `dp` process exits right after this call: its device buffers need no orderly release (dp_main.cpp).
+    if (getenv("SD_FAST_EXIT")) (void)eng.release();
 
-    // per read: add segment offsets (main.cpp:110), PostProcessing (:116), SaveBatch (:117, :272-285)
-    FdWriter outw(out_fd);
-    std::vector<Record> all, kept;
+    // per read: add segment offsets (main.cpp:110), PostProcessing (:116), SaveBatch (:117, :272-285); reads are
+    // formatted in contiguous chunks on a few host threads and written in order
     const int M = (int)mons.seqs.size();
-    for (size_t p = 0; p < reads.seqs.size(); ++p) {
-        all.clear();
-        for (int64_t s = first[p]; s < first[p + 1]; ++s)
-            for (int64_t x = res.rec_off[s]; x < res.rec_off[s + 1]; ++x) {
-                Record r = res.recs[x];
-                r.start += segs[s].first; r.end += segs[s].first;
-                all.push_back(r);
+    const size_t nreads = reads.seqs.size();
+    const int nthr = (int)std::max<size_t>(1, std::min<size_t>({8, std::thread::hardware_concurrency(), (res.recs.size() >> 14) + 1}));
+    std::vector<std::string> out_part(nthr), err_part(nthr);
+    auto format_reads = [&](int t) {
+        std::string &ob = out_part[t], &eb = err_part[t];
+        FdWriter w(-1);
+        std::vector<Record> all, kept;
+        // chunk borders balanced by segment count
+        const int64_t s_lo = (int64_t)segs.size() * t / nthr, s_hi = (int64_t)segs.size() * (t + 1) / nthr;
+        for (size_t p = 0; p < nreads; ++p) {
+            if (first[p] < s_lo || first[p] >= s_hi) continue;
+            all.clear();
+            for (int64_t s = first[p]; s < first[p + 1]; ++s)
+                for (int64_t x = res.rec_off[s]; x < res.rec_off[s + 1]; ++x) {
+                    Record r = res.recs[x];
+                    r.start += segs[s].first; r.end += segs[s].first;
+                    all.push_back(r);
+                }
+            if (all.empty()) continue;     // the reference dereferences batch[0] of an empty vector here (UB)
+            eb += std::to_string((p + 1) * 100 / nreads) + "%: Aligned " + reads.names[p] + "\n";            // main.cpp:115
+            postprocess(all, kept);
+            int prev_end = 0;
+            for (const Record &r : kept) {
+                w.buf += reads.names[p]; w.buf.push_back('\t');
+                w.buf += mons.names[r.row < M ? r.row : r.row - M];
+                if (r.row >= M) w.buf.push_back('\'');
+                w.buf.push_back('\t'); w.add_int(r.start);
+                w.buf.push_back('\t'); w.add_int(r.end);
+                w.buf.push_back('\t'); w.add_int(r.score); w.buf += ".000000";      // to_string(float), main.cpp:279
+                w.buf.push_back('\t'); w.add_int(r.start - prev_end);
+                w.buf.push_back('\t'); w.add_int(r.end - r.start);
+                w.buf.push_back('\n');
+                prev_end = r.end;
             }
-        if (all.empty()) continue;     // the reference dereferences batch[0] of an empty vector here (UB)
-        err.add(std::to_string((p + 1) * 100 / reads.seqs.size()) + "%: Aligned " + reads.names[p] + "\n");   // main.cpp:115
-        postprocess(all, kept);
-        int prev_end = 0;
-        for (const Record &r : kept) {
-            outw.add(reads.names[p]); outw.buf.push_back('\t');
-            outw.add(mons.names[r.row < M ? r.row : r.row - M]);
-            if (r.row >= M) outw.buf.push_back('\'');
-            outw.buf.push_back('\t'); outw.add_int(r.start);
-            outw.buf.push_back('\t'); outw.add_int(r.end);
-            outw.buf.push_back('\t'); outw.add_int(r.score); outw.buf += ".000000";      // to_string(float), main.cpp:279
-            outw.buf.push_back('\t'); outw.add_int(r.start - prev_end);
-            outw.buf.push_back('\t'); outw.add_int(r.end - r.start);
-            outw.buf.push_back('\n');
-            prev_end = r.end;
-            if (outw.buf.size() > (1 << 20)) outw.flush();
         }
+        ob.swap(w.buf);
+    };
+    {
+        std::vector<std::thread> pool;
+        for (int t = 1; t < nthr; ++t) pool.emplace_back(format_reads, t);
+        format_reads(0);
+        for (auto &th : pool) th.join();
     }
-    outw.flush();
+    FdWriter outw(out_fd);
+    for (int t = 0; t < nthr; ++t) {
+        err.add(err_part[t]); err.flush();
+        outw.buf.swap(out_part[t]); outw.flush();
+    }
     if (prof) {
         char line[256];
-        snprintf(line, sizeof line, "[sd_b200 profile] run_files: fasta %.1f engine %.1f batch %.1f decompose %.1f output %.1f ms\n",
-                 tms(t_begin, t_loaded), tms(t_loaded, t_engine), tms(t_engine, t_batch), tms(t_batch, t_done), tms(t_done, tnow()));
+        snprintf(line, sizeof line, "[sd_b200 profile] run_files: fasta %.1f batch %.1f wait-for-device %.1f decompose %.1f output %.1f ms (%d threads)\n",
+                 tms(t_begin, t_loaded), tms(t_loaded, t_batch), tms(t_batch, t_engine), tms(t_engine, t_done), tms(t_done, tnow()), nthr);
         err.add(line);
     }
     return 0;

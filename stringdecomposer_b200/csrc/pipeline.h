@@ -1,6 +1,7 @@
 // pipeline.h -- host driver: FASTA ingest, segmentation, device scheduling, overlap resolution, raw TSV.
 #pragma once
 #include <cstdio>
+#include <functional>
 #include <memory>
 #include <string>
 #include <vector>
@@ -50,9 +51,10 @@ private:
     Batch staged_; std::vector<int> staged_bounds_;
 };
 
-// The whole `dp` run (main.cpp:374-402 after argv parsing).  Returns the exit status.
+// The whole `dp` run (main.cpp:374-402 after argv parsing).  Returns the exit status.  `open_devices` creates the
+// backends (CUDA context creation, ~0.4 s); it runs on its own thread while the FASTA files are read and segmented.
+using DeviceOpener = std::function<int(std::vector<std::unique_ptr<Backend>> &, std::string &)>;
 int run_files(const std::string &reads_path, const std::string &monomers_path, int threads, int part_size, int overlap,
-              const Scoring &sc, int ed_thr, std::vector<std::unique_ptr<Backend>> devs, int out_fd, int err_fd,
-              std::string &error);
+              const Scoring &sc, int ed_thr, DeviceOpener open_devices, int out_fd, int err_fd, std::string &error);
 
 } // namespace sdb
