@@ -63,12 +63,15 @@ SDI_HD void nw_lane_init(NwLane<R> &st, const char *q, int qlen, int row0)
 template <int R>
 SDI_HD uint32_t nw_lane_step(NwLane<R> &st, uint32_t top, uint32_t tc)
 {
-    uint32_t diag = st.up_prev, up = top;
+    // diagonal candidates first: they only read the previous column, so they are independent of the chain below
+    uint32_t cd[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+        cd[r] = (r ? st.left[r - 1] : st.up_prev) + (st.qc[r] == tc ? NW_K_DIAG_EQ : NW_K_DIAG_NE);
+    uint32_t up = top;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const uint32_t cd = diag + (st.qc[r] == tc ? NW_K_DIAG_EQ : NW_K_DIAG_NE);
-        const uint32_t v = nw_addmin(up, NW_K_UP, nw_addmin(st.left[r], NW_K_LEFT, cd)) & NW_CLEAR;
-        diag = st.left[r];
+        const uint32_t v = nw_addmin(up, NW_K_UP, nw_addmin(st.left[r], NW_K_LEFT, cd[r])) & NW_CLEAR;
         st.left[r] = v;
         up = v;
     }
@@ -76,7 +79,11 @@ SDI_HD uint32_t nw_lane_step(NwLane<R> &st, uint32_t top, uint32_t tc)
     return up;              // bottom cell of the strip
 }
 
-SDI_HD int nw_rows_per_lane(int max_qlen) { return max_qlen <= 64 ? 2 : max_qlen <= 128 ? 4 : max_qlen <= 192 ? 6 : 8; }
+// A pair is swept by a group of NW_LANES lanes (four pairs per warp), each lane owning R consecutive query rows:
+// long strips amortise the per-step bookkeeping and the SHFL over many cells and keep the wavefront fill small
+// (171 columns + 7 fill steps), while the 2-deep dependent chain per cell leaves enough independent work per warp.
+constexpr int NW_LANES = 8;
+SDI_HD int nw_rows_per_lane(int max_qlen) { return max_qlen <= 64 ? 8 : max_qlen <= 128 ? 16 : 24; }
 
 // Above 1 MiB of traceback state edlib switches to Hirschberg splitting (edlib.cpp:1187-1191), whose path may differ.
 SDI_HD bool nw_edlib_traceback_domain(int qlen, int tlen)
@@ -90,7 +97,7 @@ struct IdentityArgs {
     const char *ttext; const int64_t *toff; int64_t nt;
     const int32_t *pair_q, *pair_t; int64_t npairs;        // pair_q == nullptr: all queries x all targets, query-major
     int32_t *matches, *columns, *distance;                 // distance may be nullptr
-    uint32_t *scratch; int64_t scratch_stride;             // one row of max target length per warp (tiled queries)
+    uint32_t *scratch; int64_t scratch_stride;             // one row of max target length per lane group (tiled queries)
 };
 
 } // namespace sdb

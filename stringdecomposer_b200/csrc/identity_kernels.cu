@@ -1,7 +1,7 @@
 // identity_kernels.cu -- batched global-alignment identity on the device (replaces the per-alignment
-// edlib.align calls of stringdecomposer/main.py:29-60,96-150).  One warp per (interval, monomer) pair: lanes own
-// strips of R query rows and sweep the target columns as a skewed wavefront; the only cross-lane traffic is one
-// SHFL.UP per step.  No matrix and no traceback state ever leave the registers (identity_core.cuh).
+// edlib.align calls of stringdecomposer/main.py:29-60,96-150).  Eight lanes per (interval, monomer) pair, four pairs
+// per warp: a lane owns a strip of R query rows and the group sweeps the target columns as a skewed wavefront; the
+// only cross-lane traffic is one SHFL.UP per step.  No matrix and no traceback state ever leave the registers (identity_core.cuh).
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -24,50 +24,51 @@ namespace sdb {
                                                __FILE__ + ":" + std::to_string(__LINE__)};                      \
     } while (0)
 
-template <int R>
+template <int R, int L>
 __global__ void __launch_bounds__(256) identity_kernel(IdentityArgs a)
 {
-    const int lane = threadIdx.x & 31;
+    constexpr int G = 32 / L;
+    const int lane = threadIdx.x & 31, gl = lane % L, sub = lane / L;
+    const unsigned mask = ((1u << L) - 1u) << (sub * L);
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    uint32_t *scratch = a.scratch ? a.scratch + warp * a.scratch_stride : nullptr;
-    for (int64_t p = warp; p < a.npairs; p += nwarps) {
+    const int64_t group = warp * G + sub, ngroups = (((int64_t)gridDim.x * blockDim.x) >> 5) * G;
+    uint32_t *scratch = a.scratch ? a.scratch + group * a.scratch_stride : nullptr;
+    for (int64_t p = group; p < a.npairs; p += ngroups) {
         const int64_t qi = a.pair_q ? a.pair_q[p] : p / a.nt, ti = a.pair_q ? a.pair_t[p] : p % a.nt;
         const char *q = a.qtext + a.qoff[qi], *t = a.ttext + a.toff[ti];
         const int qlen = (int)(a.qoff[qi + 1] - a.qoff[qi]), tlen = (int)(a.toff[ti + 1] - a.toff[ti]);
         if (qlen == 0 || tlen == 0) {                       // main.py:30-33: no alignment, identity 0
-            if (lane == 0) { a.matches[p] = 0; a.columns[p] = 0; if (a.distance) a.distance[p] = -1; }
+            if (gl == 0) { a.matches[p] = 0; a.columns[p] = 0; a.distance[p] = -1; }
             continue;
         }
-        const int ntiles = (qlen + 32 * R - 1) / (32 * R);
+        const int ntiles = (qlen + L * R - 1) / (L * R);
         NwLane<R> st;
         for (int tile = 0; tile < ntiles; ++tile) {
-            const int base = tile * 32 * R;
-            nw_lane_init<R>(st, q, qlen, base + lane * R);
-            const int nl = min(32, (qlen - base + R - 1) / R);          // lanes that own at least one row
-            const bool spill = tile + 1 < ntiles;                       // lane 31's bottom row feeds the next tile
+            const int base = tile * L * R;
+            nw_lane_init<R>(st, q, qlen, base + gl * R);
+            const int nl = min(L, (qlen - base + R - 1) / R);           // lanes that own at least one row
+            const bool spill = tile + 1 < ntiles;                       // the last lane's bottom row feeds the next tile
             uint32_t bottom = 0;
             const int nsteps = tlen + nl - 1;
             for (int s = 0; s < nsteps; ++s) {
-                uint32_t top = __shfl_up_sync(0xffffffffu, bottom, 1);
-                const int j = s - lane;
+                uint32_t top = __shfl_up_sync(mask, bottom, 1, L);
+                const int j = s - gl;
                 if (j >= 0 && j < tlen) {
-                    if (lane == 0) top = tile == 0 ? (uint32_t)(j + 1) << NW_DSHIFT : scratch[j];
+                    if (gl == 0) top = tile == 0 ? (uint32_t)(j + 1) << NW_DSHIFT : scratch[j];
                     bottom = nw_lane_step<R>(st, top, (uint32_t)(uint8_t)__ldg(t + j));
-                    if (spill && lane == 31) scratch[j] = bottom;
+                    if (spill && gl == L - 1) scratch[j] = bottom;
                 }
             }
-            __syncwarp();
+            __syncwarp(mask);
         }
-        const int fr = qlen - 1 - (ntiles - 1) * 32 * R;
+        const int fr = qlen - 1 - (ntiles - 1) * L * R;
         uint32_t v = 0;
 #pragma unroll
         for (int r = 0; r < R; ++r) if (r == fr % R) v = st.left[r];
-        v = __shfl_sync(0xffffffffu, v, fr / R);
-        if (lane == 0) {
+        v = __shfl_sync(mask, v, fr / R, L);
+        if (gl == 0) {
             const int d = (int)(v >> NW_DSHIFT), m = (int)(v & 0xffffu);
-            a.matches[p] = m; a.columns[p] = m + d;
-            if (a.distance) a.distance[p] = d;
+            a.matches[p] = m; a.columns[p] = m + d; a.distance[p] = d;
         }
     }
 }
@@ -112,11 +113,33 @@ int cuda_identity(const IdentityArgs &h, int max_qlen, int max_tlen, int device,
         const auto t_begin = std::chrono::steady_clock::now();
         auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
         const size_t qbytes = (size_t)h.qoff[h.nq], tbytes = (size_t)h.toff[h.nt];
-        const int R = nw_rows_per_lane(max_qlen);
-        const int threads = 256, wpb = threads / 32;
-        int64_t blocks = std::min<int64_t>((h.npairs + wpb - 1) / wpb, (int64_t)sms * 8);          // 64 warps per SM
+        // rows per lane: the strip length that minimises tiles x instructions per step over the batch's queries
+        int R = 24, L = NW_LANES;
+        {
+            double best = 1e300;
+            for (int cand : {8, 16, 24}) {
+                double cost = 0;
+                for (int64_t i = 0; i < h.nq; ++i) {
+                    const int64_t ql = h.qoff[i + 1] - h.qoff[i];
+                    cost += (double)((ql + L * cand - 1) / (L * cand)) * (7.0 * cand + 25.0);
+                }
+                if (cost < best) { best = cost; R = cand; }
+            }
+        }
+        if (const char *e = getenv("SD_NW_GEOM")) { int l = 0, r = 0; if (sscanf(e, "%d,%d", &l, &r) == 2) { L = l; R = r; } }   // experiments
+        void (*kernel)(IdentityArgs) = nullptr;
+        if (L == 8 && R == 8) kernel = identity_kernel<8, 8>;
+        else if (L == 8 && R == 16) kernel = identity_kernel<16, 8>;
+        else if (L == 8 && R == 24) kernel = identity_kernel<24, 8>;
+        else if (L == 16 && R == 12) kernel = identity_kernel<12, 16>;
+        else if (L == 32 && R == 6) kernel = identity_kernel<6, 32>;
+        else { err = "unsupported SD_NW_GEOM"; return 4; }
+        const int threads = 256, wpb = threads / 32 * (32 / L);                                    // pairs in flight per block
+        int resident = 1;                                           // grid-stride kernel: exactly one resident wave of blocks
+        SDI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, threads, 0));
+        int64_t blocks = std::min<int64_t>((h.npairs + wpb - 1) / wpb, (int64_t)sms * std::max(1, resident));
         if (blocks < 1) blocks = 1;
-        const size_t stride = max_qlen > 32 * R ? (size_t)((max_tlen + 31) & ~31) : 0;
+        const size_t stride = max_qlen > L * R ? (size_t)((max_tlen + 31) & ~31) : 0;
         const size_t np = (size_t)h.npairs;
         Arena &ar = g_arena[device];
         ar.reserve(pad(qbytes) + pad(tbytes) + pad(8 * (h.nq + 1)) + pad(8 * (h.nt + 1)) + 5 * pad(4 * np) +
@@ -142,12 +165,7 @@ int cuda_identity(const IdentityArgs &h, int max_qlen, int max_tlen, int device,
         a.scratch_stride = (int64_t)stride;
         const double t_h2d = since();
         SDI_CUDA(cudaEventRecord(ar.e0));
-        switch (R) {
-        case 2: identity_kernel<2><<<(unsigned)blocks, threads>>>(a); break;
-        case 4: identity_kernel<4><<<(unsigned)blocks, threads>>>(a); break;
-        case 6: identity_kernel<6><<<(unsigned)blocks, threads>>>(a); break;
-        default: identity_kernel<8><<<(unsigned)blocks, threads>>>(a); break;
-        }
+        kernel<<<(unsigned)blocks, threads>>>(a);
         SDI_CUDA(cudaGetLastError());
         SDI_CUDA(cudaEventRecord(ar.e1));
         SDI_CUDA(cudaMemcpyAsync(h.matches, a.matches, 4 * np, cudaMemcpyDeviceToHost));

@@ -250,30 +250,31 @@ private:
 Backend *make_emu_backend() { return new EmuBackend(); }
 
 // Host emulation of identity_kernel (identity_kernels.cu): the same strips, tiles, wavefront steps and spill row,
-// with the 32 lanes of the warp walked in descending order so that lane l reads lane l-1's bottom cell of the
+// with the NW_LANES lanes of a group walked in descending order so that lane l reads lane l-1's bottom cell of the
 // previous step, exactly what the SHFL.UP delivers on the device.
 template <int R>
 static void emu_identity_pair(const char *q, int qlen, const char *t, int tlen, std::vector<uint32_t> &scratch, int &m, int &d)
 {
-    const int ntiles = (qlen + 32 * R - 1) / (32 * R);
-    NwLane<R> st[32];
-    uint32_t bottom[32];
+    constexpr int L = NW_LANES;
+    const int ntiles = (qlen + L * R - 1) / (L * R);
+    NwLane<R> st[L];
+    uint32_t bottom[L];
     for (int tile = 0; tile < ntiles; ++tile) {
-        const int base = tile * 32 * R;
-        for (int l = 0; l < 32; ++l) { nw_lane_init<R>(st[l], q, qlen, base + l * R); bottom[l] = 0; }
-        const int nl = std::min(32, (qlen - base + R - 1) / R);
+        const int base = tile * L * R;
+        for (int l = 0; l < L; ++l) { nw_lane_init<R>(st[l], q, qlen, base + l * R); bottom[l] = 0; }
+        const int nl = std::min(L, (qlen - base + R - 1) / R);
         const bool spill = tile + 1 < ntiles;
         for (int s = 0; s < tlen + nl - 1; ++s)
-            for (int l = 31; l >= 0; --l) {
+            for (int l = L - 1; l >= 0; --l) {
                 uint32_t top = bottom[l ? l - 1 : 0];
                 const int j = s - l;
                 if (j < 0 || j >= tlen) continue;
                 if (l == 0) top = tile == 0 ? (uint32_t)(j + 1) << NW_DSHIFT : scratch[j];
                 bottom[l] = nw_lane_step<R>(st[l], top, (uint32_t)(uint8_t)t[j]);
-                if (spill && l == 31) scratch[j] = bottom[l];
+                if (spill && l == L - 1) scratch[j] = bottom[l];
             }
     }
-    const int fr = qlen - 1 - (ntiles - 1) * 32 * R;
+    const int fr = qlen - 1 - (ntiles - 1) * L * R;
     const uint32_t v = st[fr / R].left[fr % R];
     d = (int)(v >> NW_DSHIFT); m = (int)(v & 0xffffu);
 }
@@ -289,10 +290,9 @@ int emu_identity(const IdentityArgs &a, int max_qlen, int max_tlen, double *kern
         int m = 0, d = -1;
         if (qlen > 0 && tlen > 0) {
             switch (R) {
-            case 2: emu_identity_pair<2>(q, qlen, t, tlen, scratch, m, d); break;
-            case 4: emu_identity_pair<4>(q, qlen, t, tlen, scratch, m, d); break;
-            case 6: emu_identity_pair<6>(q, qlen, t, tlen, scratch, m, d); break;
-            default: emu_identity_pair<8>(q, qlen, t, tlen, scratch, m, d); break;
+            case 8: emu_identity_pair<8>(q, qlen, t, tlen, scratch, m, d); break;
+            case 16: emu_identity_pair<16>(q, qlen, t, tlen, scratch, m, d); break;
+            default: emu_identity_pair<24>(q, qlen, t, tlen, scratch, m, d); break;
             }
         }
         a.matches[p] = m; a.columns[p] = d < 0 ? 0 : m + d;
