@@ -83,7 +83,22 @@ SDI_HD uint32_t nw_lane_step(NwLane<R> &st, uint32_t top, uint32_t tc)
 // long strips amortise the per-step bookkeeping and the SHFL over many cells and keep the wavefront fill small
 // (171 columns + 7 fill steps), while the 2-deep dependent chain per cell leaves enough independent work per warp.
 constexpr int NW_LANES = 8;
-SDI_HD int nw_rows_per_lane(int max_qlen) { return max_qlen <= 64 ? 8 : max_qlen <= 128 ? 16 : 24; }
+// Rows per lane for a batch: the strip length (8, 16 or 24) that minimises tiles x instructions per step summed
+// over the batch's queries (a query longer than NW_LANES * R rows is swept in several tiles).
+inline int nw_choose_rows(const int64_t *qoff, int64_t nq)
+{
+    int best_r = 24;
+    double best = 1e300;
+    for (int cand : {8, 16, 24}) {
+        double cost = 0;
+        for (int64_t i = 0; i < nq; ++i) {
+            const int64_t ql = qoff[i + 1] - qoff[i];
+            cost += (double)((ql + NW_LANES * cand - 1) / (NW_LANES * cand)) * (7.0 * cand + 25.0);
+        }
+        if (cost < best) { best = cost; best_r = cand; }
+    }
+    return best_r;
+}
 
 // Above 1 MiB of traceback state edlib switches to Hirschberg splitting (edlib.cpp:1187-1191), whose path may differ.
 SDI_HD bool nw_edlib_traceback_domain(int qlen, int tlen)

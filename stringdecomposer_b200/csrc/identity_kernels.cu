@@ -113,19 +113,7 @@ int cuda_identity(const IdentityArgs &h, int max_qlen, int max_tlen, int device,
         const auto t_begin = std::chrono::steady_clock::now();
         auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
         const size_t qbytes = (size_t)h.qoff[h.nq], tbytes = (size_t)h.toff[h.nt];
-        // rows per lane: the strip length that minimises tiles x instructions per step over the batch's queries
-        int R = 24, L = NW_LANES;
-        {
-            double best = 1e300;
-            for (int cand : {8, 16, 24}) {
-                double cost = 0;
-                for (int64_t i = 0; i < h.nq; ++i) {
-                    const int64_t ql = h.qoff[i + 1] - h.qoff[i];
-                    cost += (double)((ql + L * cand - 1) / (L * cand)) * (7.0 * cand + 25.0);
-                }
-                if (cost < best) { best = cost; R = cand; }
-            }
-        }
+        int R = nw_choose_rows(h.qoff, h.nq), L = NW_LANES;
         if (const char *e = getenv("SD_NW_GEOM")) { int l = 0, r = 0; if (sscanf(e, "%d,%d", &l, &r) == 2) { L = l; R = r; } }   // experiments
         void (*kernel)(IdentityArgs) = nullptr;
         if (L == 8 && R == 8) kernel = identity_kernel<8, 8>;

@@ -281,7 +281,8 @@ static void emu_identity_pair(const char *q, int qlen, const char *t, int tlen, 
 
 int emu_identity(const IdentityArgs &a, int max_qlen, int max_tlen, double *kernel_ms, std::string &)
 {
-    const int R = nw_rows_per_lane(max_qlen);
+    (void)max_qlen;
+    const int R = nw_choose_rows(a.qoff, a.nq);
     std::vector<uint32_t> scratch((size_t)max_tlen + 32);
     for (int64_t p = 0; p < a.npairs; ++p) {
         const int64_t qi = a.pair_q ? a.pair_q[p] : p / a.nt, ti = a.pair_q ? a.pair_t[p] : p % a.nt;

@@ -16,7 +16,7 @@ import sd_convert_oracle as CO
 import sd_oracle as O
 import stringdecomposer_b200 as sd
 from stringdecomposer_b200 import convert as cv
-from stringdecomposer_b200 import main as sdmain
+from stringdecomposer_b200 import cli as sdmain
 
 G = cases.GOLDEN
 

@@ -13,7 +13,7 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from stringdecomposer_b200 import synth, main as sdmain, convert as cv  # noqa: E402
+from stringdecomposer_b200 import synth, cli as sdmain, convert as cv  # noqa: E402
 
 
 def main():
