@@ -336,6 +336,11 @@ def main():
         dist.destroy_process_group()
 
 
+# ALU-pipe instructions per cell of identity_kernel (2 VIADDMNMX + 2 VIADD + 1 LOP3; the ISETP issues elsewhere):
+# 4.96 measured from sm__inst_executed_pipe_alu in profiles/r01_identity_r1.md
+IDENTITY_ALU_OPS_PER_CELL = 5
+
+
 def rescoring(segs, mons, recs, roff, device, alu_peak):
     """Extra, outside the timed step: the reference's next stage (main.py:29-60, one edlib global alignment per
     interval/monomer pair) on the intervals this very decomposition produced, against all 24 monomer rows."""
@@ -352,7 +357,8 @@ def rescoring(segs, mons, recs, roff, device, alu_peak):
     return {"what": "identity_kernel: NW identity of every decomposed interval x %d monomer rows (main.py aai)" % len(rows),
             "pairs": len(res["matches"]), "cells": cells, "kernel_ms": best_k, "kernel_gcups": cells / best_k / 1e6,
             "call_ms_host_buffers": best_w * 1e3, "alignments_per_s_host_buffers": len(res["matches"]) / best_w,
-            "alu_ops_per_cell": 6, "int_alu_roofline_frac": cells / (best_k * 1e-3) * 6 / alu_peak}
+            "alu_ops_per_cell": IDENTITY_ALU_OPS_PER_CELL,
+            "int_alu_roofline_frac": cells / (best_k * 1e-3) * IDENTITY_ALU_OPS_PER_CELL / alu_peak}
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one sweep_kernel launch on this workload (ncu --set full, profiles/)
