@@ -26,6 +26,11 @@ with open(os.path.join(out_dir, "%s_launches.md" % tag), "w") as f:
     f.write("Per-launch times under ncu are cold-cache and serialised: compare shares, not absolutes.\n\n| kernel | launches | total ms | share |\n|---|---|---|---|\n")
     for name, (n, ms) in sorted(tot.items(), key=lambda x: -x[1][1]):
         f.write("| %s | %d | %.3f | %.1f %% |\n" % (name, n, ms, 100 * ms / allms))
+    step = {k: v[1] for k, v in tot.items() if any(x in k for x in ("sweep_kernel", "sweep_group_kernel", "traceback_kernel", "gather_kernel", "hw_distance_kernel"))}
+    if step:
+        f.write("\nThe timed step of bench.py is sweep + traceback (+ gather); `identity_kernel` (the `rescoring` extra), `int_peak_kernel` "
+                "(the roofline peak probe) and torch's memset run outside it.  Shares within the step: " +
+                ", ".join("%s %.1f %%" % (k.split("::")[-1], 100 * v / sum(step.values())) for k, v in sorted(step.items(), key=lambda x: -x[1])) + ".\n")
 print(open(os.path.join(out_dir, "%s_launches.md" % tag)).read())
 
 KEYS = ["gpu__time_duration.sum", "sm__cycles_elapsed.avg", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
