@@ -97,6 +97,15 @@ def test_library_exports_identity_symbol():
         assert hasattr(ctypes.CDLL(path), "sd_identity")
 
 
+def test_identity_has_no_cpu_path():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(sd.SdError) as e:                    # the CUDA library refuses, it does not fall back
+        sd.nw_identity(["ACGT"], ["ACGA"])
+    assert e.value.status == 2 and "no CPU path" in str(e.value)
+
+
 def test_emulated_kernel_equals_golden_pairs():
     ps = golden_pairs()
     qs, ts = [p["q"] for p in ps], [p["t"] for p in ps]
