@@ -189,7 +189,9 @@ __global__ void sweep_kernel(const SweepArgs a)
             const int wk = __reduce_max_sync(0xffffffffu, key);
             if (lane == 0) asm volatile("st.shared.b32 [%0], %1;" ::"r"(key_wr_s + kboff), "r"(wk) : "memory");
         } else {
-            const uint32_t kclr = (kboff == 0) ? 2 * kbytes : kboff - kbytes;      // buffer read two columns ago
+            // reset the buffer of the NEXT column: it was last read two columns ago, and every thread has passed a
+            // barrier since (the buffer of the previous column may still be being read by a slower warp)
+            const uint32_t kclr = (kboff == 2 * kbytes) ? 0 : kboff + kbytes;
             if (tid < NS) asm volatile("st.shared.b32 [%0], %1;" ::"r"(skey_s + kclr + 4u * tid), "r"(INT_MIN) : "memory");
             if (is_end) atomicMax(reinterpret_cast<int *>(reinterpret_cast<char *>(skey) + kboff) + seg_local, key);
         }
