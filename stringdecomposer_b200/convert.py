@@ -78,11 +78,25 @@ def _collapse(blob, off):
 
 
 def _pack(seqs):
-    bs = [s.encode() for s in seqs]
-    off = np.zeros(len(bs) + 1, dtype=np.int64)
-    if bs:
+    """Sequences -> (blob, int64 offsets), each without the one trailing '*' that aai() drops (main.py:38-41)."""
+    lens = np.fromiter(map(len, seqs), dtype=np.int64, count=len(seqs))
+    blob = "".join(seqs).encode()
+    off = np.zeros(len(seqs) + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    if len(blob) != off[-1]:                                  # non-ASCII text: byte lengths differ from str lengths
+        bs = [s.encode() for s in seqs]
+        blob = b"".join(bs)
         np.cumsum([len(x) for x in bs], out=off[1:])
-    return b"".join(bs), off
+    if b"*" in blob:
+        b = np.frombuffer(blob, dtype=np.uint8)
+        ends = off[1:] - 1
+        star = (off[1:] > off[:-1]) & (b[np.maximum(ends, 0)] == ord("*"))
+        if star.any():
+            keep = np.ones(len(b), dtype=bool)
+            keep[ends[star]] = False
+            blob = b[keep].tobytes()
+            off = off - np.concatenate(([0], np.cumsum(star)))
+    return blob, off
 
 
 def _percent(res):
@@ -111,15 +125,15 @@ def classify(score, second_best_score):
     return np.where(x.dot(np.asarray(LR_MODEL_COEF)) > 0, "+", "?") if len(score) else np.zeros(0, dtype="<U1")
 
 
-def _rescore(meta, pieces, monomers, light, device, flavour, stats):
-    """The body of convert_read (main.py:107-150) for any number of raw lines at once.  meta: [(monomer name, start,
-    end)]; pieces: the read intervals of those lines.  Returns the reference's list of dicts (same keys)."""
+def _score(meta, pieces, monomers, light, device, flavour, stats):
+    """The numeric body of convert_read + classify (main.py:96-150) for any number of raw lines at once.  meta:
+    [(monomer name, start, end)]; pieces: the read intervals of those lines.  Returns plain lists / arrays:
+    light: {"score", "q"};  else also "second", "second_score", "homo" / "homo_score" (two best, by name), "uniq"
+    (the keys of the reference's `scores` dict, in its order) and "table" (n x len(uniq) identities)."""
     n = len(meta)
-    if n == 0:
-        return []
     names = [m[0] for m in monomers]
-    qblob, qoff = _pack([_strip_star(p) for p in pieces])
-    tblob, toff = _pack([_strip_star(m[1]) for m in monomers])
+    qblob, qoff = _pack(pieces)                       # aai() drops one trailing '*' of either side (main.py:38-41)
+    tblob, toff = _pack([m[1] for m in monomers])
 
     def run(q, t, pairs=None):
         r = nw_identity(q, t, pairs=pairs, device=device, flavour=flavour)
@@ -130,17 +144,11 @@ def _rescore(meta, pieces, monomers, light, device, flavour, stats):
             stats["hirschberg_pairs"] = stats.get("hirschberg_pairs", 0) + r["hirschberg_pairs"]
         return _percent(r)
 
-    res = []
     if light:
         last = {nm: i for i, nm in enumerate(names)}              # the loop at main.py:113-116 keeps the last match
         cols = np.array([last[m[0]] for m in meta], dtype=np.int32)          # KeyError like scores[monomer]
         score = run((qblob, qoff), (tblob, toff), pairs=(np.arange(n, dtype=np.int32), cols))
-        flags = classify(score, np.full(n, -1.0))
-        for k, (mono, start, end) in enumerate(meta):
-            res.append({"m": mono, "start": str(start), "end": str(end), "score": float(score[k]),
-                        "second_best": "None", "second_best_score": -1, "homo_best": "None", "homo_best_score": -1,
-                        "homo_second_best": "None", "homo_second_best_score": -1, "alt": {}, "q": str(flags[k])})
-        return res
+        return {"score": score.tolist(), "q": classify(score, np.full(n, -1.0)).tolist()}
 
     nm = len(names)
     plain = run((qblob, qoff), (tblob, toff)).reshape(n, nm)
@@ -161,19 +169,37 @@ def _rescore(meta, pieces, monomers, light, device, flavour, stats):
         masked[rows, mine] = -np.inf
         second = np.argmax(masked, axis=1)                          # first of the largest, like main.py:131-135
         second_score = masked[rows, second]
-        second_name = [uniq[i] for i in second]
+        second_name = [uniq[i] for i in second.tolist()]
+        second_out = second_score.tolist()
     else:
         second_score = np.full(n, -1.0)
-        second_name = ["None"] * n
+        second_name = ["None"] * n                                  # str(None), main.py:145
+        second_out = [-1] * n
     order = np.argsort(-homo, axis=1, kind="stable")[:, :2]          # sorted(..., key=-score), main.py:143
-    flags = classify(best, second_score)
+    return {"score": best.tolist(), "q": classify(best, second_score).tolist(), "second": second_name,
+            "second_score": second_out,
+            "homo": [[names[a], names[b]] for a, b in order.tolist()],
+            "homo_score": np.take_along_axis(homo, order, axis=1).tolist(),
+            "uniq": uniq, "table": table.tolist()}
+
+
+def _rescore(meta, pieces, monomers, light, device, flavour, stats):
+    """_score() in the shape convert_read returns: the reference's list of dicts (same keys, main.py:117-147)."""
+    if not meta:
+        return []
+    sc = _score(meta, pieces, monomers, light, device, flavour, stats)
+    res = []
     for k, (mono, start, end) in enumerate(meta):
-        h0, h1 = int(order[k, 0]), int(order[k, 1])
-        res.append({"m": mono, "start": str(start), "end": str(end), "score": float(best[k]),
-                    "second_best": second_name[k], "second_best_score": float(second_score[k]) if len(uniq) > 1 else -1,
-                    "homo_best": names[h0], "homo_best_score": float(homo[k, h0]),
-                    "homo_second_best": names[h1], "homo_second_best_score": float(homo[k, h1]),
-                    "alt": {u: float(table[k, i]) for i, u in enumerate(uniq)}, "q": str(flags[k])})
+        if light:
+            res.append({"m": mono, "start": str(start), "end": str(end), "score": sc["score"][k],
+                        "second_best": "None", "second_best_score": -1, "homo_best": "None", "homo_best_score": -1,
+                        "homo_second_best": "None", "homo_second_best_score": -1, "alt": {}, "q": sc["q"][k]})
+        else:
+            res.append({"m": mono, "start": str(start), "end": str(end), "score": sc["score"][k],
+                        "second_best": sc["second"][k], "second_best_score": sc["second_score"][k],
+                        "homo_best": sc["homo"][k][0], "homo_best_score": sc["homo_score"][k][0],
+                        "homo_second_best": sc["homo"][k][1], "homo_second_best_score": sc["homo_score"][k][1],
+                        "alt": dict(zip(sc["uniq"], sc["table"][k])), "q": sc["q"][k]})
     return res
 
 
@@ -211,30 +237,50 @@ def print_read(fout, fout_alt, dec, read, monomers, identity_th, light, read_nam
     _write(fout, fout_alt, [read_name] * len(out), out, identity_th)
 
 
+def _write_chunk(fout, fout_alt, names, meta, sc, identity_th, light):
+    """print_read's two loops (main.py:155-166) straight from the arrays of _score(): same text as _write() on the
+    dicts, without building them (the formatting is what this stage costs on the host)."""
+    if light:
+        fout.write("".join(
+            f"{nm}\t{m}\t{s}\t{e}\t{v:.2f}\tNone\t-1.00\tNone\t-1.00\tNone\t-1.00\t{q}\n"
+            for nm, (m, s, e), v, q in zip(names, meta, sc["score"], sc["q"]) if v >= identity_th))
+        return
+    uniq = sc["uniq"]
+    main, alt = [], []
+    for nm, (m, s, e), v, q, sn, sv, hn, hv, row in zip(names, meta, sc["score"], sc["q"], sc["second"], sc["second_score"],
+                                                        sc["homo"], sc["homo_score"], sc["table"]):
+        if v >= identity_th:
+            main.append(f"{nm}\t{m}\t{s}\t{e}\t{v:.2f}\t{sn}\t{sv:.2f}\t{hn[0]}\t{hv[0]:.2f}\t{hn[1]}\t{hv[1]:.2f}\t{q}\n")
+            head = f"{nm}\t"
+            tail = f"\t{s}\t{e}\t"
+            alt.append("".join(f"{head}{u}{tail}{x:.2f}\t{'*' if u == m else '-'}\n" for u, x in zip(uniq, row)))
+    fout.write("".join(main))
+    fout_alt.write("".join(alt))
+
+
 def convert_tsv(decomposition, reads, monomers, outfile, identity_th, light, device=0, flavour="cuda", stats=None):
     """main.py:168-184: raw `dp` text -> ``outfile`` and ``outfile[:-4] + "_alt.tsv"``.  reads: {id: sequence};
     monomers: the add_rc_monomers() list.  Every raw line is rescored independently of the others (the reference's
     per-read grouping only selects the read to cut from), so lines of many reads share one device call."""
     per_line = 1 if light else 2 * max(1, len(monomers))
     chunk = max(1, MAX_PAIRS_PER_CALL // per_line)
+    lines = decomposition.split("\n")[:-1]
+    first_word = {}                   # `x.split()[0]` of main.py:175-176, once per distinct name instead of per line
     with open(outfile[:-len(".tsv")] + "_alt.tsv", "w") as fout_alt, open(outfile, "w") as fout:
-        names, meta, pieces = [], [], []
-
-        def flush():
-            _write(fout, fout_alt, names, _rescore(meta, pieces, monomers, light, device, flavour, stats), identity_th)
-            names.clear(); meta.clear(); pieces.clear()
-
-        for ln in decomposition.split("\n")[:-1]:
-            read, monomer, start, end = ln.split("\t")[:4]
-            read, monomer = read.split()[0], monomer.split()[0]
-            start, end = int(start), int(end)
-            names.append(read)
-            meta.append((monomer, start, end))
-            pieces.append(reads[read][start:end + 1])
-            if len(meta) >= chunk:
-                flush()
-        if meta:
-            flush()
+        for lo in range(0, len(lines), chunk):
+            names, meta, pieces = [], [], []
+            for ln in lines[lo:lo + chunk]:
+                read, monomer, start, end = ln.split("\t")[:4]
+                if read not in first_word:
+                    first_word[read] = read.split()[0]
+                if monomer not in first_word:
+                    first_word[monomer] = monomer.split()[0]
+                read, start, end = first_word[read], int(start), int(end)
+                names.append(read)
+                meta.append((first_word[monomer], start, end))
+                pieces.append(reads[read][start:end + 1])
+            _write_chunk(fout, fout_alt, names, meta, _score(meta, pieces, monomers, light, device, flavour, stats),
+                         identity_th, light)
 
 
 __all__ = ["LR_MODEL_COEF", "load_fasta", "add_rc_monomers", "convert_to_homo", "aai", "classify", "convert_read",

@@ -170,6 +170,12 @@ def test_convert_min_identity_duplicates_and_chunking(tmp_path, monkeypatch):
             cv.convert_tsv(raw, {"rd": read}, cv.add_rc_monomers(mons), out, thr, light, flavour=cases.EMU_LIB)
             fin, alt = CO.final_tsv(raw, {"rd": read}, mons, thr, light)
             assert open(out).read() == fin and open(out[:-4] + "_alt.tsv").read() == alt
+            # the per-read entry points of the reference (print_read / convert_read dicts) give the same text
+            import io
+            fo, fa = io.StringIO(), io.StringIO()
+            dec = [{"m": ln.split("\t")[1], "start": int(ln.split("\t")[2]), "end": int(ln.split("\t")[3])} for ln in raw.splitlines()]
+            cv.print_read(fo, fa, dec, read, cv.add_rc_monomers(mons), thr, light, read_name="rd", flavour=cases.EMU_LIB)
+            assert fo.getvalue() == fin and fa.getvalue() == alt
 
 
 def test_helpers_follow_the_reference():
@@ -177,6 +183,8 @@ def test_helpers_follow_the_reference():
     assert cv.add_rc_monomers([("x", "AACGN")]) == [("x", "AACGN"), ("x'", "NCGTT")]
     blob, off = cv._collapse(b"AAACCAAT", np.array([0, 3, 5, 8]))
     assert (blob, list(off)) == (b"ACAT", [0, 1, 2, 4])
+    blob, off = cv._pack(["ACGT*", "", "A*", "*", "AC", "**"])                      # one trailing '*' dropped, main.py:38-41
+    assert (blob, list(off)) == (b"ACGTAAC*", [0, 4, 4, 5, 5, 7, 8])
     assert list(cv.classify([95.0, 20.0], [-1, -1])) == ["+", "?"]
     assert cv.aai(["ACGT*", "ACGT"], flavour=cases.EMU_LIB) == 100.0
     assert cv.aai(["", "ACGT"], flavour=cases.EMU_LIB) == 0.0
