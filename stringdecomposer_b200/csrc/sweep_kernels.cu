@@ -51,7 +51,7 @@ struct TbArgs {
 // three consecutive backpointer words around the cell the diagonal through the current position predicts.  Every
 // round all lanes decode "their" cell on that diagonal at once; a ballot finds the first column whose move is not
 // diagonal, the walk jumps over the whole diagonal run, and only the odd move (deletion, insertion, close, k==0)
-// is handled serially.  The window is refilled (one HBM round trip) when the path leaves it.
+// is handled serially.  Windows further down the diagonal are fetched ahead with cp.async (see TB_RING).
 constexpr int TB_WARPS = 4;
 __global__ void __launch_bounds__(TB_WARPS * 32) traceback_kernel(const TbArgs a)
 {
@@ -75,22 +75,35 @@ __global__ void __launch_bounds__(TB_WARPS * 32) traceback_kernel(const TbArgs a
     int r = r2r ? r2r[jr[n].row] : jr[n].row;
     int last = a.row_off[r + 1] - a.row_off[r] - 1;
     int k = last, end = i, end_score = jr[n].j, cnt = 0;
-    // window (per lane) and the prefetched next window (columns i0-32-lane along the same diagonal)
-    int i0 = -1000, row0 = -1, half = 0;
+    // Window (per lane): the three words around this lane's cell, and a ring of look-ahead windows further down the
+    // same diagonal (columns i0-32j-lane).  A clean 32-column window is consumed in ~150 cycles, a tenth of an HBM
+    // round trip, and the backpointers left L2 long ago, so the walk is bound by how many windows one round trip
+    // brings in.  A refill therefore fetches TB_RING windows at once -- for a 171-bp monomer the whole row -- with
+    // cp.async into shared memory: unlike a register ring, nothing touches the data (and stalls on it) before the
+    // window is adopted.  Every lane reads back only what it copied itself, so no barrier is involved.
+    constexpr int TB_RING = 8;
+    __shared__ uint32_t s_ring[TB_WARPS][TB_RING][4][32];          // [.][.][0..2] words, [3] = word base | valid << 31
+    uint32_t (*ring)[4][32] = s_ring[threadIdx.x >> 5];
+    int i0 = -1000, row0 = -1, half = 0, ni0 = -2000, cur = 0;
     uint32_t w0 = 0, w1 = 0, w2 = 0; int wb = 0; bool colok = false;
-    uint32_t n0 = 0, n1 = 0, n2 = 0; int nwb = 0; bool ncolok = false; int ni0 = -2000;
     const uint32_t *rowbase = nullptr;                  // first word of the current row's slot in column 0
-    auto load_window = [&](int iw, int kw, uint32_t &x0, uint32_t &x1, uint32_t &x2, int &xb, bool &xok) {
+    auto issue_window = [&](int slot, int iw, int kw) {
         const int c = iw - lane;
-        xok = c >= 0;
+        const bool xok = c >= 0 && kw >= 1;             // kw < 1: the window lies before the start of the row
+        int xb = 0;
         if (xok) {
             const int kp = max(kw - lane, 0);
             const int t = (kp * invC) >> 16;
             const int wl = t * CW + ((kp - t * C) >> cshift);
             xb = min(max(wl - 1, 0), max(maxwl - 2, 0));
             const uint32_t *col = rowbase + (size_t)c * cstride;
-            x0 = col[xb]; x1 = col[min(xb + 1, maxwl)]; x2 = col[min(xb + 2, maxwl)];
+            const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(&ring[slot][0][lane]);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d0), "l"(col + xb) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d0 + 128u), "l"(col + min(xb + 1, maxwl)) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d0 + 256u), "l"(col + min(xb + 2, maxwl)) : "memory");
         }
+        ring[slot][3][lane] = (uint32_t)xb | (xok ? 0x80000000u : 0u);
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
     for (;;) {
@@ -110,19 +123,29 @@ __global__ void __launch_bounds__(TB_WARPS * 32) traceback_kernel(const TbArgs a
         } else {
             if (r != row0 || i > i0 || i <= i0 - 32) {
                 if (r == row0 && i == ni0) {
-                    // the walk ran straight into the prefetched window: adopt it (if the path drifted out of its three
-                    // words the decode below notices and forces a reload) and prefetch the one after it
-                    i0 = ni0; w0 = n0; w1 = n1; w2 = n2; wb = nwb; colok = ncolok;
+                    // the walk ran straight into the next window of the ring: adopt it (if the path drifted out of its
+                    // three words the decode below notices and forces a refill) and reuse the freed slot for the
+                    // window TB_RING-1 further down
+                    i0 = ni0;
+                    const int freed = cur;
+                    cur = cur + 1 == TB_RING ? 0 : cur + 1;
+                    issue_window(freed, i0 - 32 * (TB_RING - 1), k - 32 * (TB_RING - 1));
                 } else {
-                    // refill: lane d loads the words around cell k-d of column i-d
+                    // refill: lane d fetches the words around cell k-d of column i-d, and of the windows behind it
                     i0 = i; row0 = r;
                     const RowPlace pl = place_row(g, seg_local, r);
                     half = pl.half;
                     rowbase = a.codes + a.cta_code_off[cta0 + (g.NG > 1 ? pl.grp : 0)] + (size_t)lane_tid(g.T, pl.ginst, 0) * CW;
-                    load_window(i, k, w0, w1, w2, wb, colok);
+                    asm volatile("cp.async.wait_all;" ::: "memory");     // nothing of an abandoned ring may land later
+                    cur = 0;
+#pragma unroll
+                    for (int j = 0; j < TB_RING; ++j) issue_window(j, i - 32 * j, k - 32 * j);
                 }
                 ni0 = i0 - 32;
-                load_window(ni0, k - 32, n0, n1, n2, nwb, ncolok);
+                asm volatile("cp.async.wait_group %0;" ::"n"(TB_RING - 1) : "memory");
+                w0 = ring[cur][0][lane]; w1 = ring[cur][1][lane]; w2 = ring[cur][2][lane];
+                const uint32_t meta = ring[cur][3][lane];
+                wb = (int)(meta & 0x7fffffffu); colok = (meta >> 31) != 0;
             }
             const int dcur = i0 - i;
             const int kd = k - (lane - dcur);
