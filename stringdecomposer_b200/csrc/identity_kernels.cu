@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "common.h"
+#include "cuda_scope.h"
 #include "identity_core.cuh"
 
 namespace sdb {
@@ -104,7 +105,8 @@ int cuda_identity(const IdentityArgs &h, int max_qlen, int max_tlen, int device,
     std::lock_guard<std::mutex> lock(g_arena_mu);
     try {
         if (device < 0 || device >= 64) { err = "device id out of range"; return 2; }
-        SDI_CUDA(cudaSetDevice(device));
+        DeviceScope scope(device);                       // the caller's current device is restored on return
+        SDI_CUDA(scope.status);
         int major = 0, sms = 0;
         SDI_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
         SDI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));

@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "sweep_kernel.cuh"
+#include "cuda_scope.h"
 
 namespace sdb {
 
@@ -267,7 +268,7 @@ class CudaBackend : public Backend {
 public:
     explicit CudaBackend(int dev) : dev_(dev)
     {
-        SD_CUDA(cudaSetDevice(dev_));
+        DeviceScope scope_(dev_); SD_CUDA(scope_.status);
         SD_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
         for (auto &e : ev_) SD_CUDA(cudaEventCreate(&e));
         SD_CUDA(cudaGetDeviceProperties(&prop_, dev_));
@@ -278,7 +279,7 @@ public:
     }
     ~CudaBackend() override
     {
-        cudaSetDevice(dev_);
+        DeviceScope scope_(dev_);
         for (auto &e : ev_) cudaEventDestroy(e);
         cudaStreamDestroy(st_);
     }
@@ -286,7 +287,7 @@ public:
 
     void configure(const Plan &p, const MonomerSet &ms) override
     {
-        SD_CUDA(cudaSetDevice(dev_));
+        DeviceScope scope_(dev_); SD_CUDA(scope_.status);
         plan_ = p; ms_ = ms;
         const Geometry &g = p.g;
         const int spw = 32 / g.T;
@@ -326,7 +327,7 @@ public:
 
     void stage(const Batch &b, int s0, int s1) override
     {
-        SD_CUDA(cudaSetDevice(dev_));
+        DeviceScope scope_(dev_); SD_CUDA(scope_.status);
         const Geometry &g = plan_.g;
         s0_ = s0; s1_ = s1; nseg_ = s1 - s0;
         lay_ = make_cta_layout(plan_, b, s0, s1);
@@ -441,7 +442,7 @@ public:
 
     void execute() override
     {
-        SD_CUDA(cudaSetDevice(dev_));
+        DeviceScope scope_(dev_); SD_CUDA(scope_.status);
         const Geometry &g = plan_.g;
         const int seg_stride = (nmax_ + 16) / 16 * 16;
         SD_CUDA(cudaEventRecord(ev_[0], st_));
@@ -477,7 +478,7 @@ public:
 
     void fetch(BatchResult &out) override
     {
-        SD_CUDA(cudaSetDevice(dev_));
+        DeviceScope scope_(dev_); SD_CUDA(scope_.status);
         hcnt_.resize((size_t)nseg_);
         SD_CUDA(cudaEventRecord(ev_[0], st_));
         SD_CUDA(cudaMemcpyAsync(hcnt_.data(), d_counts_.p, (size_t)nseg_ * 4, cudaMemcpyDeviceToHost, st_));
@@ -546,7 +547,7 @@ int cuda_int_peak(int device, double *alu, double *both, double *mhz, std::strin
 {
     using namespace sdb;
     try {
-        SD_CUDA(cudaSetDevice(device));
+        DeviceScope scope_(device); SD_CUDA(scope_.status);
         cudaDeviceProp p; SD_CUDA(cudaGetDeviceProperties(&p, device));
         const int nblk = p.multiProcessorCount * 2, nthr = 512;
         unsigned *d; SD_CUDA(cudaMalloc(&d, (size_t)nblk * nthr * 4));
