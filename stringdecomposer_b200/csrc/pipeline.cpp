@@ -224,10 +224,18 @@ void Engine::stage(const Batch &b)
         if (devs_[d]->wave_bytes(staged_, staged_bounds_[d], staged_bounds_[d + 1]) > devs_[d]->wave_budget())
             throw PlanError{"staged batch does not fit one wave on the device"};
     }
-    auto work = [&](int d) { if (staged_bounds_[d] < staged_bounds_[d + 1]) devs_[d]->stage(staged_, staged_bounds_[d], staged_bounds_[d + 1]); };
-    std::vector<std::thread> th;
-    for (int d = 0; d < ndev(); ++d) th.emplace_back(work, d);
-    for (auto &t : th) t.join();
+    std::vector<std::string> errs(ndev());
+    auto work = [&](int d) {
+        try { if (staged_bounds_[d] < staged_bounds_[d + 1]) devs_[d]->stage(staged_, staged_bounds_[d], staged_bounds_[d + 1]); }
+        catch (PlanError &e) { errs[d] = e.msg.empty() ? "error" : e.msg; }
+    };
+    if (ndev() == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int d = 0; d < ndev(); ++d) th.emplace_back(work, d);
+        for (auto &t : th) t.join();
+    }
+    for (auto &e : errs) if (!e.empty()) throw PlanError{e};
 }
 
 double Engine::run_staged()
@@ -240,9 +248,12 @@ double Engine::run_staged()
             if (staged_bounds_[d] < staged_bounds_[d + 1]) devs_[d]->execute();
         } catch (PlanError &e) { errs[d] = e.msg; }
     };
-    std::vector<std::thread> th;
-    for (int d = 0; d < ndev(); ++d) th.emplace_back(work, d);
-    for (auto &t : th) t.join();
+    if (ndev() == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int d = 0; d < ndev(); ++d) th.emplace_back(work, d);
+        for (auto &t : th) t.join();
+    }
     for (auto &e : errs) if (!e.empty()) throw PlanError{e};
     double ms = 0, sw = 0, tb = 0;
     for (auto &d : devs_) { ms = std::max(ms, d->sweep_ms + d->traceback_ms); sw = std::max(sw, d->sweep_ms); tb = std::max(tb, d->traceback_ms); stats.launches += d->launches; }
