@@ -145,6 +145,21 @@ def test_config2_full_size_properties_and_sampled_parity():
     d.close()
 
 
+@pytest.mark.skipif(not os.path.exists(cases.DP_REF), reason="the compiled reference binary (oracle/_ref/dp) is not here")
+def test_config2_full_output_identical_to_the_reference_binary(tmp_path):
+    # BASELINE config 2 in full through both binaries: the unmodified reference needs ~4 s on 16 cores for it
+    rn, reads, mn, mons = synth.config2()
+    rp, mp = str(tmp_path / "reads.fa"), str(tmp_path / "monomers.fa")
+    synth.write_fasta(rp, rn, reads, width=80)
+    synth.write_fasta(mp, mn, mons)
+    tail = [str(os.cpu_count() or 1), "5000", "500"]
+    ours = subprocess.run([cases.DP_CUDA, rp, mp] + tail, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    ref = subprocess.run([cases.DP_REF, rp, mp] + tail, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert ours.returncode == 0 and ref.returncode == 0
+    assert ours.stdout == ref.stdout and ours.stdout.count(b"\n") > 11000
+    assert [ln for ln in ours.stderr.splitlines() if not ln.startswith(b"[sd_b200]")] == ref.stderr.splitlines()
+
+
 def test_config4_custom_scoring_sample():
     rn, reads, mn, mons = synth.config4(n_reads=6, read_len=15000)
     sc = (-2, -2, -3, 1)
