@@ -327,7 +327,7 @@ def main():
                 "gpu_launches": int(st["launches"]), "clocks": clocks, "roofline": roof}
         if ws == 1:
             line["rescoring"] = rescoring(segs, mons, recs, roff, local, alu)
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and ws == 1:          # reported at N=1 only
             line["cpu_baseline"] = cpu_baseline(reads, rnames, mnames, mons)
         print(json.dumps(line))
     if ws > 1:
