@@ -178,6 +178,31 @@ def test_convert_min_identity_duplicates_and_chunking(tmp_path, monkeypatch):
             assert fo.getvalue() == fin and fa.getvalue() == alt
 
 
+def test_convert_edge_cases_follow_the_reference(tmp_path):
+    mons = [("m1", "ACGTACGTTACG"), ("m2", "TTGACCAGTAGC")]
+    rc = cv.add_rc_monomers(mons)
+    reads = {"r1": "ACGTACGTTACGTTGACCAGTAGCACGT", "r2": "GCTACTGGTCAA"}
+    out = str(tmp_path / "o.tsv")
+    cv.convert_tsv("", reads, rc, out, 0, True, flavour=cases.EMU_LIB)                      # no raw lines at all
+    assert open(out).read() == "" and open(out[:-4] + "_alt.tsv").read() == ""
+    # columns 1 and 2 are cut at the first blank (main.py:175-176); the last three columns of the raw file are unused
+    raw = "r1 tail words\tm1 x\t0\t11\t9.0\t0\t11\nr1\tm2\t12\t23\t9.0\t0\t11\nr2\tm2'\t0\t11\t1.0\t0\t11\nr1\tm1\t24\t27\t1.0\t0\t3\n"
+    for light in (True, False):
+        cv.convert_tsv(raw, reads, rc, out, 0, light, flavour=cases.EMU_LIB)
+        fin, alt = CO.final_tsv(raw, reads, mons, 0, light)
+        assert open(out).read() == fin and open(out[:-4] + "_alt.tsv").read() == alt
+        assert fin.splitlines()[0].startswith("r1\tm1\t0\t11\t100.00\t") and fin.splitlines()[2].startswith("r2\tm2'\t0\t11\t100.00\t")
+    with pytest.raises(KeyError):                                                            # reads[prev_read], main.py:178
+        cv.convert_tsv("nope\tm1\t0\t3\t1\t0\t3\n", reads, rc, out, 0, True, flavour=cases.EMU_LIB)
+    with pytest.raises(KeyError):                                                            # scores[monomer], main.py:117
+        cv.convert_tsv("r1\tother\t0\t3\t1\t0\t3\n", reads, rc, out, 0, True, flavour=cases.EMU_LIB)
+    # an interval that runs past the end of the read is cut by the slice (main.py:115), an empty one scores 0
+    raw = "r2\tm1\t8\t40\t1\t0\t3\nr2\tm1\t30\t40\t1\t0\t3\n"
+    cv.convert_tsv(raw, reads, rc, out, 0, True, flavour=cases.EMU_LIB)
+    assert open(out).read() == CO.final_tsv(raw, reads, mons, 0, True)[0]
+    assert open(out).read().splitlines()[1].split("\t")[4] == "0.00"
+
+
 def test_helpers_follow_the_reference():
     assert cv.convert_to_homo("AAACCGTTTA") == "ACGTA" and cv.convert_to_homo("") == ""
     assert cv.add_rc_monomers([("x", "AACGN")]) == [("x", "AACGN"), ("x'", "NCGTT")]
