@@ -113,6 +113,27 @@ int sd_identity(const char *queries, const int64_t *query_offsets, int64_t n_que
                 int32_t *matches, int32_t *columns, int32_t *distance,
                 int32_t device, int64_t *hirschberg_pairs, double *kernel_ms);
 
+/* Replaces convert_tsv / print_read / convert_read / classify (stringdecomposer/main.py:96-184): turns the raw `dp`
+ * text into the final TSV (12 columns, main.py:158-162) on out_fd and, with light == 0 (--second-best), the per-monomer
+ * `_alt` lines (main.py:163-166) on alt_fd.  All alignments of a chunk of lines go through sd_identity on `device`.
+ *   raw, raw_len          the text `dp` wrote; as in the reference only its first four columns are read, names are cut
+ *                         at the first blank and only newline-terminated lines count (main.py:173-176)
+ *   read_names/reads      ids and (upper-case) sequences of the reads, concatenated + n_reads+1 offsets each
+ *   mono_names/monos      the monomers in add_rc_monomers() order (main.py:80-85: each followed by its reverse
+ *                         complement, named with a trailing quote), concatenated + n_monomers+1 offsets each
+ *   min_identity          lines with identity below it are dropped (main.py:157)
+ * Returns SD_OK or an SD_ERR_* code (sd_convert_error() has the text; a read or monomer of the raw text that is not in
+ * the inputs -- a KeyError in the reference -- is SD_ERR_ARG).  Byte-identical to the Python mirror convert.convert_tsv. */
+typedef struct sd_convert_stats {
+    int64_t lines_in, lines_out, pairs, hirschberg_pairs;
+    double kernel_ms;
+} sd_convert_stats;
+int sd_convert(const char *raw, int64_t raw_len,
+               const char *read_names, const int64_t *read_name_off, const char *reads, const int64_t *read_off, int64_t n_reads,
+               const char *mono_names, const int64_t *mono_name_off, const char *monos, const int64_t *mono_off, int32_t n_monomers,
+               int32_t min_identity, int32_t light, int32_t device, int out_fd, int alt_fd, sd_convert_stats *stats);
+const char *sd_convert_error(void);
+
 int sd_get_stats(sd_handle *h, sd_stats *out);
 void sd_reset_stats(sd_handle *h);
 const char *sd_last_error(sd_handle *h);       /* h may be NULL: error of the last failed sd_create/sd_run_files */

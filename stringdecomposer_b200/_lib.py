@@ -23,9 +23,15 @@ class _Stats(C.Structure):
 
 
 # every symbol include/sd_b200.h declares (tests/test_abi.py checks the header against this list)
+class _ConvertStats(C.Structure):
+    _fields_ = [("lines_in", C.c_int64), ("lines_out", C.c_int64), ("pairs", C.c_int64), ("hirschberg_pairs", C.c_int64),
+                ("kernel_ms", C.c_double)]
+
+
 SYMBOLS = ["sd_create", "sd_decompose", "sd_stage", "sd_run_staged", "sd_fetch_staged", "sd_segment_read",
            "sd_postprocess", "sd_run_files", "sd_set_ed_thr", "sd_hw_distance", "sd_get_stats", "sd_reset_stats", "sd_last_error", "sd_free",
-           "sd_destroy", "sd_device_count", "sd_version", "sd_int_peak", "sd_identity"]
+           "sd_destroy", "sd_device_count", "sd_version", "sd_int_peak", "sd_identity", "sd_convert",
+           "sd_convert_error"]
 
 _libs = {}
 
@@ -87,6 +93,10 @@ def load_library(flavour="cuda"):
     lib.sd_identity.argtypes = [C.c_char_p, i64p, C.c_int64, C.c_char_p, i64p, C.c_int64, i32p, i32p, C.c_int64,
                                 i32p, i32p, i32p, C.c_int32, i64p, C.POINTER(C.c_double)]
     lib.sd_identity.restype = C.c_int
+    lib.sd_convert.argtypes = [C.c_char_p, C.c_int64, C.c_char_p, i64p, C.c_char_p, i64p, C.c_int64, C.c_char_p, i64p, C.c_char_p,
+                               i64p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int, C.c_int, C.POINTER(_ConvertStats)]
+    lib.sd_convert.restype = C.c_int
+    lib.sd_convert_error.restype = C.c_char_p
     _libs[flavour] = lib
     return lib
 
@@ -275,3 +285,25 @@ def nw_identity(queries, targets, pairs=None, device=0, flavour="cuda"):
     if st:
         raise SdError(st, (lib.sd_last_error(None) or b"").decode())
     return {"matches": m, "columns": c, "distance": d, "kernel_ms": ms.value, "hirschberg_pairs": hb.value}
+
+
+def convert_raw(raw, reads, monomers, out_fd, alt_fd, min_identity=0, light=True, device=0, flavour="cuda"):
+    """sd_convert: raw `dp` text -> final TSV on out_fd (and the `_alt` lines on alt_fd with light=False).
+    reads: {id: sequence}; monomers: [(name, sequence)] in add_rc_monomers() order.  Returns the stage's counters."""
+    lib = load_library(flavour)
+    rb = raw.encode() if isinstance(raw, str) else bytes(raw)
+    rn, rno = _pack(list(reads.keys()))
+    rs, rso = _pack(list(reads.values()))
+    mn, mno = _pack([m[0] for m in monomers])
+    ms, mso = _pack([m[1] for m in monomers])
+    i64p = C.POINTER(C.c_int64)
+    st = _ConvertStats()
+    rc = lib.sd_convert(rb, len(rb), rn, rno.ctypes.data_as(i64p), rs, rso.ctypes.data_as(i64p), len(reads),
+                        mn, mno.ctypes.data_as(i64p), ms, mso.ctypes.data_as(i64p), len(monomers),
+                        int(min_identity), 1 if light else 0, device, out_fd, alt_fd, C.byref(st))
+    if rc:
+        msg = (lib.sd_convert_error() or b"").decode()
+        if msg.startswith("KeyError"):
+            raise KeyError(msg)
+        raise SdError(rc, msg)
+    return {k: getattr(st, k) for k, _ in _ConvertStats._fields_}

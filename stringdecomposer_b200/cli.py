@@ -19,7 +19,7 @@ import sys
 import time
 
 from . import _lib
-from .convert import load_fasta, add_rc_monomers, convert_tsv
+from .convert import load_fasta, add_rc_monomers, convert_tsv_native
 
 
 def get_logger(filename, logger_name="StringDecomposer"):
@@ -89,8 +89,8 @@ def main(argv=None, flavour="cuda"):
     logger.info("Transforming raw alignments...")
     out_fn = os.path.join(args.out_dir, args.out_file + ".tsv")
     stats = {}
-    convert_tsv(raw, reads, monomers, out_fn, int(args.min_identity), not args.second_best, device=args.device,
-                flavour=flavour, stats=stats)
+    convert_tsv_native(raw, reads, monomers, out_fn, int(args.min_identity), not args.second_best, device=args.device,
+                       flavour=flavour, stats=stats)
     t2 = time.time()
     if stats.get("hirschberg_pairs"):
         logger.info("NOTE: %d interval/monomer pairs are large enough for edlib to leave its traceback for Hirschberg "

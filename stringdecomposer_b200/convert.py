@@ -9,7 +9,7 @@ the identity call raises.
 """
 import numpy as np
 
-from ._lib import nw_identity, SdError
+from ._lib import nw_identity, convert_raw, SdError
 
 # stringdecomposer/models/ont_logreg_model.txt as read at main.py:22-26: intercept, identity, identity - second best
 LR_MODEL_COEF = [-31.48494996, 0.41784018, 0.69186882]
@@ -283,5 +283,18 @@ def convert_tsv(decomposition, reads, monomers, outfile, identity_th, light, dev
                          identity_th, light)
 
 
+def convert_tsv_native(decomposition, reads, monomers, outfile, identity_th, light, device=0, flavour="cuda", stats=None):
+    """convert_tsv() through the library's sd_convert (csrc/convert.cpp): same two files, byte for byte, without the
+    per-line Python work -- the path the command line takes."""
+    with open(outfile[:-len(".tsv")] + "_alt.tsv", "w") as fout_alt, open(outfile, "w") as fout:
+        fout.flush(); fout_alt.flush()
+        st = convert_raw(decomposition, reads, monomers, fout.fileno(), fout_alt.fileno(), identity_th, light,
+                         device=device, flavour=flavour)
+    if stats is not None:
+        for k in ("pairs", "kernel_ms", "hirschberg_pairs"):
+            stats[k] = stats.get(k, 0) + st[k]
+    return st
+
+
 __all__ = ["LR_MODEL_COEF", "load_fasta", "add_rc_monomers", "convert_to_homo", "aai", "classify", "convert_read",
-           "print_read", "convert_tsv", "SdError"]
+           "print_read", "convert_tsv", "convert_tsv_native", "SdError"]

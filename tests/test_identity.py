@@ -203,6 +203,53 @@ def test_convert_edge_cases_follow_the_reference(tmp_path):
     assert open(out).read().splitlines()[1].split("\t")[4] == "0.00"
 
 
+@pytest.mark.parametrize("light", [False, True])
+def test_native_convert_equals_python_mirror_and_golden(tmp_path, light):
+    reads, mons, raw = _golden_inputs()
+    out = str(tmp_path / "n.tsv")
+    st = cv.convert_tsv_native(raw, cv.load_fasta(os.path.join(G, "config1_read.fa"), "map"),
+                               cv.add_rc_monomers(cv.load_fasta(os.path.join(G, "DXZ1_star_monomers.fa"))), out, 0, light,
+                               flavour=cases.EMU_LIB)
+    fin, alt = CO.final_tsv(raw, reads, mons, 0, light)
+    assert open(out).read() == fin and open(out[:-4] + "_alt.tsv").read() == alt
+    assert st["lines_in"] == 557 and st["lines_out"] == 557 and st["pairs"] == (557 if light else 557 * 48)
+    if not light:
+        assert fin == open(os.path.join(G, "config1_final_decomposition.tsv")).read()
+
+
+def test_native_convert_edge_cases(tmp_path):
+    r = random.Random(12)
+    mons = [("m1", rnd_seq(r, 60)), ("m2", rnd_seq(r, 70) + "*"), ("m1", rnd_seq(r, 65)), ("m3", "AAAAAACCCCCCGGGGGTTTT")]
+    rc = cv.add_rc_monomers(mons)
+    read = "".join(noisy(r, mons[r.randrange(3)][1].rstrip("*"), 0.1) for _ in range(12)) + "*"
+    reads = {"rd": read, "other": "ACGTTTGACA"}
+    raw = []
+    pos = 0
+    for k in range(12):
+        raw.append("rd extra words\t%s more\t%d\t%d\t1.0\t0\t0\n" % (r.choice(["m1", "m2", "m1'", "m3'"]), pos, pos + 59))
+        pos += 60
+    raw += ["other\tm3\t2\t400\t1\t0\t0\n", "other\tm2\t50\t60\t1\t0\t0\n", "rd\tm1\t%d\t%d\t1\t0\t0\n" % (len(read) - 20, len(read) - 1),
+            "rd\tm2\t0\t10\ttrailing line without newline"]
+    raw = "".join(raw)
+    for light in (True, False):
+        for thr in (0, 55, 101):
+            a, b = str(tmp_path / "p.tsv"), str(tmp_path / "n.tsv")
+            cv.convert_tsv(raw, reads, rc, a, thr, light, flavour=cases.EMU_LIB)
+            st = cv.convert_tsv_native(raw, reads, rc, b, thr, light, flavour=cases.EMU_LIB)
+            assert open(a).read() == open(b).read() and open(a[:-4] + "_alt.tsv").read() == open(b[:-4] + "_alt.tsv").read()
+            assert st["lines_in"] == 15 and open(b).read() == CO.final_tsv(raw, reads, mons, thr, light)[0]
+    out = str(tmp_path / "e.tsv")
+    assert cv.convert_tsv_native("", reads, rc, out, 0, True, flavour=cases.EMU_LIB)["lines_in"] == 0 and open(out).read() == ""
+    with pytest.raises(KeyError):
+        cv.convert_tsv_native("nope\tm1\t0\t3\t1\t0\t3\n", reads, rc, out, 0, True, flavour=cases.EMU_LIB)
+    with pytest.raises(KeyError):
+        cv.convert_tsv_native("rd\tnope\t0\t3\t1\t0\t3\n", reads, rc, out, 0, False, flavour=cases.EMU_LIB)
+    with pytest.raises(sd.SdError):
+        cv.convert_tsv_native("rd\tm1\t0\n", reads, rc, out, 0, True, flavour=cases.EMU_LIB)
+    with pytest.raises(sd.SdError):
+        cv.convert_tsv_native("rd\tm1\tx\t3\t1\n", reads, rc, out, 0, True, flavour=cases.EMU_LIB)
+
+
 def test_helpers_follow_the_reference():
     assert cv.convert_to_homo("AAACCGTTTA") == "ACGTA" and cv.convert_to_homo("") == ""
     assert cv.add_rc_monomers([("x", "AACGN")]) == [("x", "AACGN"), ("x'", "NCGTT")]
@@ -270,6 +317,20 @@ def test_gpu_final_tsv_equals_reference_golden_file(tmp_path, light):
     if not light:
         assert fin == open(os.path.join(G, "config1_final_decomposition.tsv")).read()      # the reference's own file
     assert stats["kernel_ms"] > 0 and stats["hirschberg_pairs"] == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("light", [False, True])
+def test_gpu_native_convert_equals_reference_golden_file(tmp_path, light):
+    reads, mons, raw = _golden_inputs()
+    out = str(tmp_path / "n.tsv")
+    st = cv.convert_tsv_native(raw, cv.load_fasta(os.path.join(G, "config1_read.fa"), "map"),
+                               cv.add_rc_monomers(cv.load_fasta(os.path.join(G, "DXZ1_star_monomers.fa"))), out, 0, light)
+    fin, alt = CO.final_tsv(raw, reads, mons, 0, light)
+    assert open(out).read() == fin and open(out[:-4] + "_alt.tsv").read() == alt
+    if not light:
+        assert fin == open(os.path.join(G, "config1_final_decomposition.tsv")).read()      # the reference's own file
+    assert st["kernel_ms"] > 0 and st["lines_out"] == 557
 
 
 @pytest.mark.gpu
