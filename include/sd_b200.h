@@ -105,7 +105,7 @@ int32_t sd_hw_distance(const char *query, int32_t query_len, const char *target,
  *                       matches = columns = 0, distance = -1 (main.py:30-33 -> identity 0)
  *   hirschberg_pairs    optional: number of pairs so large that edlib would leave its traceback for Hirschberg
  *                       splitting (edlib.cpp:1187-1191) and might report another optimal path; they are still
- *                       computed with the traceback rule.  Lengths above 16383 are refused (SD_ERR_UNSUPPORTED).
+ *                       computed with the traceback rule.  Lengths above 16382 are refused (SD_ERR_UNSUPPORTED).
  *   kernel_ms           optional: device time of the kernel */
 int sd_identity(const char *queries, const int64_t *query_offsets, int64_t n_queries,
                 const char *targets, const int64_t *target_offsets, int64_t n_targets,

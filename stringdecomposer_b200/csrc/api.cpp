@@ -234,13 +234,13 @@ int sd_identity(const char *queries, const int64_t *qoff, int64_t nq, const char
     for (int64_t i = 0; i < nq; ++i) {
         const int64_t l = qoff[i + 1] - qoff[i];
         if (l < 0) return fail(SD_ERR_ARG, "sd_identity: query offsets must not decrease");
-        if (l > SD_NW_MAXLEN) return fail(SD_ERR_UNSUPPORTED, "sd_identity: sequence longer than 16383");
+        if (l > SD_NW_MAXLEN) return fail(SD_ERR_UNSUPPORTED, "sd_identity: sequence longer than 16382");
         max_q = std::max<int>(max_q, (int)l);
     }
     for (int64_t i = 0; i < nt; ++i) {
         const int64_t l = toff[i + 1] - toff[i];
         if (l < 0) return fail(SD_ERR_ARG, "sd_identity: target offsets must not decrease");
-        if (l > SD_NW_MAXLEN) return fail(SD_ERR_UNSUPPORTED, "sd_identity: sequence longer than 16383");
+        if (l > SD_NW_MAXLEN) return fail(SD_ERR_UNSUPPORTED, "sd_identity: sequence longer than 16382");
         max_t = std::max<int>(max_t, (int)l);
     }
     if ((qoff[nq] > qoff[0] && !queries) || (toff[nt] > toff[0] && !targets) || qoff[0] != 0 || toff[0] != 0) return fail(SD_ERR_ARG, "sd_identity: bad text buffers");

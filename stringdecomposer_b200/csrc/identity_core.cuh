@@ -21,7 +21,7 @@
 
 namespace sdb {
 
-constexpr int SD_NW_MAXLEN = 16383;                 // D < 2^14 and M < 2^16
+constexpr int SD_NW_MAXLEN = 16382;                 // every candidate D + 1 <= max(len) + 1 must fit 14 bits; M < 2^16
 constexpr uint32_t NW_DSHIFT = 18;
 constexpr uint32_t NW_K_UP = 1u << 18;                              // +1, priority 0
 constexpr uint32_t NW_K_LEFT = (1u << 18) | (1u << 16);             // +1, priority 1

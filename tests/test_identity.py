@@ -128,12 +128,19 @@ def test_emulated_kernel_all_against_all_and_pair_list(maxlen):
 
 def test_identity_argument_errors():
     with pytest.raises(sd.SdError) as e:
-        sd.nw_identity(["A" * 16384], ["A"], flavour=cases.EMU_LIB)
+        sd.nw_identity(["A" * 16383], ["A"], flavour=cases.EMU_LIB)
     assert e.value.status == 3
     with pytest.raises(sd.SdError):
         sd.nw_identity(["A"], ["A"], pairs=([0], [1]), flavour=cases.EMU_LIB)
     res = sd.nw_identity([], ["A"], flavour=cases.EMU_LIB)
     assert len(res["matches"]) == 0
+    # long sequences: all mismatches, a pure length difference, a periodic pair
+    ext = sd.nw_identity(["A" * 8000, "A" * 8000, "ACGT" * 2000], ["C" * 8000, "A" * 7000, "ACGA" * 2000], pairs=([0, 1, 2], [0, 1, 2]),
+                         flavour=cases.EMU_LIB)
+    assert list(ext["distance"]) == [8000, 1000, 2000] and list(ext["matches"]) == [0, 7000, 6000]
+    assert list(ext["columns"]) == [8000, 8000, 8000]
+    edge = sd.nw_identity(["A" * 16382, "C" * 5], ["C" * 5, "A" * 16382], pairs=([0, 1], [0, 1]), flavour=cases.EMU_LIB)   # the longest
+    assert list(edge["distance"]) == [16382, 16382] and list(edge["columns"]) == [16382, 16382]
     big = sd.nw_identity(["A" * 2300], ["A" * 1536], flavour=cases.EMU_LIB)
     assert big["hirschberg_pairs"] == 1 and big["distance"][0] == 764
 
@@ -302,6 +309,16 @@ def test_gpu_identity_fuzz_against_oracle(maxlen):
     pq = [r.randrange(len(qs)) for _ in range(50)]
     pt = [r.randrange(len(ts)) for _ in range(50)]
     check_against_oracle(sd.nw_identity(qs, ts, pairs=(pq, pt)), qs, ts, (pq, pt))
+
+
+@pytest.mark.gpu
+def test_gpu_identity_longest_supported_sequences():
+    ext = sd.nw_identity(["A" * 16382, "A" * 16382, "ACGT" * 4000, "G"], ["C" * 16382, "A" * 15000, "ACGA" * 4000, "T" * 16382],
+                         pairs=([0, 1, 2, 3, 0], [0, 1, 2, 3, 3]))
+    assert list(ext["distance"]) == [16382, 1382, 4000, 16382, 16382] and list(ext["matches"]) == [0, 15000, 12000, 0, 0]
+    assert list(ext["columns"]) == [16382, 16382, 16000, 16382, 16382]
+    with pytest.raises(sd.SdError):
+        sd.nw_identity(["A" * 16383], ["A"])
 
 
 @pytest.mark.gpu
