@@ -1,5 +1,5 @@
 import os, sys, time
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from stringdecomposer_b200 import synth, Decomposer
 from stringdecomposer_b200.hostpipe import segment_reads
