@@ -64,3 +64,50 @@ def test_emulated_kernels_match_oracle(problem):
 @given(problems())
 def test_cuda_kernels_match_oracle(problem):
     run("cuda", problem)
+
+
+# ---- the rescoring stage: sd_identity / sd_convert against the oracle on random inputs ---------------------------------
+@st.composite
+def rescoring_problems(draw):
+    alphabet = draw(st.sampled_from(["A", "AC", "ACGT", "ACGTN"]))
+    monomers = draw(st.lists(seq(alphabet, 1, 60), min_size=1, max_size=4))
+    names = ["m%d" % i for i in range(len(monomers))]
+    if draw(st.booleans()) and len(names) > 1:
+        names[-1] = names[0]                              # repeated name: the `scores` dict of main.py:123 collapses it
+    reads = draw(st.lists(seq(alphabet, 1, 200), min_size=1, max_size=3))
+    lines = []
+    for _ in range(draw(st.integers(0, 8))):
+        r = draw(st.integers(0, len(reads) - 1))
+        a = draw(st.integers(0, len(reads[r]) + 3))
+        b = draw(st.integers(a - 1, a + 80))
+        m = draw(st.sampled_from(names)) + draw(st.sampled_from(["", "'"]))
+        lines.append("r%d\t%s\t%d\t%d\t1.0\t0\t0\n" % (r, m, a, b))
+    return list(zip(names, monomers)), {"r%d" % i: s for i, s in enumerate(reads)}, "".join(lines), \
+        draw(st.sampled_from([0, 50, 100])), draw(st.booleans())
+
+
+def run_rescoring(flavour, problem, tmp):
+    import sd_convert_oracle as CO
+    from stringdecomposer_b200 import convert as cv
+    monomers, reads, raw, thr, light = problem
+    want, want_alt = CO.final_tsv(raw, reads, monomers, thr, light)
+    rc = cv.add_rc_monomers(monomers)
+    for fn in (cv.convert_tsv, cv.convert_tsv_native):
+        out = os.path.join(tmp, "o.tsv")
+        fn(raw, reads, rc, out, thr, light, flavour=flavour)
+        assert open(out).read() == want and open(out[:-4] + "_alt.tsv").read() == want_alt, (problem, fn.__name__)
+
+
+@settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large,
+                                                                 HealthCheck.function_scoped_fixture])
+@given(rescoring_problems())
+def test_emulated_rescoring_matches_oracle(tmp_path, problem):
+    run_rescoring(cases.EMU_LIB, problem, str(tmp_path))
+
+
+@pytest.mark.gpu
+@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large,
+                                                                 HealthCheck.function_scoped_fixture])
+@given(rescoring_problems())
+def test_cuda_rescoring_matches_oracle(tmp_path, problem):
+    run_rescoring("cuda", problem, str(tmp_path))
