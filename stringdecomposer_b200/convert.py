@@ -16,6 +16,7 @@ LR_MODEL_COEF = [-31.48494996, 0.41784018, 0.69186882]
 
 _COMPLEMENT = bytes.maketrans(b"ACGTNacgtn", b"TGCANtgcan")
 MAX_PAIRS_PER_CALL = 1 << 24
+MAX_LINES_PER_CALL = 1 << 21
 
 
 def load_fasta(filename, tp="list"):
@@ -263,7 +264,7 @@ def convert_tsv(decomposition, reads, monomers, outfile, identity_th, light, dev
     monomers: the add_rc_monomers() list.  Every raw line is rescored independently of the others (the reference's
     per-read grouping only selects the read to cut from), so lines of many reads share one device call."""
     per_line = 1 if light else 2 * max(1, len(monomers))
-    chunk = max(1, MAX_PAIRS_PER_CALL // per_line)
+    chunk = max(1, min(MAX_PAIRS_PER_CALL // per_line, MAX_LINES_PER_CALL))
     lines = decomposition.split("\n")[:-1]
     first_word = {}                   # `x.split()[0]` of main.py:175-176, once per distinct name instead of per line
     with open(outfile[:-len(".tsv")] + "_alt.tsv", "w") as fout_alt, open(outfile, "w") as fout:

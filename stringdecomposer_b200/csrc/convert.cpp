@@ -18,6 +18,7 @@ namespace {
 // stringdecomposer/models/ont_logreg_model.txt as read at main.py:22-26: intercept, identity, identity - second best
 const double kLogReg[3] = {-31.48494996, 0.41784018, 0.69186882};
 const int64_t kMaxPairsPerCall = int64_t(1) << 24;
+const int64_t kMaxLinesPerCall = int64_t(1) << 21;      // bounds the packed intervals of one call (~0.4 GB for 171-bp monomers)
 
 struct View { const char *p; size_t n; std::string str() const { return std::string(p, n); } };
 
@@ -186,7 +187,7 @@ extern "C" int sd_convert(const char *raw, int64_t raw_len,
 
     Writer out(out_fd), alt(alt_fd);
     const int64_t per_line = light ? 1 : 2 * (int64_t)std::max(1, nm);
-    const size_t chunk = (size_t)std::max<int64_t>(1, kMaxPairsPerCall / per_line);
+    const size_t chunk = (size_t)std::max<int64_t>(1, std::min<int64_t>(kMaxPairsPerCall / per_line, kMaxLinesPerCall));
     std::string qblob, qcblob; std::vector<int64_t> qoff, qcoff;
     std::vector<int32_t> pq, pt, mt, col, mt2, col2;
     for (size_t lo = 0; lo < lines.size(); lo += chunk) {
