@@ -5,6 +5,7 @@
 // All alignments go through sd_identity (identity_kernels.cu); nothing here computes an alignment on the host.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -187,7 +188,8 @@ extern "C" int sd_convert(const char *raw, int64_t raw_len,
 
     Writer out(out_fd), alt(alt_fd);
     const int64_t per_line = light ? 1 : 2 * (int64_t)std::max(1, nm);
-    const size_t chunk = (size_t)std::max<int64_t>(1, std::min<int64_t>(kMaxPairsPerCall / per_line, kMaxLinesPerCall));
+    size_t chunk = (size_t)std::max<int64_t>(1, std::min<int64_t>(kMaxPairsPerCall / per_line, kMaxLinesPerCall));
+    if (const char *e = getenv("SD_CONVERT_LINES")) if (atoll(e) > 0) chunk = (size_t)atoll(e);        // tests: several device calls
     std::string qblob, qcblob; std::vector<int64_t> qoff, qcoff;
     std::vector<int32_t> pq, pt, mt, col, mt2, col2;
     for (size_t lo = 0; lo < lines.size(); lo += chunk) {

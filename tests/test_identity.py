@@ -224,7 +224,7 @@ def test_native_convert_equals_python_mirror_and_golden(tmp_path, light):
         assert fin == open(os.path.join(G, "config1_final_decomposition.tsv")).read()
 
 
-def test_native_convert_edge_cases(tmp_path):
+def test_native_convert_edge_cases(tmp_path, monkeypatch):
     r = random.Random(12)
     mons = [("m1", rnd_seq(r, 60)), ("m2", rnd_seq(r, 70) + "*"), ("m1", rnd_seq(r, 65)), ("m3", "AAAAAACCCCCCGGGGGTTTT")]
     rc = cv.add_rc_monomers(mons)
@@ -245,6 +245,13 @@ def test_native_convert_edge_cases(tmp_path):
             st = cv.convert_tsv_native(raw, reads, rc, b, thr, light, flavour=cases.EMU_LIB)
             assert open(a).read() == open(b).read() and open(a[:-4] + "_alt.tsv").read() == open(b[:-4] + "_alt.tsv").read()
             assert st["lines_in"] == 15 and open(b).read() == CO.final_tsv(raw, reads, mons, thr, light)[0]
+    monkeypatch.setenv("SD_CONVERT_LINES", "4")                                  # four device calls instead of one
+    for light in (True, False):
+        a, b = str(tmp_path / "p.tsv"), str(tmp_path / "n.tsv")
+        cv.convert_tsv(raw, reads, rc, a, 0, light, flavour=cases.EMU_LIB)
+        cv.convert_tsv_native(raw, reads, rc, b, 0, light, flavour=cases.EMU_LIB)
+        assert open(a).read() == open(b).read() and open(a[:-4] + "_alt.tsv").read() == open(b[:-4] + "_alt.tsv").read()
+    monkeypatch.delenv("SD_CONVERT_LINES")
     out = str(tmp_path / "e.tsv")
     assert cv.convert_tsv_native("", reads, rc, out, 0, True, flavour=cases.EMU_LIB)["lines_in"] == 0 and open(out).read() == ""
     with pytest.raises(KeyError):
