@@ -3,8 +3,8 @@
  *
  * The reference (ablab/stringdecomposer v1.1.2) has no FFI: its boundary is the process CLI of the `dp`
  * binary that stringdecomposer/main.py:194 spawns.  The entry points below are what a binding for that
- * path would need; each cites the reference code it replaces (paths relative to
- * stringdecomposer/src/main.cpp).  Plain C types only, caller-owned inputs, library-owned outputs that
+ * path would need; each cites the reference code it replaces (main.cpp = stringdecomposer/src/main.cpp,
+ * main.py = stringdecomposer/main.py, edlib.cpp = stringdecomposer/src/edlib.cpp).  Plain C types only, caller-owned inputs, library-owned outputs that
  * are released with sd_free(), integer status codes (0 = ok), no exceptions cross the boundary.
  * A handle may be used from one host thread at a time.  There is no CPU fallback: sd_create() fails
  * with SD_ERR_NO_DEVICE when no CUDA device is usable.
@@ -23,7 +23,7 @@ enum {
     SD_ERR_ARG = 1,          /* bad argument (NULL, negative size, symbol outside ACGTN, ...) */
     SD_ERR_NO_DEVICE = 2,    /* no usable CUDA device / CUDA runtime error at start-up */
     SD_ERR_UNSUPPORTED = 3,  /* outside the supported domain (monomer set too large for this build, scores reaching
-                                the reference's INF sentinel, ed_thr pre-filter) */
+                                the reference's INF sentinel, a sequence too long for sd_identity) */
     SD_ERR_CUDA = 4,         /* CUDA failure while running */
     SD_ERR_INTERNAL = 5,
     SD_ERR_INPUT = 255       /* illegal FASTA symbol: the reference exits with status 255 (main.cpp:333-336) */
