@@ -338,20 +338,24 @@ public:
         const size_t nb = (size_t)(b.off[s1] - base);
         hoff_.resize((size_t)nseg_ + 1);
         for (int s = 0; s <= nseg_; ++s) hoff_[s] = b.off[s0 + s] - base;
-        d_bases_.need(nb + 16); d_segoff_.need(hoff_.size() * 8);
-        d_ctanmax_.need(lay_.cta_nmax.size() * 4); d_ctacode_.need(lay_.cta_code_off.size() * 8);
-        d_segj_.need(lay_.seg_j_off.size() * 8); d_segrec_.need(lay_.seg_rec_off.size() * 8);
+        d_bases_.need(nb + 16);
+        // the five small per-wave tables travel as one block: one pageable copy instead of five
+        const size_t msz[5] = {hoff_.size() * 8, lay_.cta_nmax.size() * 4, lay_.cta_code_off.size() * 8, lay_.seg_j_off.size() * 8,
+                               lay_.seg_rec_off.size() * 8};
+        const void *msrc[5] = {hoff_.data(), lay_.cta_nmax.data(), lay_.cta_code_off.data(), lay_.seg_j_off.data(), lay_.seg_rec_off.data()};
+        MetaView *mdst[5] = {&d_segoff_, &d_ctanmax_, &d_ctacode_, &d_segj_, &d_segrec_};
+        size_t mtotal = 0, moff[5];
+        for (int x = 0; x < 5; ++x) { moff[x] = mtotal; mtotal += (msz[x] + 255) & ~size_t(255); }
+        d_meta_.need(mtotal + 16);
+        hmeta_.resize(mtotal);
+        for (int x = 0; x < 5; ++x) { memcpy(hmeta_.data() + moff[x], msrc[x], msz[x]); mdst[x]->p = d_meta_.as<char>() + moff[x]; }
         d_codes_.need((size_t)lay_.cta_code_off.back() * 4 + 16);
         d_jr_.need((size_t)lay_.seg_j_off.back() * sizeof(JR) + 16);
         d_scratch_.need((size_t)lay_.seg_rec_off.back() * sizeof(Record) + 16);
         d_counts_.need((size_t)nseg_ * 4 + 16); d_outoff_.need(((size_t)nseg_ + 1) * 8);
         SD_CUDA(cudaEventRecord(ev_[0], st_));
         SD_CUDA(cudaMemcpyAsync(d_bases_.p, b.text + base, nb, cudaMemcpyHostToDevice, st_));
-        SD_CUDA(cudaMemcpyAsync(d_segoff_.p, hoff_.data(), hoff_.size() * 8, cudaMemcpyHostToDevice, st_));
-        SD_CUDA(cudaMemcpyAsync(d_ctanmax_.p, lay_.cta_nmax.data(), lay_.cta_nmax.size() * 4, cudaMemcpyHostToDevice, st_));
-        SD_CUDA(cudaMemcpyAsync(d_ctacode_.p, lay_.cta_code_off.data(), lay_.cta_code_off.size() * 8, cudaMemcpyHostToDevice, st_));
-        SD_CUDA(cudaMemcpyAsync(d_segj_.p, lay_.seg_j_off.data(), lay_.seg_j_off.size() * 8, cudaMemcpyHostToDevice, st_));
-        SD_CUDA(cudaMemcpyAsync(d_segrec_.p, lay_.seg_rec_off.data(), lay_.seg_rec_off.size() * 8, cudaMemcpyHostToDevice, st_));
+        SD_CUDA(cudaMemcpyAsync(d_meta_.p, hmeta_.data(), mtotal, cudaMemcpyHostToDevice, st_));
         SD_CUDA(cudaEventRecord(ev_[1], st_));
         SD_CUDA(cudaStreamSynchronize(st_));
         float ms = 0; SD_CUDA(cudaEventElapsedTime(&ms, ev_[0], ev_[1]));
@@ -522,7 +526,10 @@ private:
     bool filter_on_ = false;
     int64_t budget_ = 0;
     DevBuf d_prof_, d_slotlen_, d_slotend_, d_rows_, d_rowoff_;
-    DevBuf d_bases_, d_segoff_, d_ctanmax_, d_ctacode_, d_segj_, d_segrec_;
+    struct MetaView { void *p = nullptr; template <class U> U *as() { return reinterpret_cast<U *>(p); } };
+    DevBuf d_bases_, d_meta_;
+    MetaView d_segoff_, d_ctanmax_, d_ctacode_, d_segj_, d_segrec_;     // slices of d_meta_
+    std::vector<char> hmeta_;
     DevBuf d_flag_, d_xchg_, d_dist_, d_rank_, d_r2r_, d_codes_, d_jr_, d_scratch_, d_counts_, d_outoff_, d_dense_;
 };
 
