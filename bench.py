@@ -5,8 +5,10 @@ One "step" = one pass of the hot path (forward sweep + traceback kernels) over o
 cenX-like DXZ1 HOR array cut into 400 segments (part 5000, overlap 500) against the 12 DXZ1 monomers and their
 reverse complements.  `value` is measured with the segments already resident in HBM (CUDA events on the library's
 stream); `e2e` goes through the public C ABI (sd_decompose) with host buffers, H2D and D2H inside the timed region.
-N > 1: one process per GPU (torchrun), every rank decomposes its own 2 Mb array (weak scaling, no collective on the
-data path -- segments are independent); torch.distributed is used for the barrier and the max over ranks.
+N > 1 (north_star: strong scaling of ONE 2 Mb array): rank 0 of the torchrun launch drives all N GPUs through the
+library's own partitioning (Engine::split: contiguous segment ranges, one host thread + stream per GPU, records
+gathered on the host; no collective on the data path -- segments are independent); the other ranks only
+join the barriers.  The round-1 replica measurement (one array per GPU, one process per GPU) is kept under "replicas".
 
 --impl reference times the unmodified reference binary (oracle/_ref/dp, built from /root/reference by
 oracle/Makefile) on the same workload with -t <host cores>.
@@ -27,6 +29,7 @@ sys.path.insert(0, ROOT)
 
 PART, OVERLAP = 5000, 500
 SCORING = (-1, -1, -1, 1)
+WORKLOAD = "config2: synthetic 2 Mb cenX-like DXZ1 HOR array, 12 monomers (+RC), part 5000 overlap 500"
 METRIC = "dp_gcups"
 UNIT = "GCUPS"
 # ALU-pipe instructions the sweep needs per DP cell in the packed s16x2 kernel: per register
@@ -211,15 +214,57 @@ def run_reference_arm(args, ws, rank):
     cells = headline_cells(reads, mons) * len(times)
     val = cells / T / 1e9
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * T / len(times), "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * T / len(times), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-            "config": {"workload": "config2: synthetic 2 Mb cenX-like DXZ1 HOR array, 12 monomers (+RC), part 5000 overlap 500",
-                       "segments": 400, "scoring": "-1,-1,-1,1"},
+            "config": {"workload": WORKLOAD, "segments": 400, "scoring": "-1,-1,-1,1"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
                              "sample": "full config-2 contig (2,000,000 bp) per step, dp -t %d, wall time of the process" % cores},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "decomposed_mbp_per_s": sum(len(r) for r in reads) * len(times) / T / 1e6, "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def timed_resident(dec, packed, args, ws, flushes, sampler_gpu):
+    """`value` leg: segments resident in HBM, sweep + traceback kernels, CUDA events on the library's streams."""
+    import torch
+    dec.stage(packed)
+    for _ in range(args.warmup):
+        dec.run_staged()
+    sampler = ClockSampler(sampler_gpu)
+    barrier_sync(ws)
+    sampler.start()
+    dec.reset_stats()
+    dev_ms = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for f in flushes:
+            f.zero_()                         # 256 MiB > 126 MB L2, on every device that takes part
+        for d in range(len(flushes)):
+            torch.cuda.synchronize(flushes[d].device)
+        dev_ms += dec.run_staged()            # max over devices of (sweep + traceback), CUDA events per device
+    barrier_sync(ws)
+    wall = time.perf_counter() - t0
+    return dev_ms, wall, sampler.stop(), dec.stats()
+
+
+def timed_e2e(dec, packed, args, ws):
+    """`e2e` leg: host buffers through sd_decompose, H2D + kernels + D2H inside the timed region."""
+    for _ in range(args.warmup):
+        dec.decompose(packed)
+    dec.reset_stats()
+    barrier_sync(ws)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r2, o2 = dec.decompose(packed)
+    barrier_sync(ws)
+    return time.perf_counter() - t0, dec.stats(), r2, o2
+
+
+def pack_segments(segs):
+    blob = "".join(segs).encode()
+    off = np.zeros(len(segs) + 1, dtype=np.int64)
+    np.cumsum([len(s) for s in segs], out=off[1:])
+    return blob, off
 
 
 def main():
@@ -229,6 +274,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the rescoring / process / replica extras")
     ap.add_argument("--geom", default=None, help="override launch geometry C,T,NS (exploration)")
     args = ap.parse_args()
     if args.geom:
@@ -247,93 +293,108 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local)
-    rnames, reads, mnames, mons, segs = workload(rank)
-    blob = "".join(segs).encode()
-    off = np.zeros(len(segs) + 1, dtype=np.int64)
-    np.cumsum([len(s) for s in segs], out=off[1:])
-    packed = (blob, off)
-    dec = Decomposer(mons, *SCORING, devices=[local])
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
 
-    # ---- value: inputs resident in HBM, kernels only ------------------------------------------------
-    dec.stage(packed)
-    for _ in range(args.warmup):
-        dec.run_staged()
-    sampler = ClockSampler(local)
-    barrier_sync(ws)
-    sampler.start()
-    dec.reset_stats()
-    dev_ms = 0.0
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        flush.zero_()
-        torch.cuda.synchronize()
-        dev_ms += dec.run_staged()            # CUDA events around sweep + traceback on the library's stream
-    barrier_sync(ws)
-    wall = time.perf_counter() - t0
-    clocks = sampler.stop()
-    st = dec.stats()
-    dev_ms = max_over_ranks(dev_ms, ws)
-    recs, roff = dec.fetch_staged()
-    cells_hl = sum_over_ranks(float(headline_cells(reads, mons)), ws)
-    cells_act = sum_over_ranks(float(cells_of(segs, mons)), ws)
-    value = cells_hl * args.steps / (dev_ms * 1e-3) / 1e9
-    sweep_ms = st["sweep_ms"] / args.steps
-    tb_ms = st["traceback_ms"] / args.steps
-
-    # ---- e2e: host buffers through sd_decompose, H2D + D2H inside the timed region -----------------
-    for _ in range(args.warmup):
-        dec.decompose(packed)
-    dec.reset_stats()
-    barrier_sync(ws)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        r2, o2 = dec.decompose(packed)
-    barrier_sync(ws)
-    e2e_s = max_over_ranks(time.perf_counter() - t0, ws)
-    st2 = dec.stats()
-    e2e_val = cells_hl * args.steps / e2e_s / 1e9
-    same = bool(len(r2) == len(recs) and (r2 == recs).all() and (o2 == roff).all())
-
+    # ---- strong scaling (north_star): ONE 2 Mb array, its 400 segments split over the N GPUs of the box by the
+    # library (Engine::split, one host thread + stream per GPU, records gathered on the host in segment order --
+    # the AlignReadsSet gather of main.cpp:84-121).  Rank 0 drives all N devices; the other ranks of the torchrun
+    # launch only take part in the barriers.
+    rnames, reads, mnames, mons, segs = workload(0)
+    packed = pack_segments(segs)
+    cells_hl = float(headline_cells(reads, mons))
+    cells_act = float(cells_of(segs, mons))
+    line = None
     if rank == 0:
-        # ---- roofline of the dominant kernel (sweep): integer issue rate --------------------------------
+        dec = Decomposer(mons, *SCORING, devices=list(range(ws)))
+        flushes = [torch.empty(256 << 20, dtype=torch.uint8, device="cuda:%d" % d) for d in range(ws)]
+        dev_ms, wall, clocks, st = timed_resident(dec, packed, args, ws, flushes, local)
+        recs, roff = dec.fetch_staged()
+        e2e_s, st2, r2, o2 = timed_e2e(dec, packed, args, ws)
+        same = bool(len(r2) == len(recs) and (r2 == recs).all() and (o2 == roff).all())
+        value = cells_hl * args.steps / (dev_ms * 1e-3) / 1e9
+        sweep_ms = st["sweep_ms"] / args.steps
+        tb_ms = st["traceback_ms"] / args.steps
+        # ---- roofline of the dominant kernel (sweep): integer issue rate, aggregated over the N devices ----
         alu, both, mhz = int_peak(local)
-        cells_rank = float(cells_of(segs, mons))
         opc = OPS_PER_CELL[1 if st["packed"] else 0]
-        ach = cells_rank / (sweep_ms * 1e-3) * opc / 1e12
-        peak = alu / 1e12
-        codes_bytes = cells_rank * 0.25
+        ach = cells_act / (sweep_ms * 1e-3) * opc / 1e12
+        peak = ws * alu / 1e12
+        in_bytes = float(sum(len(s) for s in segs))
         roof = {"bound": "int_alu", "achieved": ach, "peak": peak, "unit": "Tlane-op/s", "frac": ach / peak,
-                "traffic": TRAFFIC_BYTES_PER_LAUNCH,
+                "traffic": float(st["sweep_store_bytes"]) + in_bytes,
+                "traffic_source": "computed at run time from the launch layout (sd_get_stats: 2-bit backpointer words incl. slot "
+                                  "padding + 8 B per column + 1 B per column read); the ncu dram__bytes of the same launch are in profiles/",
+                "traffic_algorithmic": 0.25 * cells_act + 9.0 * in_bytes,
                 "peak_source": "measured in this run by sd_int_peak: independent VIADDMNMX.S16x2 streams on all SMs "
-                               "(the integer ALU pipe, 64 lanes/clk/SM); with the FMA pipe (IMAD) in parallel: %.2f" % (both / 1e12),
-                "ops_per_cell": opc, "kernel": "sweep_kernel", "kernel_ms": sweep_ms, "traceback_ms": tb_ms,
-                "frac_with_survey_ops_per_cell": cells_rank / (sweep_ms * 1e-3) * SURVEY_OPS_PER_CELL[1 if st["packed"] else 0] / alu,
-                "hbm": {"achieved_gbs": (codes_bytes + sum(len(s) for s in segs) * 9.0) / (sweep_ms * 1e-3) / 1e9,
-                        "peak_gbs": _hbm_peak(), "note": "2-bit backpointers, 0.25 B/cell; not the limiter"}}
+                               "(the integer ALU pipe, 64 lanes/clk/SM), times %d GPUs; with the FMA pipe (IMAD) in parallel: %.2f per GPU" % (ws, both / 1e12),
+                "ops_per_cell": opc, "kernel": "sweep_lat_kernel" if st["lat"] else "sweep_kernel", "kernel_ms": sweep_ms, "traceback_ms": tb_ms,
+                "frac_with_survey_ops_per_cell": cells_act / (sweep_ms * 1e-3) * SURVEY_OPS_PER_CELL[1 if st["packed"] else 0] / (ws * alu),
+                "hbm": {"achieved_gbs": (float(st["sweep_store_bytes"]) + in_bytes) / (sweep_ms * 1e-3) / 1e9,
+                        "peak_gbs": _hbm_peak() * ws, "note": "2-bit backpointers, 0.25 B/cell; not the limiter"}}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "s16x2" if st["packed"] else "s32", "data": "synthetic",
-                "config": {"workload": "config2: synthetic 2 Mb cenX-like DXZ1 HOR array per GPU, 12 monomers (+RC), part 5000 overlap 500",
-                           "segments_per_gpu": len(segs), "scoring": "-1,-1,-1,1", "l2": "256 MiB memset between timed steps; "
-                           "the 2.5 GB backpointer stream exceeds L2 by itself",
-                           "geometry": {k: st[k] for k in ("C", "T", "NS", "NT")}},
+                "config": {"workload": WORKLOAD, "segments": len(segs), "segments_per_gpu": st["dev_segments"], "scoring": "-1,-1,-1,1",
+                           "partition": "one array; contiguous column-balanced segment ranges, one per GPU, driven by one host process "
+                                        "(Engine::split); no collective on the data path",
+                           "l2": "256 MiB memset on every GPU between timed steps",
+                           "geometry": {k: st[k] for k in ("C", "T", "NS", "NT", "NG", "lat", "scanw")}},
                 "cells_actual_gcups": cells_act * args.steps / (dev_ms * 1e-3) / 1e9,
-                "decomposed_mbp_per_s": sum_len(reads) * ws * args.steps / (dev_ms * 1e-3) / 1e6,
+                "decomposed_mbp_per_s": sum_len(reads) * args.steps / (dev_ms * 1e-3) / 1e6,
                 "wall_ms_per_step": 1e3 * wall / args.steps,
-                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": st2["h2d_bytes"] // args.steps,
+                "e2e": {"value": cells_hl * args.steps / e2e_s / 1e9, "unit": UNIT, "h2d_bytes_per_step": st2["h2d_bytes"] // args.steps,
                         "d2h_bytes_per_step": st2["d2h_bytes"] // args.steps, "ms_per_step": 1e3 * e2e_s / args.steps,
                         "matches_resident_run": same},
                 "gpu_launches": int(st["launches"]), "clocks": clocks, "roofline": roof}
-        if ws == 1:
+        if ws == 1 and not args.no_extras:
             line["rescoring"] = rescoring(segs, mons, recs, roff, local, alu)
+            line["process"] = process_boundary(rnames, reads, mnames, mons)
         if not args.no_cpu_baseline and ws == 1:          # reported at N=1 only
             line["cpu_baseline"] = cpu_baseline(reads, rnames, mnames, mons)
+        dec.close()
+        del flushes
+    else:
+        # same sequence of barriers as rank 0 (timed_resident: 2, timed_e2e: 2)
+        for _ in range(4):
+            barrier_sync(ws)
+
+    # ---- replicas (extra key): every GPU decomposes its own 2 Mb array, one process per GPU (weak scaling) ----
+    if ws > 1 and not args.no_extras:
+        rn_r, reads_r, mn_r, mons_r, segs_r = workload(rank)
+        dec = Decomposer(mons_r, *SCORING, devices=[local])
+        flush = [torch.empty(256 << 20, dtype=torch.uint8, device="cuda:%d" % local)]
+        dev_ms_r, wall_r, _, st_r = timed_resident(dec, pack_segments(segs_r), args, ws, flush, local)
+        dev_ms_r = max_over_ranks(dev_ms_r, ws)
+        cells_r = sum_over_ranks(float(headline_cells(reads_r, mons_r)), ws)
+        if rank == 0:
+            line["replicas"] = {"what": "one 2 Mb array per GPU, one process per GPU (round-1 measurement, weak scaling)",
+                                "value": cells_r * args.steps / (dev_ms_r * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": dev_ms_r / args.steps}
+        dec.close()
+    if rank == 0:
         print(json.dumps(line))
     if ws > 1:
         import torch.distributed as dist
         dist.barrier()
         dist.destroy_process_group()
+
+
+def process_boundary(rnames, reads, mnames, mons):
+    """The boundary main.py:194 actually crosses is a process: wall time of `dp` on the config-2 contig, cold (CUDA
+    context creation, module load, FASTA ingest, TSV) -- not the warm-handle number `e2e` reports."""
+    from stringdecomposer_b200 import synth
+    dp = os.path.join(ROOT, "stringdecomposer_b200", "build", "bin", "dp")
+    with tempfile.TemporaryDirectory() as td:
+        rp, mp = os.path.join(td, "reads.fa"), os.path.join(td, "monomers.fa")
+        synth.write_fasta(rp, rnames, reads)
+        synth.write_fasta(mp, mnames, mons)
+        walls = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            with open(os.path.join(td, "out.tsv"), "wb") as out:
+                subprocess.run([dp, rp, mp, "1", str(PART), str(OVERLAP)], stdout=out, stderr=subprocess.DEVNULL, check=True)
+            walls.append(time.perf_counter() - t0)
+    return {"what": "wall time of the drop-in `dp` process on the config-2 contig (2 Mb), including CUDA start-up",
+            "dp_process_s": min(walls), "dp_process_s_all": walls,
+            "gcups": headline_cells(reads, mons) / min(walls) / 1e9}
 
 
 # ALU-pipe instructions per cell of identity_kernel (2 VIADDMNMX + 2 VIADD + 1 LOP3; the ISETP issues elsewhere):
@@ -361,10 +422,6 @@ def rescoring(segs, mons, recs, roff, device, alu_peak):
             "int_alu_roofline_frac": cells / (best_k * 1e-3) * IDENTITY_ALU_OPS_PER_CELL / alu_peak}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one sweep_kernel launch on this workload (ncu --set full, profiles/)
-TRAFFIC_BYTES_PER_LAUNCH = 3.62e9     # profiles/r01_sweep_r1_final.md: 0.288 GB read + 3.335 GB written (2.26 GB algorithmic)
-
-
 def sum_len(reads):
     return sum(len(r) for r in reads)
 
@@ -388,7 +445,7 @@ def cpu_baseline(reads, rnames, mnames, mons):
     if not os.path.exists(ref):
         return {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": "oracle not built"}
     cores = os.cpu_count() or 1
-    sample = reads[0][:1_000_000]
+    sample = reads[0]
     with tempfile.TemporaryDirectory() as td:
         rp, mp = os.path.join(td, "reads.fa"), os.path.join(td, "monomers.fa")
         synth.write_fasta(rp, rnames[:1], [sample])
@@ -399,7 +456,8 @@ def cpu_baseline(reads, rnames, mnames, mons):
         dt = time.perf_counter() - t0
     cells = len(sample) * 2 * sum(len(m) for m in mons)
     return {"value": cells / dt / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": "first 1,000,000 bp of the config-2 contig (200 segments), dp -t %d, process wall time %.2f s" % (cores, dt)}
+            "sample": "the full config-2 contig (2,000,000 bp, 400 segments), dp -t %d, process wall time %.2f s" % (cores, dt),
+            "process_wall_s": dt}
 
 
 if __name__ == "__main__":

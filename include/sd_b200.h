@@ -45,6 +45,11 @@ typedef struct {
     int32_t n_devices;
     int32_t packed;                     /* 1: s16x2 sweep, 0: s32 sweep (last call) */
     int32_t C, T, NS, NT;               /* launch geometry of the last call */
+    int32_t NG, lat, scanw, pad_;       /* CTAs per segment; 1 = deferred-jump sweep; carry window of the scan */
+    int64_t sweep_store_bytes;          /* bytes the sweep writes per pass over the last batch: 2-bit codes (incl. slot
+                                           padding) + 8 B per column, summed over devices -- computed from the layout */
+    int32_t dev_segments[8];            /* segments each device got in the last batch (AlignReadsSet's gather,
+                                           main.cpp:84-121, is the concatenation in device order) */
 } sd_stats;
 
 /* Replaces the MonomersAligner constructor (main.cpp:59-65) + add_reverse_complement (main.cpp:364-371).

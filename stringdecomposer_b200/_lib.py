@@ -19,7 +19,9 @@ class _Stats(C.Structure):
     _fields_ = [("sweep_ms", C.c_double), ("traceback_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
                 ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("cells", C.c_int64), ("segments", C.c_int64),
                 ("columns", C.c_int64), ("launches", C.c_int64), ("n_devices", C.c_int32), ("packed", C.c_int32),
-                ("C", C.c_int32), ("T", C.c_int32), ("NS", C.c_int32), ("NT", C.c_int32)]
+                ("C", C.c_int32), ("T", C.c_int32), ("NS", C.c_int32), ("NT", C.c_int32),
+                ("NG", C.c_int32), ("lat", C.c_int32), ("scanw", C.c_int32), ("pad_", C.c_int32),
+                ("sweep_store_bytes", C.c_int64), ("dev_segments", C.c_int32 * 8)]
 
 
 # every symbol include/sd_b200.h declares (tests/test_abi.py checks the header against this list)
@@ -200,7 +202,9 @@ class Decomposer:
     def stats(self):
         s = _Stats()
         self._lib.sd_get_stats(self._h, C.byref(s))
-        return {k: getattr(s, k) for k, _ in _Stats._fields_}
+        d = {k: getattr(s, k) for k, _ in _Stats._fields_ if k != "pad_"}
+        d["dev_segments"] = [int(x) for x in d["dev_segments"]][:max(1, d["n_devices"])]
+        return d
 
     def reset_stats(self):
         self._lib.sd_reset_stats(self._h)

@@ -14,6 +14,7 @@ reference; export ``SD_HONOR_SCORING=1`` to have ``-s`` applied.
 import argparse
 import logging
 import os
+import re
 import pathlib
 import sys
 import time
@@ -33,13 +34,21 @@ def get_logger(filename, logger_name="StringDecomposer"):
     return logger
 
 
+def honor_scoring():
+    """SD_HONOR_SCORING parsed exactly like csrc/dp_main.cpp does (atoi != 0): "0" and "" mean off."""
+    m = re.match(r"\s*([+-]?\d+)", os.environ.get("SD_HONOR_SCORING", ""))
+    return bool(m) and int(m.group(1)) != 0
+
+
 def run(sequences, monomers, num_threads, scoring, batch_size, raw_file, ed_thr, overlap, logger, flavour="cuda"):
     """main.py:186-197: run the DP on the two FASTA files, leave its stdout in raw_file and return it as text."""
     ins, dels, mm, match = (int(x) for x in scoring.split(","))
-    if not os.environ.get("SD_HONOR_SCORING"):
+    if not honor_scoring():
         if (ins, dels, mm, match) != (-1, -1, -1, 1):
-            logger.info("NOTE: like the reference's dp (main.cpp:380-391), the DP ignores --scoring when it is driven by "
-                        "main.py; export SD_HONOR_SCORING=1 to apply it")
+            note = ("NOTE: like the reference's dp (main.cpp:380-391), the DP ignores --scoring when it is driven by "
+                    "main.py; export SD_HONOR_SCORING=1 to apply it")
+            logger.info(note)
+            print(note, file=sys.stderr)
         ins, dels, mm, match = -1, -1, -1, 1
     logger.info(" ".join(["Run", _lib.library_path(flavour), "with parameters", sequences, monomers, str(num_threads),
                           str(batch_size), str(overlap), scoring]))

@@ -152,6 +152,7 @@ int sd_stage(sd_handle *h, const char *segments, const int64_t *offsets, int64_t
     if (st) return st;
     try { h->eng->stage(b); }
     catch (PlanError &e) { h->err = e.msg; return status_of(e.msg); }
+    catch (std::exception &e) { h->err = e.what(); return SD_ERR_INTERNAL; }
     return SD_OK;
 }
 
@@ -160,6 +161,7 @@ int sd_run_staged(sd_handle *h, double *kernel_ms)
     if (!h) return SD_ERR_ARG;
     try { double ms = h->eng->run_staged(); if (kernel_ms) *kernel_ms = ms; }
     catch (PlanError &e) { h->err = e.msg; return status_of(e.msg); }
+    catch (std::exception &e) { h->err = e.what(); return SD_ERR_INTERNAL; }
     return SD_OK;
 }
 
@@ -169,6 +171,7 @@ int sd_fetch_staged(sd_handle *h, sd_record **records, int64_t **rec_offsets)
     BatchResult res;
     try { h->eng->fetch_staged(res); }
     catch (PlanError &e) { h->err = e.msg; return SD_ERR_CUDA; }
+    catch (std::exception &e) { h->err = e.what(); return SD_ERR_INTERNAL; }
     return export_result(res, records, rec_offsets);
 }
 
@@ -271,10 +274,20 @@ int sd_get_stats(sd_handle *h, sd_stats *o)
     o->h2d_bytes = s.h2d_bytes; o->d2h_bytes = s.d2h_bytes; o->cells = s.cells; o->segments = s.segments;
     o->columns = s.columns; o->launches = s.launches; o->n_devices = h->n_devices;
     o->packed = s.g.packed; o->C = s.g.C; o->T = s.g.T; o->NS = s.g.NS; o->NT = s.g.NT;
+    o->NG = s.g.NG; o->lat = s.g.lat; o->scanw = s.g.scanw;
+    o->sweep_store_bytes = s.sweep_store_bytes;
+    for (int d = 0; d < 8; ++d) o->dev_segments[d] = s.dev_segments[d];
     return SD_OK;
 }
 
-void sd_reset_stats(sd_handle *h) { if (h) { Geometry g = h->eng->stats.g; h->eng->stats = EngineStats(); h->eng->stats.g = g; } }
+void sd_reset_stats(sd_handle *h)
+{
+    if (!h) return;
+    const EngineStats old = h->eng->stats;
+    h->eng->stats = EngineStats();
+    h->eng->stats.g = old.g; h->eng->stats.sweep_store_bytes = old.sweep_store_bytes;
+    for (int d = 0; d < 8; ++d) h->eng->stats.dev_segments[d] = old.dev_segments[d];
+}
 
 const char *sd_last_error(sd_handle *h)
 {

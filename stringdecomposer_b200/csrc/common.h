@@ -37,6 +37,12 @@ struct Plan {
     std::vector<uint32_t> prof;          // [5 symbols][nsl][qp][4] profile words 4*s''-1 (pad cells: very negative)
     std::vector<int> slot_len;           // row length of each slot
     std::vector<int> slot_endadd;        // (L-1)*del of each slot
+    // deferred-jump sweep (Geometry::lat): profile rows carry p and, right behind it, the tagged prefix maximum PT of
+    // the jump candidates: [5 symbols][nsl][qp2][4] with words [0,C) = p, [C,2C) = PT
+    std::vector<uint32_t> prof2;
+    int qp2 = 0;                         // uint4 per lane row of prof2: ceil(2C/4) padded to an odd count
+    int kj[5] = {0, 0, 0, 0, 0};         // per symbol: best key of a jump-derived row end, relative to the jump base
+    int lat_th = 0;                      // rebase threshold of the deferred form (SD_REBASE_TH minus one column step)
     size_t smem_bytes(int seg_stride) const;
 };
 
@@ -70,6 +76,12 @@ void build_monomer_set(const std::vector<std::string> &forward, MonomerSet &ms);
 Plan make_plan(const MonomerSet &ms, const Scoring &sc, int max_seg_len, int64_t nseg_hint);  // throws PlanError
 bool packed_range_ok(const MonomerSet &ms, const Scoring &sc, int *deadz, int *pad_s);
 bool geometry_compiled(int packed, int C, int T);
+bool lat_geometry_compiled(int C, int T);
+// per symbol: max over the DP rows of ((best s'' of the row for that symbol) + (L-1)*del) * 4096 + 4095 - tie-break index;
+// rank_of_row: the --ed_thr ranks of one segment ([row] -> position in the filtered list, -1 = filtered out) or null
+void lat_jump_keys(const MonomerSet &ms, const Scoring &sc, const int *rank_of_row, int out[5]);
+// lanes a lane of a slot must look back so that the windowed deletion carry equals the full prefix maximum
+int scan_window(const MonomerSet &ms, const Scoring &sc, int packed, int C, int T);
 // CTA bookkeeping shared by backend and emulator
 struct CtaLayout {
     std::vector<int> cta_nmax;           // longest segment of each CTA

@@ -2,6 +2,7 @@
 // overlap resolution and the raw TSV writer.  Reference behaviour restated from stringdecomposer/src/main.cpp
 // (line numbers cited per function); the data structures and control flow are this project's own.
 #include <algorithm>
+#include <cerrno>
 #include <cstring>
 #include <fstream>
 #include <chrono>
@@ -128,6 +129,18 @@ void Engine::plan_for(const Batch &b)
     stats.g = plan_.g;
 }
 
+void Engine::note_split(const Batch &b, const std::vector<int> &bounds)
+{
+    stats.sweep_store_bytes = 0;
+    for (int d = 0; d < 8; ++d) stats.dev_segments[d] = 0;
+    for (int d = 0; d < ndev(); ++d) {
+        if (d < 8) stats.dev_segments[d] = bounds[d + 1] - bounds[d];
+        if (bounds[d] == bounds[d + 1]) continue;
+        const CtaLayout l = make_cta_layout(plan_, b, bounds[d], bounds[d + 1]);
+        stats.sweep_store_bytes += l.cta_code_off.back() * 4 + l.seg_j_off.back() * (int64_t)sizeof(JR);
+    }
+}
+
 // contiguous, column-balanced ranges, one per device (segments are independent, no collective)
 void Engine::split(const Batch &b, std::vector<int> &bounds) const
 {
@@ -151,6 +164,7 @@ void Engine::decompose(const Batch &b, BatchResult &out)
     for (int s = 0; s < b.nseg(); ++s) if (b.len(s) <= 0) throw PlanError{"empty segment"};
     plan_for(b);
     std::vector<int> bounds; split(b, bounds);
+    note_split(b, bounds);
     const int nd = ndev();
     std::vector<BatchResult> part(nd);
     std::vector<std::string> errs(nd);
@@ -219,6 +233,7 @@ void Engine::stage(const Batch &b)
     staged_.text = staged_.own.data();
     plan_for(staged_);
     split(staged_, staged_bounds_);
+    note_split(staged_, staged_bounds_);
     for (int d = 0; d < ndev(); ++d) {
         if (staged_bounds_[d] == staged_bounds_[d + 1]) continue;
         if (devs_[d]->wave_bytes(staged_, staged_bounds_[d], staged_bounds_[d + 1]) > devs_[d]->wave_budget())
@@ -228,6 +243,7 @@ void Engine::stage(const Batch &b)
     auto work = [&](int d) {
         try { if (staged_bounds_[d] < staged_bounds_[d + 1]) devs_[d]->stage(staged_, staged_bounds_[d], staged_bounds_[d + 1]); }
         catch (PlanError &e) { errs[d] = e.msg.empty() ? "error" : e.msg; }
+        catch (std::exception &e) { errs[d] = e.what(); }
     };
     if (ndev() == 1) work(0);
     else {
@@ -246,7 +262,8 @@ double Engine::run_staged()
         try {
             devs_[d]->reset_stats();
             if (staged_bounds_[d] < staged_bounds_[d + 1]) devs_[d]->execute();
-        } catch (PlanError &e) { errs[d] = e.msg; }
+        } catch (PlanError &e) { errs[d] = e.msg.empty() ? "error" : e.msg; }
+        catch (std::exception &e) { errs[d] = e.what(); }
     };
     if (ndev() == 1) work(0);
     else {
@@ -278,7 +295,20 @@ namespace {
 struct FdWriter {
     int fd; std::string buf;
     explicit FdWriter(int f) : fd(f) { buf.reserve(1 << 20); }
-    void flush() { if (fd < 0) return; size_t o = 0; while (o < buf.size()) { ssize_t w = ::write(fd, buf.data() + o, buf.size() - o); if (w <= 0) break; o += (size_t)w; } buf.clear(); }
+    bool failed = false;             // a write() error other than EINTR: the output is incomplete (ENOSPC, EPIPE, ...)
+    bool flush()
+    {
+        if (fd < 0) return true;
+        size_t o = 0;
+        while (o < buf.size()) {
+            ssize_t w = ::write(fd, buf.data() + o, buf.size() - o);
+            if (w < 0 && errno == EINTR) continue;
+            if (w <= 0) { failed = true; break; }
+            o += (size_t)w;
+        }
+        buf.clear();
+        return !failed;
+    }
     void add(const std::string &s) { buf += s; if (buf.size() > (1 << 20)) flush(); }
     void add_int(long v) { char t[24]; int n = 0; bool neg = v < 0; unsigned long u = neg ? 0ul - (unsigned long)v : (unsigned long)v;
         do { t[n++] = (char)('0' + u % 10); u /= 10; } while (u); if (neg) t[n++] = '-'; while (n) buf.push_back(t[--n]); }
@@ -423,7 +453,12 @@ int run_files(const std::string &reads_path, const std::string &monomers_path, i
     FdWriter outw(out_fd);
     for (int t = 0; t < nthr; ++t) {
         err.add(err_part[t]); err.flush();
-        outw.buf.swap(out_part[t]); outw.flush();
+        outw.buf.swap(out_part[t]);
+        if (!outw.flush()) {                      // ENOSPC / EPIPE ...: a truncated raw TSV must not look like success
+            error = std::string("writing the raw decomposition failed: ") + strerror(errno);
+            err.add("ERROR: " + error + "\n");
+            return 5;
+        }
     }
     if (prof) {
         char line[256];

@@ -26,6 +26,8 @@ struct EngineStats {
     double sweep_ms = 0, traceback_ms = 0, h2d_ms = 0, d2h_ms = 0;
     int64_t h2d_bytes = 0, d2h_bytes = 0, cells = 0, segments = 0, columns = 0, launches = 0;
     Geometry g{};
+    int64_t sweep_store_bytes = 0;      // codes + J/argJ bytes of the last batch (all devices), from the layout
+    int dev_segments[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 // Owns the monomer set, the scoring and one backend per device; decomposes batches of segments.
@@ -44,6 +46,7 @@ public:
 private:
     void plan_for(const Batch &b);
     void split(const Batch &b, std::vector<int> &bounds) const;
+    void note_split(const Batch &b, const std::vector<int> &bounds);
     MonomerSet ms_;
     Scoring sc_;
     std::vector<std::unique_ptr<Backend>> devs_;

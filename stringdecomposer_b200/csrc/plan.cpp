@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <climits>
 #include <cstring>
 
 #include "common.h"
@@ -68,6 +69,68 @@ bool geometry_compiled(int packed, int C, int T)
     for (int x : kC) c |= (x == C);
     for (int x : kT) t |= (x == T);
     return c && t;
+}
+
+// (C, T) pairs the deferred-jump kernel is compiled for (sweep_inst_lat_*.cu instantiates exactly this table)
+static const int kLatGeom[][2] = {{6, 32}, {12, 16}, {12, 32}, {24, 8}, {24, 16}, {24, 32}, {48, 32}};
+bool lat_geometry_compiled(int C, int T)
+{
+    for (auto &g : kLatGeom) if (g[0] == C && g[1] == T) return true;
+    return false;
+}
+
+void lat_jump_keys(const MonomerSet &ms, const Scoring &sc, const int *rank_of_row, int out[5])
+{
+    const int shift = -sc.ins - sc.del;
+    for (int sym = 0; sym < 5; ++sym) {
+        int best = INT_MIN;
+        for (int r = 0; r < ms.nrows(); ++r) {
+            const int tb = rank_of_row ? rank_of_row[r] : r;
+            if (tb < 0) continue;
+            int s2 = INT_MIN;
+            for (int k = ms.row_off[r]; k < ms.row_off[r + 1]; ++k) s2 = std::max(s2, (ms.rows[k] == sym ? sc.match : sc.mismatch) + shift);
+            best = std::max(best, make_key(4 * s2, (ms.rowlen(r) - 1) * sc.del, tb));
+        }
+        out[sym] = best;
+    }
+}
+
+// Windowed deletion carry.  The carry into lane t of a slot is the maximum of the lane totals of ALL lanes on its left.
+// Scores along a row never decrease in the shifted domain (deletions are free), so a candidate of an earlier lane is
+// dominated by any later candidate of the same or a better score class: "up" candidates by the nearest lane, diagonal
+// and jump candidates of the better class (match, normally) by the nearest lane that holds a position of that class
+// for the column's symbol, those of the worse class by either.  The window is the largest such distance over all
+// symbols, slots, lanes and (packed) both rows of a slot; it is a property of the monomer set, not of the reads.
+int scan_window(const MonomerSet &ms, const Scoring &sc, int packed, int C, int T)
+{
+    if (T <= 1) return 0;
+    const int nslots = packed ? ms.M : 2 * ms.M;
+    const int SL = C * T;
+    int W = 1;
+    for (int slot = 0; slot < nslots; ++slot) {
+        const int L = ms.rowlen(slot), lead = (L == 1) ? SL - 1 : 0;
+        for (int half = 0; half < (packed ? 2 : 1); ++half) {
+            const uint8_t *row = ms.rows.data() + ms.row_off[half ? ms.M + slot : slot];
+            for (int sym = 0; sym < 5; ++sym) {
+                // nearest lane so far that holds a position of the better / the worse score class (pad cells: neither --
+                // the lanes behind a short row must look all the way back to its last real cells)
+                int last_hi = -1, last_lo = -1;
+                for (int t = 0; t < T; ++t) {
+                    if (t > 0) {
+                        const int need = last_hi >= 0 ? last_hi : last_lo;
+                        if (need >= 0) W = std::max(W, t - need);
+                    }
+                    for (int kk = 0; kk < C; ++kk) {
+                        const int k = t * C + kk - lead;
+                        if (k < 0 || k >= L) continue;
+                        const int s = row[k] == sym ? sc.match : sc.mismatch;
+                        if (s >= std::max(sc.match, sc.mismatch)) last_hi = t; else last_lo = t;
+                    }
+                }
+            }
+        }
+    }
+    return std::min(W, T - 1);
 }
 
 static const size_t kSmemLimit = 200 * 1024;
@@ -153,7 +216,9 @@ Plan make_plan(const MonomerSet &ms, const Scoring &sc, int max_seg_len, int64_t
     g.NG = 1;
     int force_sg = 0;
     if (const char *e = getenv("SD_GROUP_SLOTS")) force_sg = atoi(e);
-    if (!bestC || force_sg > 0) {
+    const bool lat_forced = getenv("SD_LAT") && atoi(getenv("SD_LAT")) > 0;
+    if (lat_forced && !bestC) { bestC = 6; bestT = 32; bestNS = 1; bestNT = 32; }      // placeholder, replaced below
+    else if (!bestC || force_sg > 0) {
         // The monomer set does not fit one CTA (threads, registers or the shared-memory profile table): split the slots
         // into NG groups, one CTA each; the per-column key then meets in global memory (sweep_group_kernel).
         // fewest partner CTAs per segment first (the exchange latency grows with them), then least padding
@@ -191,6 +256,47 @@ Plan make_plan(const MonomerSet &ms, const Scoring &sc, int max_seg_len, int64_t
     }
     g.packed = packed; g.C = bestC; g.T = bestT; g.nslots = nslots; g.M = ms.M; g.NS = bestNS; g.NT = bestNT;
     if (g.NG == 1) g.SG = nslots;
+    g.lat = 0;
+    // Deferred-jump sweep (sweep_core.cuh: lat_*): a segment is spread over many warps -- a cluster of CTAs that exchange
+    // the column key through distributed shared memory -- and runs at the latency of one column instead of at the
+    // throughput of a loaded SM.  It pays when there are too few segments to fill the GPU with classic CTAs (config 1,
+    // or one array shared by several GPUs); it costs 5.5 instead of 4.5 ALU instructions per register.
+    {
+        int lat_mode = -1, lat_warps = 0;
+        if (const char *e = getenv("SD_LAT")) lat_mode = atoi(e);
+        if (const char *e = getenv("SD_LAT_WARPS")) lat_warps = atoi(e);
+        const int64_t nseg = std::max<int64_t>(nseg_hint, 1);
+        double lbest = 1e300; int lC = 0, lT = 0, lNT = 0, lNG = 0, lSG = 0, lW = 0;
+        if (lat_mode != 0 && force_sg <= 0)
+            for (auto &cand : kLatGeom) {
+                const int C = cand[0], T = cand[1];
+                if (fC && (C != fC || T != fT)) continue;
+                if (C * T < ms.Lmax) continue;
+                if (!fC && C * T >= 2 * std::max(ms.Lmax, 96) && C * T > 192) continue;       // far too much padding
+                const int spw = 32 / T, ws = (nslots + spw - 1) / spw;                        // warps per segment
+                const int W = scan_window(ms, sc, packed, C, T);
+                // warps per CTA: one per scheduler unless that needs more than 8 CTAs per cluster
+                int wc = lat_warps > 0 ? lat_warps : std::min(ws, 4);
+                while ((ws + wc - 1) / wc > 8 && wc < 32) ++wc;
+                if (wc > 32 || (ws + wc - 1) / wc > 8) continue;
+                wc = (ws + (ws + wc - 1) / wc - 1) / ((ws + wc - 1) / wc);                    // even out the CTAs of a cluster
+                const int ng = (ws + wc - 1) / wc, sg = wc * spw;
+                const int qp2c = ((2 * C + 3) / 4) | 1;
+                const size_t smem = (size_t)5 * sg * T * qp2c * 16 + (size_t)max_seg_len + 4096;
+                if (smem > kSmemLimit) continue;
+                const double alu = 2.0 * (5.5 * C + 45.0 + 2.0 * W);
+                const double floor_c = 150.0 + 8.0 * C + 6.0 * W + (ng > 1 ? 120.0 : 0.0);
+                const double wps = std::ceil((double)nseg * ws / (148.0 * 4.0));
+                const double cost = (double)std::max(max_seg_len, 1) * std::max(wps * alu / 0.85, floor_c);
+                if (cost < lbest) { lbest = cost; lC = C; lT = T; lNT = wc * 32; lNG = ng; lSG = sg; lW = W; }
+            }
+        const bool want = lat_mode > 0 || (lat_mode < 0 && lC && g.NG == 1 && nseg <= 2 * 148 && lbest < best);
+        if (want && lC) {
+            g.lat = 1; g.C = lC; g.T = lT; g.NS = 1; g.NT = lNT; g.NG = lNG; g.SG = lNG > 1 ? lSG : nslots; g.scanw = lW;
+        } else if (lat_mode > 0) {
+            throw PlanError{"SD_LAT=1: no deferred-jump geometry fits this monomer set"};
+        }
+    }
     {
         // the lanes of a CTA must cover its slots: NS*nslots slot instances (single CTA) or SG (group sweep)
         const int spw = 32 / g.T;
@@ -201,6 +307,13 @@ Plan make_plan(const MonomerSet &ms, const Scoring &sc, int max_seg_len, int64_t
     const int cpw = packed ? 8 : 16;
     g.CW = (g.C + cpw - 1) / cpw;
     p.nsl = nslots * g.T;
+    if (!g.lat) g.scanw = scan_window(ms, sc, packed, g.C, g.T);
+    {
+        const int64_t D = -(int64_t)sc.del, I = -(int64_t)sc.ins;
+        const int64_t dmax = std::llabs(D) * (std::max(ms.Lmax, 2) + 1) + std::llabs(I) + std::max(std::abs(sc.match), std::abs(sc.mismatch)) + 1;
+        p.lat_th = (int)std::max<int64_t>(0, SD_REBASE_TH - 4 * dmax);
+    }
+    lat_jump_keys(ms, sc, nullptr, p.kj);
 
     // profile words: prof[sym][sl][q][e] = 4*s''(sym, row cell k) - 1 with k = t*C + 4q + e; pad cells get 4*pad_s - 1.
     const int C = g.C, T = g.T, SL = C * T;
@@ -225,6 +338,26 @@ Plan make_plan(const MonomerSet &ms, const Scoring &sc, int max_seg_len, int64_t
                 int t = pos / C, kk = pos % C, q = kk / 4, e = kk % 4;
                 int sl = slot * T + t;
                 p.prof[(((size_t)sym * p.nsl + sl) * p.qp + q) * 4 + e] = w;
+            }
+    }
+    if (g.lat) {
+        // rows of the deferred form: [p | PT], PT[pos] = max(p[pos], max_{pos' < pos} p[pos'] + 3) per half (sweep_core.cuh)
+        p.qp2 = ((2 * C + 3) / 4) | 1;
+        p.prof2.assign((size_t)5 * p.nsl * p.qp2 * 4, 0u);
+        auto word = [&](int sym, int slot, int pos) { return p.prof[(((size_t)sym * p.nsl + slot * T + pos / C) * p.qp + (pos % C) / 4) * 4 + (pos % C) % 4]; };
+        for (int sym = 0; sym < 5; ++sym)
+            for (int slot = 0; slot < nslots; ++slot) {
+                int run_lo = INT_MIN, run_hi = INT_MIN;         // max over earlier positions of p + 3
+                for (int pos = 0; pos < SL; ++pos) {
+                    const uint32_t w = word(sym, slot, pos);
+                    const int lo = packed ? (int)(int16_t)(w & 0xffffu) : (int)w, hi = packed ? (int)(int16_t)(w >> 16) : 0;
+                    const int plo = std::max(lo, run_lo), phi = std::max(hi, run_hi);
+                    run_lo = std::max(run_lo, lo + 3); run_hi = std::max(run_hi, hi + 3);
+                    const uint32_t pt = packed ? (((uint32_t)plo & 0xffffu) | ((uint32_t)phi << 16)) : (uint32_t)plo;
+                    uint32_t *row = p.prof2.data() + (((size_t)sym * p.nsl + slot * T + pos / C) * p.qp2) * 4;
+                    row[pos % C] = w;
+                    row[C + pos % C] = pt;
+                }
             }
     }
     return p;

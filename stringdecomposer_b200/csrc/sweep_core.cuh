@@ -229,6 +229,58 @@ SD_HD uint32_t lane_pre_first(uint32_t prevU, uint32_t pn0, uint32_t u_first, ui
     return P::addmax(prevU, pn0, (kill_first || kill_only) ? deadu : u_first);
 }
 
+// --------------------------------------------------------------------------------------------
+// Deferred-jump ("latency") form of the same column, used when a segment is spread over many warps / CTAs and the
+// per-column exchange of the jump value J[i] would otherwise sit on the critical path.
+//
+// In the shifted domain a jump can only win at a row's first cell and where the profile rises (everywhere else the
+// left neighbour holds at least the same jump-derived value and wins the tie), so column i factors into
+//   h[k] = max( h0[k] , JT[k] )     h0[k] = max( g[k], m[k] ),  g[k] = max_{k'<k} (m[k'] | 3)    -- independent of J[i]
+//                                   JT[k] = PT[k] + 4*(B[i]-Bref) + 1,  PT[k] = max( p[k], max_{k'<k} p[k'] + 3 )
+// with m[k] = max(U[k-1] + p[k], U[k]) as before and PT a second, static profile (the tagged prefix maximum of the
+// jump candidates of the slot).  This is the same tagged maximum the classic form computes -- (x | 3) distributes over
+// max -- so values, tie-breaks and backpointer codes are identical.  What changes is the dependency: the vector work
+// of column i needs B[i-1] only through U[i-1]; B[i] enters in one VIADDMNMX per register at the very end.  The key of
+// the J-independent row ends (K0[i]) is therefore published one whole column before anybody needs it:
+//   B[i+1] <- max( K0[i] , B[i] + KJ[sym_i] )      KJ: static per symbol (best jump-derived row end)
+// Per register: VIADDMNMX (m), VIMNMX + LOP3 (chain), VIADDMNMX (merge), LOP3 (re-tag) + 1/2 VIMNMX3 (lane total)
+// = 5.5 ALU-pipe instructions (classic: 4.5) -- the price of taking the exchange latency off the critical path.
+//
+// lat_total: the lane's contribution to the left candidates of the lanes on its right, tag 3.
+template <class P, int C> SD_HD uint32_t lat_total(const uint32_t (&M)[C], TagRegs tr) { return tree_max<P, C>(M) | tr.mask3; }
+
+// Deletion chain of the J-independent part, in place: X[kk] = m[kk] -> h0[kk] = max(g, m[kk]); g <- h0[kk] | 3.
+// carry: maximum of lat_total over the lanes on the left (tag 3; dead for the first lane of a slot).
+// Returns g after the last cell = (h0 of the lane's last cell) | 3.
+template <class P, int C>
+SD_HD uint32_t lat_chain(uint32_t (&X)[C], uint32_t carry, TagRegs tr)
+{
+    uint32_t g = carry;
+#pragma unroll
+    for (int kk = 0; kk < C; ++kk) {
+        X[kk] = P::max2(g, X[kk]);
+        g = X[kk] | tr.mask3;
+    }
+    return g;
+}
+
+// Merge with the jump-derived candidates and re-tag, in place: X[kk] = h0 -> U (tag-2 form); backpointer digits as in
+// lane_pass2_pre.  pt: the PT words of the column, jump0p1 = splat(4*(B[i]-Bref) + 1).  Returns U[C-1].
+template <class P, int C>
+SD_HD uint32_t lat_merge(uint32_t (&X)[C], const uint32_t *pt, uint32_t jump0p1, uint32_t *codes, TagRegs tr)
+{
+    constexpr int CPW = P::CELLS_PER_WORD;
+    uint32_t w = 0;
+#pragma unroll
+    for (int kk = 0; kk < C; ++kk) {
+        const uint32_t h = P::addmax(pt[kk], jump0p1, X[kk]);
+        X[kk] = (h | tr.mask3) ^ tr.one;
+        w = w * 4u + X[kk] - h;
+        if ((kk + 1) % CPW == 0 || kk == C - 1) { codes[kk / CPW] = w; w = 0; }
+    }
+    return X[C - 1];
+}
+
 // Rebase: shift every register of the lane by -shift4 (packed per half).
 template <class P, int C>
 SD_HD void lane_rebase(uint32_t (&X)[C], int shift4)
@@ -259,6 +311,8 @@ struct Geometry {
     int CW;          // backpointer words per lane per column
     int NG;          // CTAs (slot groups) that share one segment; 1 = the whole monomer set fits one CTA
     int SG;          // slots per group (== nslots when NG == 1)
+    int lat;         // 1: deferred-jump sweep (sweep_lat_kernel; a segment = a cluster of NG CTAs, NS == 1), 0: classic
+    int scanw;       // lanes a lane must look back for the deletion carry (windowed scan; see plan.cpp: scan_window)
 };
 
 struct Record { int32_t row, start, end, score; };

@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "sweep_kernel.cuh"
+#include "sweep_lat_kernel.cuh"
 #include "cuda_scope.h"
 
 namespace sdb {
@@ -272,7 +273,7 @@ public:
         SD_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
         for (auto &e : ev_) SD_CUDA(cudaEventCreate(&e));
         SD_CUDA(cudaGetDeviceProperties(&prop_, dev_));
-        if (prop_.major < 10) throw PlanError{"CUDA device is not sm_100 class: this library carries sm_100a code only"};
+        if (prop_.major != 10) throw PlanError{"CUDA device is not sm_100 class: this library carries sm_100a code only (no PTX for other architectures)"};
         size_t fr = 0, tot = 0;
         SD_CUDA(cudaMemGetInfo(&fr, &tot));
         budget_ = std::min<int64_t>((int64_t)(fr * 0.85), (int64_t)96 << 30);
@@ -293,14 +294,16 @@ public:
         const int spw = 32 / g.T;
         fast_ = (g.nslots % spw == 0) && (g.nslots / spw <= 4) && g.NS <= 15;     // 15 named barriers besides barrier 0
         if (getenv("SD_NOFAST")) fast_ = false;
-        kernel_ = g.NG > 1 ? (g.packed ? sweep_group_lookup_p16(g.C, g.T) : sweep_group_lookup_s32(g.C, g.T))
-                           : kern(g.packed, g.C, g.T, fast_, fast_ && g.NS > 1);
+        if (g.lat) kernel_ = g.packed ? sweep_lat_lookup_p16(g.C, g.T) : sweep_lat_lookup_s32(g.C, g.T);
+        else kernel_ = g.NG > 1 ? (g.packed ? sweep_group_lookup_p16(g.C, g.T) : sweep_group_lookup_s32(g.C, g.T))
+                                : kern(g.packed, g.C, g.T, fast_, fast_ && g.NS > 1);
         if (!kernel_) throw PlanError{"no sweep kernel compiled for this geometry"};
         cudaFuncAttributes fa;
         SD_CUDA(cudaFuncGetAttributes(&fa, kernel_));
         if ((int64_t)fa.numRegs * g.NT * (g.NG > 1 ? g.NS : 1) > 65536) throw PlanError{"sweep geometry exceeds the register file (regs*threads > 64K)"};
-        d_prof_.need(p.prof.size() * 4);
-        SD_CUDA(cudaMemcpyAsync(d_prof_.p, p.prof.data(), p.prof.size() * 4, cudaMemcpyHostToDevice, st_));
+        const std::vector<uint32_t> &table = g.lat ? p.prof2 : p.prof;
+        d_prof_.need(table.size() * 4);
+        SD_CUDA(cudaMemcpyAsync(d_prof_.p, table.data(), table.size() * 4, cudaMemcpyHostToDevice, st_));
         d_slotlen_.need(p.slot_len.size() * 4); d_slotend_.need(p.slot_endadd.size() * 4);
         SD_CUDA(cudaMemcpyAsync(d_slotlen_.p, p.slot_len.data(), p.slot_len.size() * 4, cudaMemcpyHostToDevice, st_));
         SD_CUDA(cudaMemcpyAsync(d_slotend_.p, p.slot_endadd.data(), p.slot_endadd.size() * 4, cudaMemcpyHostToDevice, st_));
@@ -375,6 +378,12 @@ public:
             SD_CUDA(cudaStreamSynchronize(st_));
             for (int s = 0; s < nseg_; ++s)
                 build_filter_tables(hdist_.data() + (size_t)s * R, R, ed_thr_, hrank_.data() + (size_t)s * R, hr2r_.data() + (size_t)s * R);
+            if (plan_.g.lat) {
+                hsegkj_.resize((size_t)nseg_ * 5);
+                for (int s = 0; s < nseg_; ++s) lat_jump_keys(ms_, plan_.sc, hrank_.data() + (size_t)s * R, hsegkj_.data() + (size_t)s * 5);
+                d_segkj_.need(hsegkj_.size() * 4);
+                SD_CUDA(cudaMemcpyAsync(d_segkj_.p, hsegkj_.data(), hsegkj_.size() * 4, cudaMemcpyHostToDevice, st_));
+            }
             SD_CUDA(cudaMemcpyAsync(d_rank_.p, hrank_.data(), np * 4, cudaMemcpyHostToDevice, st_));
             SD_CUDA(cudaMemcpyAsync(d_r2r_.p, hr2r_.data(), np * 4, cudaMemcpyHostToDevice, st_));
             SD_CUDA(cudaStreamSynchronize(st_));
@@ -444,13 +453,46 @@ public:
         SD_CUDA(cudaLaunchCooperativeKernel(kernel_, dim3(a.ngslots * g.NG), dim3(g.NS * g.NT), args, smem, st_));
     }
 
+    void launch_lat(int seg_stride)
+    {
+        const Geometry &g = plan_.g;
+        LatArgs a;
+        a.prof2 = d_prof_.as<uint4>(); a.nsl_total = plan_.nsl; a.qp2 = plan_.qp2;
+        a.bases = d_bases_.as<uint8_t>(); a.seg_off = d_segoff_.as<int64_t>(); a.nseg = nseg_;
+        a.cta_code_off = d_ctacode_.as<int64_t>(); a.seg_j_off = d_segj_.as<int64_t>();
+        a.codes = d_codes_.as<uint32_t>(); a.jr = d_jr_.as<JR>();
+        a.slot_len = d_slotlen_.as<int>(); a.slot_endadd = d_slotend_.as<int>();
+        a.nslots = g.nslots; a.M = g.M; a.NT = g.NT; a.CW = g.CW; a.NG = g.NG; a.SG = g.SG;
+        a.ins = plan_.sc.ins; a.del = plan_.sc.del; a.deadz = plan_.deadz; a.lat_th = plan_.lat_th; a.scanw = g.scanw;
+        for (int q = 0; q < 5; ++q) a.kj[q] = plan_.kj[q];
+        a.seg_kj = filter_on_ ? d_segkj_.as<int>() : nullptr;
+        a.rank = filter_on_ ? d_rank_.as<int>() : nullptr;
+        a.seg_stride = seg_stride;
+        a.tr = g.packed ? tag_regs<Packed16>() : tag_regs<Scalar32>();
+        a.bad_symbol = d_flag_.as<int>(); a.error = d_flag_.as<int>() + 1;
+        const int spw = 32 / g.T, wpc = g.NT / 32;
+        const size_t sgt = (size_t)wpc * spw * g.T;
+        const size_t smem = (size_t)5 * sgt * plan_.qp2 * 16 + (size_t)LAT_NBUF * wpc * g.NG * 8 + 32 + (size_t)seg_stride;
+        if (smem > (size_t)prop_.sharedMemPerBlockOptin) throw PlanError{"deferred-jump sweep needs more shared memory than the SM has"};
+        SD_CUDA(cudaFuncSetAttribute(kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(nseg_ * g.NG)); cfg.blockDim = dim3((unsigned)g.NT);
+        cfg.dynamicSmemBytes = smem; cfg.stream = st_;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)g.NG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        void *args[] = {(void *)&a};
+        SD_CUDA(cudaLaunchKernelExC(&cfg, kernel_, args));
+    }
+
     void execute() override
     {
         DeviceScope scope_(dev_); SD_CUDA(scope_.status);
         const Geometry &g = plan_.g;
         const int seg_stride = (nmax_ + 16) / 16 * 16;
         SD_CUDA(cudaEventRecord(ev_[0], st_));
-        if (g.NG > 1) launch_group(seg_stride); else launch_single(seg_stride);
+        if (g.lat) launch_lat(seg_stride); else if (g.NG > 1) launch_group(seg_stride); else launch_single(seg_stride);
         SD_CUDA(cudaEventRecord(ev_[1], st_));
         TbArgs t;
         t.g = g; t.codes = d_codes_.as<uint32_t>(); t.cta_code_off = d_ctacode_.as<int64_t>(); t.jr = d_jr_.as<JR>();
@@ -471,7 +513,7 @@ public:
         SD_CUDA(cudaStreamSynchronize(st_));
         if (flag[0] || flag[1]) {
             SD_CUDA(cudaMemsetAsync(d_flag_.p, 0, 16, st_));
-            if (flag[1]) throw PlanError{"CUDA: group sweep timed out waiting for a partner CTA (internal error)"};
+            if (flag[1]) throw PlanError{"CUDA: sweep timed out waiting for a partner CTA (internal error)"};
             throw PlanError{"segment contains a symbol outside ACGTN"};
         }
         float ms = 0;
@@ -522,7 +564,7 @@ private:
     std::vector<int64_t> hoff_, houtoff_;
     std::vector<int> hcnt_;
     std::vector<uint8_t> rows_ascii_;
-    std::vector<int> hdist_, hrank_, hr2r_;
+    std::vector<int> hdist_, hrank_, hr2r_, hsegkj_;
     bool filter_on_ = false;
     int64_t budget_ = 0;
     DevBuf d_prof_, d_slotlen_, d_slotend_, d_rows_, d_rowoff_;
@@ -530,7 +572,7 @@ private:
     DevBuf d_bases_, d_meta_;
     MetaView d_segoff_, d_ctanmax_, d_ctacode_, d_segj_, d_segrec_;     // slices of d_meta_
     std::vector<char> hmeta_;
-    DevBuf d_flag_, d_xchg_, d_dist_, d_rank_, d_r2r_, d_codes_, d_jr_, d_scratch_, d_counts_, d_outoff_, d_dense_;
+    DevBuf d_segkj_, d_flag_, d_xchg_, d_dist_, d_rank_, d_r2r_, d_codes_, d_jr_, d_scratch_, d_counts_, d_outoff_, d_dense_;
 };
 
 } // namespace

@@ -127,6 +127,141 @@ void emu_cta(const Plan &p, const Batch &b, int seg_first, int nseg_cta, int nma
     }
 }
 
+// Deferred-jump sweep (sweep_lat_kernel): the CTAs of the segment's cluster side by side; the only coupling between
+// the warps is the column key, published at column i and consumed at column i+1 (sweep_core.cuh: lat_*).
+bool &window_violation() { static thread_local bool f = false; return f; }
+const int *&emu_kj() { static thread_local const int *p = nullptr; return p; }
+
+template <class P, int C, int T>
+void emu_cta_lat(const Plan &p, const Batch &b, int seg_first, int nseg_cta, int nmax,
+                 uint32_t *const *codes, JR *const *jr, const int *rank)
+{
+    (void)nseg_cta;
+    const Geometry &g = p.g;
+    const int NTC = g.NT, NG = g.NG, NT = NTC * NG;
+    constexpr int SPW = 32 / T;
+    const TagRegs tr = tag_regs<P>();
+    const uint32_t deadu = P::splat(p.deadz - 1);
+    const int n = b.len(seg_first);
+    std::vector<uint32_t> Xall((size_t)NT * C, deadu), PWall((size_t)NT * C, 0u), PTall((size_t)NT * C, 0u);
+    uint32_t (*X)[C] = reinterpret_cast<uint32_t (*)[C]>(Xall.data());
+    uint32_t (*PW)[C] = reinterpret_cast<uint32_t (*)[C]>(PWall.data());
+    uint32_t (*PT)[C] = reinterpret_cast<uint32_t (*)[C]>(PTall.data());
+    struct LaneId { bool ok; int slot, t, sl; bool active; };
+    auto lane_id = [&](int tid) {
+        LaneId l;
+        const int grp = tid / NTC, tin = tid % NTC;
+        const int warp = tin / 32, lane = tin % 32, siw = lane / T;
+        l.t = lane - siw * T;
+        l.ok = siw < SPW;
+        const int ginst = warp * SPW + (l.ok ? siw : 0);
+        l.slot = (NG > 1 ? grp * g.SG : 0) + ginst;
+        l.active = l.ok && ginst < g.SG && l.slot < g.nslots;
+        if (l.slot >= g.nslots) l.slot = g.nslots - 1;
+        l.sl = l.slot * T + l.t;
+        return l;
+    };
+    auto symbol = [&](int i) {
+        int sym = (i < n) ? ascii_code(b.text[b.off[seg_first] + i]) : 0;
+        if (sym > 4) { bad_symbol() = true; sym = 0; }
+        return sym;
+    };
+    auto load_profile = [&](int tid, const LaneId &l, int i) {
+        const uint32_t *row = p.prof2.data() + (((size_t)symbol(i) * p.nsl + l.sl) * p.qp2) * 4;
+        for (int kk = 0; kk < C; ++kk) { PW[tid][kk] = row[kk]; PT[tid][kk] = row[C + kk]; }
+    };
+    const int *kj = emu_kj() ? emu_kj() : p.kj;          // per-segment keys when the --ed_thr filter re-ranks the rows
+    const int R = 2 * g.M;
+    auto tie_lo = [&](const LaneId &l) { return rank ? rank[l.slot] : l.slot; };
+    auto tie_hi = [&](const LaneId &l) { return P::ROWS == 2 ? (rank ? rank[g.M + l.slot] : g.M + l.slot) : -1; };
+    (void)R;
+    std::vector<uint32_t> E(NT), carry(NT), uend(NT), ufirst(NT), gout(NT);
+    uint32_t cw[8];
+    // column 0 in the classic form (row-0 rule, main.cpp:171-182): its jump base does not depend on any exchange
+    for (int tid = 0; tid < NT; ++tid) {
+        const LaneId l = lane_id(tid);
+        const int L = p.slot_len[l.slot];
+        load_profile(tid, l, 0);
+        if (l.t == 0 && L > 1) PW[tid][0] = P::add(PW[tid][0], P::splat(4 * p.sc.del));
+        if (l.t == T - 1 && L == 1) PW[tid][C - 1] = P::add(PW[tid][C - 1], P::splat(4 * p.sc.del));
+        lane_pre<P, C>(X[tid], deadu, PW[tid], deadu, l.t == 0, l.t == T - 1 && L == 1);
+        E[tid] = lane_post<P, C>(X[tid], PW[tid], P::splat(0 + 1), deadu, tr);
+    }
+    for (int tid = 0; tid < NT; ++tid) carry[tid] = (lane_id(tid).t == 0) ? deadu : P::max2(carry[tid - 1], E[tid - 1]);
+    int kpub = INT_MIN;                                  // key published for the column just swept
+    for (int tid = 0; tid < NT; ++tid) {
+        const LaneId l = lane_id(tid);
+        load_profile(tid, l, 1);
+        uend[tid] = lane_pass2_pre<P, C>(X[tid], carry[tid], cw, tr, PW[tid], deadu, l.t == T - 1 && p.slot_len[l.slot] == 1, &ufirst[tid]);
+        if (l.active)
+            for (int w = 0; w < g.CW; ++w) codes[tid / NTC][((size_t)0 * NTC + tid % NTC) * g.CW + w] = cw[w];
+        if (l.active && l.t == T - 1) {
+            if (tie_lo(l) >= 0) kpub = std::max(kpub, make_key(P::lo(uend[tid]), p.slot_endadd[l.slot], tie_lo(l)));
+            if (tie_hi(l) >= 0) kpub = std::max(kpub, make_key(P::hi(uend[tid]), p.slot_endadd[l.slot], tie_hi(l)));
+        }
+    }
+    for (int tid = 0; tid < NT; ++tid) {
+        const LaneId l = lane_id(tid);
+        const uint32_t prevU = (l.t == 0) ? deadu : uend[tid - 1];
+        X[tid][0] = lane_pre_first<P>(prevU, PW[tid][0], ufirst[tid], deadu, l.t == 0, C == 1 && l.t == T - 1 && p.slot_len[l.slot] == 1);
+    }
+    int jbase = p.sc.ins, jump0 = 0, kjprev = INT_MIN, adj = 0;
+    auto consume = [&](int i) {                          // K[i-1] -> J[i], jump operand of column i
+        const int k = std::max(kpub - adj * SD_KEY_ROWS, kjprev);
+        adj = 0;
+        const int vmax = key_value(k);
+        jr[0][i].j = vmax + jbase; jr[0][i].row = key_row(k);
+        jbase += p.sc.ins;
+        jump0 = 4 * (vmax + p.sc.del);
+    };
+    for (int i = 1; i < nmax; ++i) {
+        // a. J-independent part of column i: lane totals, windowed carry, chain
+        for (int tid = 0; tid < NT; ++tid) E[tid] = lat_total<P, C>(X[tid], tr);
+        for (int tid = 0; tid < NT; ++tid) {
+            const LaneId l = lane_id(tid);
+            uint32_t full = deadu, win = deadu;
+            for (int d = 1; d <= l.t; ++d) { full = P::max2(full, E[tid - d]); if (d <= g.scanw) win = P::max2(win, E[tid - d]); }
+            if (full != win && l.active) window_violation() = true;
+            carry[tid] = win;
+        }
+        int knew = INT_MIN;
+        for (int tid = 0; tid < NT; ++tid) {
+            const LaneId l = lane_id(tid);
+            gout[tid] = lat_chain<P, C>(X[tid], carry[tid], tr);
+            if (l.active && l.t == T - 1) {
+                if (tie_lo(l) >= 0) knew = std::max(knew, make_key(P::lo(gout[tid]), p.slot_endadd[l.slot], tie_lo(l)));
+                if (tie_hi(l) >= 0) knew = std::max(knew, make_key(P::hi(gout[tid]), p.slot_endadd[l.slot], tie_hi(l)));
+            }
+        }
+        // c. the key of column i-1 arrives: J[i]
+        consume(i);
+        kpub = knew;
+        kjprev = (jump0 >> 2) * SD_KEY_ROWS + kj[symbol(i)];
+        // d. merge, codes
+        for (int tid = 0; tid < NT; ++tid) {
+            const LaneId l = lane_id(tid);
+            uend[tid] = lat_merge<P, C>(X[tid], PT[tid], P::splat(jump0 + 1), cw, tr);
+            if (l.active)
+                for (int w = 0; w < g.CW; ++w) codes[tid / NTC][((size_t)i * NTC + tid % NTC) * g.CW + w] = cw[w];
+        }
+        // e. rebase (the key published above is still in the old frame: adj)
+        if (jump0 > p.lat_th || jump0 < -p.lat_th) {
+            for (int tid = 0; tid < NT; ++tid) lane_rebase<P, C>(X[tid], jump0);
+            jbase += jump0 >> 2; adj = jump0 >> 2; jump0 = 0;
+            kjprev = kj[symbol(i)];
+            for (int tid = 0; tid < NT; ++tid) uend[tid] = X[tid][C - 1];
+        }
+        // f. J-independent candidates of column i+1
+        for (int tid = 0; tid < NT; ++tid) {
+            const LaneId l = lane_id(tid);
+            load_profile(tid, l, i + 1);
+            const uint32_t prevU = (l.t == 0) ? deadu : uend[tid - 1];
+            lane_pre<P, C>(X[tid], prevU, PW[tid], deadu, l.t == 0, l.t == T - 1 && p.slot_len[l.slot] == 1);
+        }
+    }
+    consume(nmax);
+}
+
 template <class P> using CtaFn = void (*)(const Plan &, const Batch &, int, int, int, uint32_t *const *, JR *const *, const int *);
 
 template <class P, int C> CtaFn<P> pick_t(int T)
@@ -145,6 +280,18 @@ template <class P> CtaFn<P> pick(int C, int T)
     case 19: return pick_t<P, 19>(T); case 20: return pick_t<P, 20>(T); case 24: return pick_t<P, 24>(T); case 32: return pick_t<P, 32>(T);
     case 48: return pick_t<P, 48>(T);
     }
+    return nullptr;
+}
+
+template <class P> CtaFn<P> pick_lat(int C, int T)
+{
+    if (C == 6 && T == 32) return emu_cta_lat<P, 6, 32>;
+    if (C == 12 && T == 16) return emu_cta_lat<P, 12, 16>;
+    if (C == 12 && T == 32) return emu_cta_lat<P, 12, 32>;
+    if (C == 24 && T == 8) return emu_cta_lat<P, 24, 8>;
+    if (C == 24 && T == 16) return emu_cta_lat<P, 24, 16>;
+    if (C == 24 && T == 32) return emu_cta_lat<P, 24, 32>;
+    if (C == 48 && T == 32) return emu_cta_lat<P, 48, 32>;
     return nullptr;
 }
 
@@ -197,10 +344,19 @@ public:
             for (int q = 0; q < g.NG; ++q) cp[q] = codes_.data() + lay_.cta_code_off[g.NG > 1 ? c * g.NG + q : c];
             const int nmax = lay_.cta_nmax[g.NG > 1 ? c * g.NG : c];
             const int *rk = rank_.empty() ? nullptr : rank_.data() + (size_t)first * ms_.nrows();
+            if (g.lat) {
+                int kj[5];
+                if (rk) { lat_jump_keys(ms_, plan_.sc, rk, kj); emu_kj() = kj; } else emu_kj() = nullptr;
+                if (g.packed) pick_lat<Packed16>(g.C, g.T)(plan_, b, s0_ + first, cnt, nmax, cp.data(), jp.data(), rk);
+                else pick_lat<Scalar32>(g.C, g.T)(plan_, b, s0_ + first, cnt, nmax, cp.data(), jp.data(), rk);
+                emu_kj() = nullptr;
+                continue;
+            }
             if (g.packed) pick<Packed16>(g.C, g.T)(plan_, b, s0_ + first, cnt, nmax, cp.data(), jp.data(), rk);
             else pick<Scalar32>(g.C, g.T)(plan_, b, s0_ + first, cnt, nmax, cp.data(), jp.data(), rk);
         }
         overflowed_ = g.packed && EmuFlags::overflow();
+        if (window_violation()) { window_violation() = false; throw PlanError{"emulator: windowed deletion carry differs from the full prefix maximum (scan_window too small)"}; }
         if (bad_symbol()) throw PlanError{"segment contains a symbol outside ACGTN"};
         // the traceback compares segment and row symbols: bring the rows to the same (ASCII) alphabet
         rows_ascii_.resize(ms_.rows.size());

@@ -176,13 +176,90 @@ def test_config3_noisy_reads_sample():
     assert decompose_reads(rn, reads, mn, mons) == want
 
 
-def test_multi_gpu_output_identical():
-    if device_count() < 2:
-        pytest.skip("needs >= 2 GPUs")
-    rn, reads, mn, mons = synth.config3(n_reads=4, read_len=30000)
-    one = decompose_reads(rn, reads, mn, mons, devices=[0])
-    allg = decompose_reads(rn, reads, mn, mons, devices="all")
+@pytest.mark.parametrize("ngpu", [2, 4, 8])
+def test_multi_gpu_output_identical(ngpu):
+    # BASELINE config 2 (one 2 Mb array, 400 segments) split over the GPUs of the box by Engine::split: records of
+    # 1 / 2 / 4 / 8 devices must be identical, whatever sweep the planner picks for the smaller per-GPU shares
+    if device_count() < ngpu:
+        pytest.skip("needs >= %d GPUs" % ngpu)
+    rn, reads, mn, mons = synth.config2()
+    segs, _ = segment_reads(reads, 5000, 500)
+    d1 = Decomposer(mons, devices=[0])
+    r1, o1 = d1.decompose(segs)
+    d1.close()
+    dn = Decomposer(mons, devices=list(range(ngpu)))
+    rn_, on_ = dn.decompose(segs)
+    st = dn.stats()
+    dn.stage(segs)
+    dn.run_staged()
+    rs, os_ = dn.fetch_staged()
+    dn.close()
+    assert st["n_devices"] == ngpu and sum(st["dev_segments"]) == len(segs) and min(st["dev_segments"]) > 0
+    assert (rn_ == r1).all() and (on_ == o1).all()
+    assert (rs == r1).all() and (os_ == o1).all()
+    # and through the drop-in binary: SD_DEVICES=all, whole raw TSV
+    rn3, reads3, mn3, mons3 = synth.config3(n_reads=4, read_len=30000)
+    one = decompose_reads(rn3, reads3, mn3, mons3, devices=[0])
+    allg = decompose_reads(rn3, reads3, mn3, mons3, devices=list(range(ngpu)))
     assert one == allg
+
+
+LAT_SUBSET = ("multi_read", "scoring_-3_-2_-4_2", "N_in_monomer", "dup_monomers_rev", "len_5501_default", "short_monomers", "N_in_read")
+
+
+@pytest.mark.parametrize("lat", ["0", "1"])
+def test_edge_cases_with_the_sweep_forced(lat):
+    # the planner picks the deferred-jump sweep for small batches; force both sweeps over a spread of the golden cases
+    names = {c["name"] for c in cases.load_cases()}
+    extra = ("ed_thr_0", "ed_thr_12", "ed_thr_dups", "ed_thr_short_monomers", "ed_thr_fuzz_00_AT", "ed_thr_fuzz_02_ACGT", "ed_thr_fuzz_03_ACGTN",
+             "tiny_alphabet_ties", "poly_A", "len1_monomer_only", "scoring_-6_-6_-6_1", "scoring_-1_0_-1_1")
+    picked = [c for c in cases.load_cases() if c["name"] in LAT_SUBSET + extra or c["name"].startswith("fuzz_0")]
+    assert len(picked) >= 25 and set(LAT_SUBSET + extra) <= names
+    for case in picked:
+        cases.check_case(cases.DP_CUDA, case, env={"SD_LAT": lat})
+
+
+@pytest.mark.parametrize("geom,warps", [("6,32,1", "4"), ("6,32,1", "1"), ("6,32,1", "2"), ("12,16,1", "3"), ("12,16,1", "1"), ("24,8,1", "0"),
+                                        ("24,8,1", "1"), ("12,32,1", "2"), ("24,16,1", "1"), ("24,32,1", "2"), ("48,32,1", "1")])
+@pytest.mark.parametrize("force32", ["0", "1"])
+def test_deferred_jump_sweep_every_geometry(geom, warps, force32):
+    # cluster shapes from one CTA per segment down to one warp per CTA (up to 8 CTAs exchanging keys through DSMEM)
+    picked = [c for c in cases.load_cases() if c["name"] in ("multi_read", "scoring_-3_-2_-4_2", "N_in_monomer", "dup_monomers_rev")]
+    for case in picked:
+        cases.check_case(cases.DP_CUDA, case, env={"SD_LAT": "1", "SD_GEOM": geom, "SD_LAT_WARPS": warps, "SD_FORCE_S32": force32})
+
+
+def test_deferred_jump_sweep_config1_and_config2_sample():
+    # config 1 in full (19 segments: the planner's own choice must be the deferred-jump sweep) and 40 segments of config 2
+    names, mons = synth.load_dxz1()
+    read = open(os.path.join(cases.GOLDEN, "config1_read.fa")).read().split("\n", 1)[1].replace("\n", "")
+    segs, _ = segment_reads([read], 5000, 500)
+    d = Decomposer(mons, devices=[0])
+    recs, off = d.decompose(segs)
+    assert d.stats()["lat"] == 1
+    d.close()
+    os.environ["SD_LAT"] = "0"
+    try:
+        d0 = Decomposer(mons, devices=[0])
+        r0, o0 = d0.decompose(segs)
+        assert d0.stats()["lat"] == 0
+        d0.close()
+    finally:
+        del os.environ["SD_LAT"]
+    assert (recs == r0).all() and (off == o0).all()
+    rn, reads, mn, mons2 = synth.config2()
+    segs2, _ = segment_reads(reads, 5000, 500)
+    for env in ({"SD_LAT": "1"}, {"SD_LAT": "1", "SD_GEOM": "12,16,1"}, {"SD_LAT": "1", "SD_GEOM": "24,8,1"}, {"SD_LAT": "1", "SD_GEOM": "6,32,1", "SD_LAT_WARPS": "2"}):
+        os.environ.update(env)
+        try:
+            d = Decomposer(mons2, devices=[0])
+            recs, off = d.decompose(segs2[100:140])
+            d.close()
+        finally:
+            for k in env:
+                del os.environ[k]
+        for j in (0, 17, 39):
+            assert as_tuples(recs[off[j]:off[j + 1]]) == sd_oracle.align_segment(segs2[100 + j], mons2)
 
 
 def test_int_peak_probe():

@@ -88,6 +88,38 @@ def test_emulated_kernels_small_slots(geom):
         assert got == want
 
 
+@pytest.mark.parametrize("case", cases.load_cases(), ids=lambda c: c["name"])
+def test_emulated_deferred_jump_sweep_on_edge_cases(case):
+    # the latency form of the recurrence (sweep_core.cuh: lat_*) forced on: same raw TSV, stderr and status
+    cases.check_case(cases.DP_EMU, case, env={"SD_LAT": "1"})
+
+
+@pytest.mark.parametrize("geom,warps", [("6,32,1", "4"), ("6,32,1", "1"), ("12,16,1", "3"), ("12,16,1", "1"), ("24,8,1", "0"), ("24,8,1", "1"),
+                                        ("12,32,1", "2"), ("24,16,1", "1"), ("24,32,1", "2"), ("48,32,1", "1")])
+@pytest.mark.parametrize("force32", ["0", "1"])
+def test_emulated_deferred_jump_sweep_every_geometry(geom, warps, force32):
+    # cluster shapes from one CTA per segment to one warp per CTA; the emulator also checks the windowed deletion carry
+    # against the full prefix maximum and traps 16-bit overflow
+    picked = [c for c in cases.load_cases() if c["name"] in ("multi_read", "scoring_-3_-2_-4_2", "N_in_monomer", "dup_monomers_rev")]
+    for case in picked:
+        cases.check_case(cases.DP_EMU, case, env={"SD_LAT": "1", "SD_GEOM": geom, "SD_LAT_WARPS": warps, "SD_FORCE_S32": force32})
+
+
+@pytest.mark.parametrize("alphabet", ["A", "AT", "ACGT", "ACGTN"])
+def test_emulated_deferred_jump_sweep_low_complexity(alphabet):
+    # long runs without a matching symbol stretch the carry window (plan.cpp: scan_window) to its maximum
+    for seed in range(5):
+        rn, rr, mn, mm = synth.random_case(900 + seed, alphabet=alphabet, mono_len=(1, 190), read_len=(1, 700))
+        for sc in ((-1, -1, -1, 1), (-1, -1, 1, -1), (-2, -3, 0, 0)):
+            want = sd_oracle.decompose_reads(rn, rr, mn, mm, part_size=300, overlap=80, scoring=sc)
+            os.environ["SD_LAT"] = "1"
+            try:
+                got = decompose_reads(rn, rr, mn, mm, part_size=300, overlap=80, scoring=sc, flavour=cases.EMU_LIB)
+            finally:
+                del os.environ["SD_LAT"]
+            assert got == want
+
+
 def test_emulated_config1_full_golden():
     st, out, err = sd_oracle.run_cli(cases.DP_EMU, os.path.join(cases.GOLDEN, "config1_read.fa"),
                                      os.path.join(cases.GOLDEN, "DXZ1_star_monomers.fa"))

@@ -25,17 +25,23 @@ def problems(draw):
                                     (-1, -1, -1, 5), (-7, -25, -3, 2), (1, -1, -1, 1), (-1, -2, 0, 0)]))
     geom = draw(st.sampled_from(["", "8,32,1", "12,16,2", "19,10,1", "24,8,3", "16,4,2", "8,8,5", "48,2,1"]))
     group = draw(st.sampled_from(["", "", "1", "4"]))
-    return monomers, segments, scoring, geom, group
+    # deferred-jump sweep: "" = the planner decides, "0" = classic, "C,T,warps-per-CTA" = forced
+    lat = draw(st.sampled_from(["", "0", "6,32,4", "6,32,1", "12,16,2", "24,8,1", "12,32,1"]))
+    return monomers, segments, scoring, geom, group, lat
 
 
 def run(flavour, problem):
-    monomers, segments, scoring, geom, group = problem
+    monomers, segments, scoring, geom, group, lat = problem
     lmax = max(len(m) for m in monomers)
     if geom:
         c, t, _ = map(int, geom.split(","))
         if c * t < lmax:
             geom = ""
-    for k, v in (("SD_GEOM", geom), ("SD_GROUP_SLOTS", group)):
+    env = {"SD_GEOM": geom, "SD_GROUP_SLOTS": group, "SD_LAT": lat, "SD_LAT_WARPS": ""}
+    if "," in lat:
+        c, t, w = lat.split(",")
+        env.update({"SD_LAT": "1", "SD_GEOM": "%s,%s,1" % (c, t), "SD_LAT_WARPS": w, "SD_GROUP_SLOTS": ""})
+    for k, v in env.items():
         if v:
             os.environ[k] = v
         else:
@@ -45,12 +51,12 @@ def run(flavour, problem):
         recs, off = d.decompose(segments)
         d.close()
     finally:
-        os.environ.pop("SD_GEOM", None)
-        os.environ.pop("SD_GROUP_SLOTS", None)
+        for k in env:
+            os.environ.pop(k, None)
     for j, s in enumerate(segments):
         want = sd_oracle.align_segment(s, monomers, scoring)
         got = [(int(r["row"]), int(r["start"]), int(r["end"]), float(r["score"])) for r in recs[off[j]:off[j + 1]]]
-        assert got == want, (monomers, s, scoring, geom, group)
+        assert got == want, (monomers, s, scoring, geom, group, lat)
 
 
 @settings(max_examples=120, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
