@@ -47,15 +47,24 @@ def dist_setup(n_gpus):
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
+        global CPU_GROUP
+        CPU_GROUP = dist.new_group(backend="gloo")
     return ws, rank, local
 
 
+CPU_GROUP = None
+
+
 def barrier_sync(ws):
+    """Barrier + device synchronisation on both sides.  The ranks meet on the CPU (gloo) first: a rank that waits for
+    rank 0 inside an NCCL barrier keeps a spinning kernel on its GPU, and in the strong-scaling leg rank 0 is running the
+    sweep on that very GPU -- the NCCL barrier proper is entered only once everybody has arrived."""
     import torch
     if torch.cuda.is_available():
         torch.cuda.synchronize()
     if ws > 1:
         import torch.distributed as dist
+        dist.barrier(group=CPU_GROUP)
         dist.barrier()
         if torch.cuda.is_available():
             torch.cuda.synchronize()

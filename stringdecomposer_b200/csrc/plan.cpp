@@ -151,7 +151,7 @@ static double geometry_cost(int C, int T, int NS, int NT, size_t smem_bytes, int
     const int lg = (T > 1) ? 32 - __builtin_clz((unsigned)(T - 1)) : 0;
     const int W = NT / 32;
     const double alu = 2.0 * (4.5 * C + 43.0 + 4.0 * lg);
-    const double lat = 350.0 + 9.0 * C + 30.0 * lg;
+    const double lat = 330.0 + 9.0 * C + (T <= 10 ? 30.0 : 75.0) * lg;     // measured: (19,10) 620, (24,8) 650, (12,16) 750 cycles
     int kmax = (int)std::min<size_t>((227u * 1024u) / std::max<size_t>(smem_bytes, 1), 32);
     kmax = std::min(kmax, 65536 / (NT * (2 * C + 40)));       // registers: X[C] + profile[C] + ~40
     kmax = std::min(kmax, 64 / W);
@@ -274,6 +274,7 @@ Plan make_plan(const MonomerSet &ms, const Scoring &sc, int max_seg_len, int64_t
                 if (C * T < ms.Lmax) continue;
                 if (!fC && C * T >= 2 * std::max(ms.Lmax, 96) && C * T > 192) continue;       // far too much padding
                 const int spw = 32 / T, ws = (nslots + spw - 1) / spw;                        // warps per segment
+                if (ws > 32) continue;                                                          // one exchange word per warp, polled by one lane each
                 const int W = scan_window(ms, sc, packed, C, T);
                 // warps per CTA: one per scheduler unless that needs more than 8 CTAs per cluster
                 int wc = lat_warps > 0 ? lat_warps : std::min(ws, 4);
@@ -284,13 +285,15 @@ Plan make_plan(const MonomerSet &ms, const Scoring &sc, int max_seg_len, int64_t
                 const int qp2c = ((2 * C + 3) / 4) | 1;
                 const size_t smem = (size_t)5 * sg * T * qp2c * 16 + (size_t)max_seg_len + 4096;
                 if (smem > kSmemLimit) continue;
-                const double alu = 2.0 * (5.5 * C + 45.0 + 2.0 * W);
-                const double floor_c = 150.0 + 8.0 * C + 6.0 * W + (ng > 1 ? 120.0 : 0.0);
-                const double wps = std::ceil((double)nseg * ws / (148.0 * 4.0));
-                const double cost = (double)std::max(max_seg_len, 1) * std::max(wps * alu / 0.85, floor_c);
+                // measured on the B200 (tools/lat_probe.py, 12 DXZ1 monomers): a lone warp per scheduler needs
+                // 392 + 9 C cycles per column -- (6,32) 446, (12,16) 495, (24,8) 607 --; warps that share a scheduler
+                // serialise on issue (~2 cycles per ALU instruction, 6.5 C + 60 of them) and jitter against each other
+                const int ctas_sm = (int)((nseg * ng + 147) / 148), wsched = (ctas_sm * wc + 3) / 4;
+                const double cost = (double)std::max(max_seg_len, 1) * std::max(392.0 + 9.0 * C + 2.0 * W, wsched * 2.0 * (6.5 * C + 60.0)) *
+                                    (wsched > 1 ? 1.18 : 1.0);
                 if (cost < lbest) { lbest = cost; lC = C; lT = T; lNT = wc * 32; lNG = ng; lSG = sg; lW = W; }
             }
-        const bool want = lat_mode > 0 || (lat_mode < 0 && lC && g.NG == 1 && nseg <= 2 * 148 && lbest < best);
+        const bool want = lat_mode > 0 || (lat_mode < 0 && lC && g.NG == 1 && nseg <= 2 * 148 && lbest < 0.97 * best);
         if (want && lC) {
             g.lat = 1; g.C = lC; g.T = lT; g.NS = 1; g.NT = lNT; g.NG = lNG; g.SG = lNG > 1 ? lSG : nslots; g.scanw = lW;
         } else if (lat_mode > 0) {

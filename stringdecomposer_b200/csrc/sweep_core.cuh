@@ -51,7 +51,14 @@ struct Packed16 {
     static constexpr int CELLS_PER_WORD = 8;   // backpointer cells per 32-bit word (per half: 8 x 2 bit)
     static constexpr uint32_t TAGMASK = 0x00030003u;
     static constexpr uint32_t ONE = 0x00010001u;
-    static SD_HD uint32_t splat(int v) { return ((uint32_t)v & 0xffffu) | ((uint32_t)v << 16); }
+    static SD_HD uint32_t splat(int v)
+    {
+#ifdef __CUDA_ARCH__
+        return __byte_perm((uint32_t)v, 0u, 0x1010);   // one PRMT
+#else
+        return ((uint32_t)v & 0xffffu) | ((uint32_t)v << 16);
+#endif
+    }
     static SD_HD int lo(uint32_t a) { return (int)(int16_t)(a & 0xffffu); }
     static SD_HD int hi(uint32_t a) { return (int)(int16_t)(a >> 16); }
     static SD_HD uint32_t addmax(uint32_t a, uint32_t b, uint32_t c) {   // per half: max(a+b, c)   VIADDMNMX.S16x2
@@ -243,25 +250,34 @@ SD_HD uint32_t lane_pre_first(uint32_t prevU, uint32_t pn0, uint32_t u_first, ui
 // of column i needs B[i-1] only through U[i-1]; B[i] enters in one VIADDMNMX per register at the very end.  The key of
 // the J-independent row ends (K0[i]) is therefore published one whole column before anybody needs it:
 //   B[i+1] <- max( K0[i] , B[i] + KJ[sym_i] )      KJ: static per symbol (best jump-derived row end)
-// Per register: VIADDMNMX (m), VIMNMX + LOP3 (chain), VIADDMNMX (merge), LOP3 (re-tag) + 1/2 VIMNMX3 (lane total)
-// = 5.5 ALU-pipe instructions (classic: 4.5) -- the price of taking the exchange latency off the critical path.
+// Per register: VIADDMNMX (m), LOP3 + VIMNMX/VIMNMX3 + VIMNMX (chain), VIADDMNMX (merge), LOP3 (re-tag) + 1/2 VIMNMX3
+// (lane total) = 6.5 ALU-pipe instructions (classic: 4.5) -- the price of taking the exchange latency off the
+// critical path; it pays only where the sweep is bound by latency, not by the ALU pipe.
 //
 // lat_total: the lane's contribution to the left candidates of the lanes on its right, tag 3.
 template <class P, int C> SD_HD uint32_t lat_total(const uint32_t (&M)[C], TagRegs tr) { return tree_max<P, C>(M) | tr.mask3; }
 
-// Deletion chain of the J-independent part, in place: X[kk] = m[kk] -> h0[kk] = max(g, m[kk]); g <- h0[kk] | 3.
-// carry: maximum of lat_total over the lanes on the left (tag 3; dead for the first lane of a slot).
+// Deletion chain of the J-independent part, in place: X[kk] = m[kk] -> h0[kk] = max(g[kk], m[kk]) with
+// g[kk] = max(carry, m[0..kk) | 3).  carry: maximum of lat_total over the lanes on the left (tag 3; dead for the first
+// lane of a slot).  The sweep runs at the latency of a lone warp, so the chain is kept shallow: the left candidates
+// m3 = m | 3 are formed up front (independent), the running maximum advances two cells per VIMNMX3, and h0 is taken off
+// the chain -- 3 instructions per register at a third of the depth of the obvious two-instruction recurrence.
 // Returns g after the last cell = (h0 of the lane's last cell) | 3.
 template <class P, int C>
 SD_HD uint32_t lat_chain(uint32_t (&X)[C], uint32_t carry, TagRegs tr)
 {
-    uint32_t g = carry;
+    uint32_t m3[C], g[C + 1];
 #pragma unroll
-    for (int kk = 0; kk < C; ++kk) {
-        X[kk] = P::max2(g, X[kk]);
-        g = X[kk] | tr.mask3;
+    for (int kk = 0; kk < C; ++kk) m3[kk] = X[kk] | tr.mask3;
+    g[0] = carry;
+#pragma unroll
+    for (int kk = 0; kk < C; kk += 2) {
+        g[kk + 1] = P::max2(g[kk], m3[kk]);
+        if (kk + 1 < C) g[kk + 2] = P::max3(g[kk], m3[kk], m3[kk + 1]);
     }
-    return g;
+#pragma unroll
+    for (int kk = 0; kk < C; ++kk) X[kk] = P::max2(g[kk], X[kk]);
+    return g[C];
 }
 
 // Merge with the jump-derived candidates and re-tag, in place: X[kk] = h0 -> U (tag-2 form); backpointer digits as in
@@ -296,6 +312,11 @@ constexpr int SD_KEY_ROWS = 4096;
 SD_HD int make_key(int z_end, int endadd, int row) { return ((z_end >> 2) + endadd) * SD_KEY_ROWS + (SD_KEY_ROWS - 1 - row); }
 SD_HD int key_const(int endadd, int row) { return endadd * SD_KEY_ROWS + (SD_KEY_ROWS - 1 - row); }      // key = (u>>2)*4096 + const
 SD_HD int key_value(int key) { return key >> 12; }
+// In the deferred form the J-independent part of a row end can be "minus infinity" (a length-1 row has nothing but its
+// jump candidate); with 32-bit lanes that value times 4096 would wrap, so it is clamped before the key is formed
+// (real cells stay far above: |rel| < 2^17 by the planner's score bound).
+constexpr int SD_KEY_FLOOR = -(1 << 20);
+SD_HD int key_floor(int z) { return z > SD_KEY_FLOOR ? z : SD_KEY_FLOOR; }
 SD_HD int key_row(int key) { return SD_KEY_ROWS - 1 - (key & (SD_KEY_ROWS - 1)); }
 
 // --------------------------------------------------------------------------------------------

@@ -22,6 +22,7 @@ struct SweepArgs {
     const int *rank;        // --ed_thr pre-filter: [segment][row] position in the filtered list, -1 = filtered out; or null
     int *bad_symbol;        // set to 1 when a segment holds a symbol outside ACGTN
     TagRegs tr;             // TAGMASK / ONE of the policy, passed as run-time values (sweep_core.cuh: TagRegs)
+    int scanw;              // carry window of the deletion scan (plan.cpp: scan_window)
 };
 
 // Exclusive prefix max of the lane maxima over the T lanes of a slot (deletion chain carried across lanes).
@@ -46,6 +47,27 @@ __device__ __forceinline__ uint32_t slot_scan(uint32_t E, int t, const int (&src
         if (t >= d) pv = P::max2(pv, o);
     }
     return pv;
+}
+
+// The same carry restricted to the W nearest lanes on the left (exact for W >= plan.cpp: scan_window): W independent
+// shuffles and a small max tree instead of T-1 shuffles or a log-depth scan.  W is a property of the monomer set, so
+// the branch is uniform over the whole launch.
+template <class P, int T>
+__device__ __forceinline__ uint32_t slot_scan_window(uint32_t E, int t, const int (&srcl)[T > 2 ? T - 2 : 1], uint32_t dead, int W)
+{
+    if (T >= 4 && W <= 2) {
+        uint32_t r[2];
+#pragma unroll
+        for (int d = 1; d <= 2; ++d) { r[d - 1] = __shfl_up_sync(0xffffffffu, E, d); if (t < d) r[d - 1] = dead; }
+        return P::max2(r[0], r[1]);
+    }
+    if (T >= 8 && W <= 4) {
+        uint32_t r[4];
+#pragma unroll
+        for (int d = 1; d <= 4; ++d) { r[d - 1] = __shfl_up_sync(0xffffffffu, E, d); if (t < d) r[d - 1] = dead; }
+        return tree_max<P, 4>(r);
+    }
+    return slot_scan<P, T>(E, t, srcl, dead);
 }
 
 // FAST: every warp serves exactly one segment and a segment has <= 4 warps: the per-column (score,row) key is
@@ -156,7 +178,7 @@ __global__ void sweep_kernel(const SweepArgs a)
         // profile of the next column (the symbol buffer is 0-padded, so the round after the last column is harmless);
         // issued here so that the loads fly during the scan
         load_profile(*cp++);
-        const uint32_t carry = slot_scan<P, T>(E, t, srcl, deadu);
+        const uint32_t carry = slot_scan_window<P, T>(E, t, srcl, deadu, a.scanw);
         constexpr int NW = (C + P::CELLS_PER_WORD - 1) / P::CELLS_PER_WORD;
         uint32_t cw[NW];
         uint32_t ufirst;
@@ -248,6 +270,7 @@ struct GroupArgs {
     int ins, del, deadz;
     TagRegs tr;
     int *bad_symbol;
+    int scanw;                                          // carry window of the deletion scan (plan.cpp: scan_window)
     unsigned long long *xbuf;                           // [ngslots][2][NG][NS] exchange slots, zeroed before the launch
     const int *rank;                                    // --ed_thr pre-filter ranks [segment][row] or null
     int ngslots;
@@ -351,7 +374,7 @@ __global__ void sweep_group_kernel(const GroupArgs a)
             const uint32_t E = lane_post<P, C>(X, pw, P::splat(jump0 + 1), deadu, tr);
             load_profile(sym_next);
             sym_next = symbol(i + 2);
-            const uint32_t carry = slot_scan<P, T>(E, t, srcl, deadu);
+            const uint32_t carry = slot_scan_window<P, T>(E, t, srcl, deadu, a.scanw);
             constexpr int NW = (C + P::CELLS_PER_WORD - 1) / P::CELLS_PER_WORD;
             uint32_t cw[NW];
             uint32_t ufirst;

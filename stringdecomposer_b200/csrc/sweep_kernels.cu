@@ -294,7 +294,12 @@ public:
         const int spw = 32 / g.T;
         fast_ = (g.nslots % spw == 0) && (g.nslots / spw <= 4) && g.NS <= 15;     // 15 named barriers besides barrier 0
         if (getenv("SD_NOFAST")) fast_ = false;
-        if (g.lat) kernel_ = g.packed ? sweep_lat_lookup_p16(g.C, g.T) : sweep_lat_lookup_s32(g.C, g.T);
+        lat_timing_ = false;
+        if (g.lat) {
+            kernel_ = g.packed ? sweep_lat_lookup_p16(g.C, g.T, g.scanw) : sweep_lat_lookup_s32(g.C, g.T, g.scanw);
+            if (getenv("SD_LAT_TIMING") && g.packed && sweep_lat_timing_lookup_p16(g.C, g.T, g.scanw)) { kernel_ = sweep_lat_timing_lookup_p16(g.C, g.T, g.scanw); lat_timing_ = true; }
+            if ((g.NT / 32) * g.NG > 32) throw PlanError{"internal: a deferred-jump cluster holds at most 32 warps"};
+        }
         else kernel_ = g.NG > 1 ? (g.packed ? sweep_group_lookup_p16(g.C, g.T) : sweep_group_lookup_s32(g.C, g.T))
                                 : kern(g.packed, g.C, g.T, fast_, fast_ && g.NS > 1);
         if (!kernel_) throw PlanError{"no sweep kernel compiled for this geometry"};
@@ -411,6 +416,7 @@ public:
         a.wps = fast_ ? g.nslots / spw : 1;
         a.kstride = fast_ ? g.NS * 4 : (g.NS + 3) / 4 * 4;
         a.tr = g.packed ? tag_regs<Packed16>() : tag_regs<Scalar32>();
+        a.scanw = getenv("SD_FULL_SCAN") ? 64 : g.scanw;
         const size_t smem = plan_.prof.size() * 4 + (size_t)3 * a.kstride * 4 + (size_t)g.NS * a.seg_stride;
         if (smem > (size_t)prop_.sharedMemPerBlockOptin) throw PlanError{"sweep geometry needs more shared memory than the SM has"};
         SD_CUDA(cudaFuncSetAttribute(kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -432,6 +438,7 @@ public:
         a.nslots = g.nslots; a.M = g.M; a.NT = g.NT; a.CW = g.CW; a.NG = g.NG; a.SG = g.SG; a.NS = g.NS;
         a.ins = plan_.sc.ins; a.del = plan_.sc.del; a.deadz = plan_.deadz;
         a.tr = g.packed ? tag_regs<Packed16>() : tag_regs<Scalar32>();
+        a.scanw = getenv("SD_FULL_SCAN") ? 64 : g.scanw;
         a.bad_symbol = d_flag_.as<int>(); a.error = d_flag_.as<int>() + 1;
         a.rank = filter_on_ ? d_rank_.as<int>() : nullptr;
         const int spw = 32 / g.T, wps = g.NT / 32;
@@ -471,8 +478,10 @@ public:
         a.tr = g.packed ? tag_regs<Packed16>() : tag_regs<Scalar32>();
         a.bad_symbol = d_flag_.as<int>(); a.error = d_flag_.as<int>() + 1;
         const int spw = 32 / g.T, wpc = g.NT / 32;
+        a.dbg = nullptr;
+        if (lat_timing_) { d_dbg_.need((size_t)nseg_ * g.NG * wpc * 64); a.dbg = d_dbg_.as<long long>(); SD_CUDA(cudaMemsetAsync(a.dbg, 0, (size_t)nseg_ * g.NG * wpc * 64, st_)); }
         const size_t sgt = (size_t)wpc * spw * g.T;
-        const size_t smem = (size_t)5 * sgt * plan_.qp2 * 16 + (size_t)LAT_NBUF * wpc * g.NG * 8 + 32 + (size_t)seg_stride;
+        const size_t smem = (size_t)5 * sgt * plan_.qp2 * 16 + (size_t)LAT_NBUF * 32 * 8 + 32 + (size_t)seg_stride;
         if (smem > (size_t)prop_.sharedMemPerBlockOptin) throw PlanError{"deferred-jump sweep needs more shared memory than the SM has"};
         SD_CUDA(cudaFuncSetAttribute(kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cudaLaunchConfig_t cfg{};
@@ -484,6 +493,17 @@ public:
         cfg.attrs = attr; cfg.numAttrs = 1;
         void *args[] = {(void *)&a};
         SD_CUDA(cudaLaunchKernelExC(&cfg, kernel_, args));
+        if (lat_timing_) {
+            const size_t nw = (size_t)nseg_ * g.NG * wpc;
+            std::vector<long long> h(nw * 8);
+            SD_CUDA(cudaMemcpyAsync(h.data(), a.dbg, nw * 64, cudaMemcpyDeviceToHost, st_));
+            SD_CUDA(cudaStreamSynchronize(st_));
+            double acc[6] = {0, 0, 0, 0, 0, 0}, cols = 0;
+            for (size_t w = 0; w < nw; ++w) { for (int q = 0; q < 6; ++q) acc[q] += (double)h[w * 8 + q]; cols += (double)h[w * 8 + 6]; }
+            fprintf(stderr, "[sd_b200 lat timing] cycles per column and warp: scan %.1f chain %.1f key+publish %.1f receive %.1f J+merge+store %.1f pre %.1f  (total %.1f)\n",
+                    acc[0] / cols, acc[1] / cols, acc[2] / cols, acc[3] / cols, acc[4] / cols, acc[5] / cols,
+                    (acc[0] + acc[1] + acc[2] + acc[3] + acc[4] + acc[5]) / cols);
+        }
     }
 
     void execute() override
@@ -558,7 +578,7 @@ private:
     cudaDeviceProp prop_{};
     Plan plan_; MonomerSet ms_;
     const void *kernel_ = nullptr;
-    bool fast_ = false;
+    bool fast_ = false, lat_timing_ = false;
     CtaLayout lay_;
     int s0_ = 0, s1_ = 0, nseg_ = 0, nmax_ = 0;
     std::vector<int64_t> hoff_, houtoff_;
@@ -572,7 +592,7 @@ private:
     DevBuf d_bases_, d_meta_;
     MetaView d_segoff_, d_ctanmax_, d_ctacode_, d_segj_, d_segrec_;     // slices of d_meta_
     std::vector<char> hmeta_;
-    DevBuf d_segkj_, d_flag_, d_xchg_, d_dist_, d_rank_, d_r2r_, d_codes_, d_jr_, d_scratch_, d_counts_, d_outoff_, d_dense_;
+    DevBuf d_dbg_, d_segkj_, d_flag_, d_xchg_, d_dist_, d_rank_, d_r2r_, d_codes_, d_jr_, d_scratch_, d_counts_, d_outoff_, d_dense_;
 };
 
 } // namespace

@@ -40,6 +40,7 @@ struct LatArgs {
     int seg_stride;                                     // bytes of the symbol buffer
     TagRegs tr;
     int *bad_symbol, *error;
+    long long *dbg;                                     // SD_LAT_TIMING: [warp][8] cycles per phase, summed over the columns
 };
 
 constexpr int LAT_NBUF = 4;
@@ -50,27 +51,29 @@ __device__ __forceinline__ void cluster_sync_all()
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-// Exclusive prefix maximum of the lane totals over the lanes of a slot, restricted to the W nearest lanes (exact by
-// construction of W, plan.cpp: scan_window; a larger window is always correct): 2, 4 or 8 independent shuffles -- one
-// shuffle latency -- instead of a log-depth scan; wider windows fall back to the scan.
-template <class P, int T, int N>
-__device__ __forceinline__ uint32_t flat_carry(uint32_t total, int t, uint32_t dead)
-{
-    uint32_t o[N];
-#pragma unroll
-    for (int d = 1; d <= N; ++d) {
-        o[d - 1] = __shfl_up_sync(0xffffffffu, total, d);
-        if (t < d) o[d - 1] = dead;
-    }
-    return tree_max<P, N>(o);
-}
-template <class P, int T>
-__device__ __forceinline__ uint32_t window_carry(uint32_t total, int t, int W, uint32_t dead)
+// Carry of the deletion chain into a lane: maximum of the lane totals of the WN nearest lanes on its left inside the slot
+// (exact when WN >= plan.cpp: scan_window; a larger window is always correct).  WN independent shuffles, each masked by
+// the shuffle's own "source lane in range" flag, then a ternary max tree -- one shuffle latency, no compares.
+// WN == 0: log-depth scan over the whole slot (any window).
+template <class P, int T, int WN>
+__device__ __forceinline__ uint32_t window_carry(uint32_t total, int t, uint32_t dead)
 {
     if (T == 1) return dead;
-    if (T >= 3 && W <= 2) return flat_carry<P, T, (T > 2 ? 2 : 1)>(total, t, dead);
-    if (T >= 5 && W <= 4) return flat_carry<P, T, (T > 4 ? 4 : 1)>(total, t, dead);
-    if (T >= 9 && W <= 8) return flat_carry<P, T, (T > 8 ? 8 : 1)>(total, t, dead);
+    if (WN > 0) {
+        constexpr int N = WN <= 0 ? 1 : (WN < T - 1 ? WN : T - 1);
+        uint32_t r[N];
+        if ((T & (T - 1)) == 0) {
+            constexpr int cseg = (32 - T) << 8;         // shfl.up clamp: segments of T lanes
+#pragma unroll
+            for (int d = 1; d <= N; ++d)
+                asm volatile("{ .reg .pred q; .reg .b32 v; shfl.sync.up.b32 v|q, %1, %2, %3, 0xffffffff; selp.b32 %0, v, %4, q; }"
+                             : "=r"(r[d - 1]) : "r"(total), "r"(d), "r"(cseg), "r"(dead));
+        } else {
+#pragma unroll
+            for (int d = 1; d <= N; ++d) { r[d - 1] = __shfl_up_sync(0xffffffffu, total, d); if (t < d) r[d - 1] = dead; }
+        }
+        return tree_max<P, N>(r);
+    }
     uint32_t pv = __shfl_up_sync(0xffffffffu, total, 1);
     if (t == 0) pv = dead;
 #pragma unroll
@@ -81,18 +84,18 @@ __device__ __forceinline__ uint32_t window_carry(uint32_t total, int t, int W, u
     return pv;
 }
 
-template <class P, int C, int T>
+template <class P, int C, int T, int WN, bool TM = false>
 __global__ void sweep_lat_kernel(const LatArgs a)
 {
     extern __shared__ uint4 smem_u4[];
     constexpr int SPW = 32 / T;
     const int NT = a.NT, NG = a.NG;
     const int wpc = NT >> 5;                             // warps per CTA
-    const int nwtot = wpc * NG;                          // warps of the segment (all CTAs of the cluster)
+    const int nwtot = wpc * NG;                          // warps of the segment (all CTAs of the cluster), <= 32
     const int sgt = wpc * SPW * T;                       // profile rows (slot lanes) kept by this CTA
     uint4 *sprof = smem_u4;                              // [5][sgt][qp2]
-    unsigned long long *xkey = reinterpret_cast<unsigned long long *>(sprof + (size_t)5 * sgt * a.qp2);   // [LAT_NBUF][nwtot]
-    int *skj = reinterpret_cast<int *>(xkey + LAT_NBUF * nwtot);                                             // [8]
+    unsigned long long *xkey = reinterpret_cast<unsigned long long *>(sprof + (size_t)5 * sgt * a.qp2);   // [LAT_NBUF][32]
+    int *skj = reinterpret_cast<int *>(xkey + LAT_NBUF * 32);                                                // [8]
     uint8_t *schar = reinterpret_cast<uint8_t *>(skj + 8);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -120,7 +123,7 @@ __global__ void sweep_lat_kernel(const LatArgs a)
         schar[x] = (uint8_t)code;
     }
     if (tid < 5) skj[tid] = a.seg_kj ? a.seg_kj[(size_t)seg * 5 + tid] : a.kj[tid];
-    for (int x = tid; x < LAT_NBUF * nwtot; x += NT) xkey[x] = 0ull;         // column tag 0 = nothing published
+    for (int x = tid; x < LAT_NBUF * 32; x += NT) xkey[x] = 0ull;            // column tag 0 = nothing published
     __syncthreads();
     if (NG > 1) cluster_sync_all();                      // nobody may store into a CTA that has not cleared its words yet
 
@@ -139,51 +142,54 @@ __global__ void sweep_lat_kernel(const LatArgs a)
     // key = (half << 10) + const: the row-end word is U (tag 2: 0x800 too much) in column 0, g (tag 3: 0xC00) afterwards
     const int kc_lo = (is_end && tb_lo >= 0) ? key_const(endadd, tb_lo) : -(1 << 30);
     const int kc_hi = (is_end && tb_hi >= 0) ? key_const(endadd, tb_hi) : -(1 << 30);
-    auto row_end_key = [&](uint32_t w, int tagbits) {
-        if (P::ROWS == 2) return max(((int)(w << 16) >> 6) + kc_lo - tagbits, ((int)(w & 0xffff0000u) >> 6) + kc_hi - tagbits);
-        return ((int)w << 10) + kc_lo - tagbits;
-    };
+    const int kc3_lo = kc_lo - 0xC00, kc3_hi = kc_hi - 0xC00;
     JR *jptr = a.jr + a.seg_j_off[seg];
     uint32_t *cptr = a.codes + a.cta_code_off[(size_t)seg * NG + grp] + (size_t)tid * a.CW;
     const size_t cstride = (size_t)NT * a.CW;
     const uint4 *myprof = sprof + (size_t)(ginst * T + t) * a.qp2;
     const int sym_stride = sgt * a.qp2;
 
-    // exchange: warp w of CTA c owns word [buf][c*wpc + w] in EVERY CTA of the cluster; lane c of a warp stores to CTA c
+    // exchange: warp w of CTA c owns word [buf][c*wpc + w] in EVERY CTA of the cluster; lane c of a warp stores to CTA c.
+    // Lanes >= nwtot read (again) the word of warp lane % nwtot, so that all lanes of a warp run the same poll.
     const uint32_t xkey_s = (uint32_t)__cvta_generic_to_shared(xkey);
-    uint32_t xremote = xkey_s;                            // this lane's destination CTA (lanes >= NG do not store)
+    uint32_t xremote = xkey_s;
     if (NG > 1 && lane < NG) asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(xremote) : "r"(xkey_s), "r"(lane));
-    const int mywarp = grp * wpc + warp;
+    // generic pointer of this lane's destination word in buffer 0: {shared::cluster offset, window high word}; the
+    // buffers are 256 B apart and the window is aligned, so the per-column offset is added to the low word only
+    uint32_t pub_lo, pub_hi;
+    {
+        unsigned long long gen;
+        asm volatile("{ .reg .u64 a; cvt.u64.u32 a, %1; cvta.shared::cluster.u64 %0, a; }" : "=l"(gen) : "r"(xremote + 8u * (uint32_t)(grp * wpc + warp)));
+        pub_lo = (uint32_t)gen; pub_hi = (uint32_t)(gen >> 32);
+    }
+    const uint32_t rcv_addr = xkey_s + 8u * (uint32_t)(lane % nwtot);
+    const bool pub_lane = lane < NG;
     // A warp publishes K0[i] and only then waits for K0[i-1]; when it publishes K0[i+3] everybody has published
     // K0[i+1], hence consumed K0[i-1] -- the word it overwrites (buffer (i+3) & 3 == (i-1) & 3) is no longer needed.
-    auto publish = [&](int col, int key) {
-        const unsigned long long v = ((unsigned long long)(unsigned)(col + 1) << 32) | (unsigned)key;
-        const uint32_t dst = xremote + 8u * (uint32_t)((col & (LAT_NBUF - 1)) * nwtot + mywarp);
-        if (lane < NG) asm volatile("st.relaxed.cluster.shared::cluster.b64 [%0], %1;" ::"r"(dst), "l"(v) : "memory");
+    auto publish = [&](uint32_t boff, int tag, int key) {                          // boff = 256 * (column & 3)
+        unsigned long long dst;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(dst) : "r"(pub_lo + boff), "r"(pub_hi));
+        if (pub_lane) asm volatile("st.relaxed.cluster.v2.b32 [%0], {%1, %2};" ::"l"(dst), "r"(key), "r"(tag) : "memory");
     };
-    auto receive = [&](int col) {
-        int k = INT_MIN;
-        const uint32_t want = (unsigned)(col + 1);
-        for (int w = lane; w < nwtot; w += 32) {
-            const uint32_t src = xkey_s + 8u * (uint32_t)((col & (LAT_NBUF - 1)) * nwtot + w);
-            unsigned long long v;
-            unsigned spins = 0;
-            for (;;) {
-                asm volatile("ld.volatile.shared.b64 %0, [%1];" : "=l"(v) : "r"(src) : "memory");
-                if ((uint32_t)(v >> 32) == want) break;
-                if (++spins > (1u << 24)) { *a.error = 1; break; }          // a partner died: fail instead of hanging
-            }
-            k = max(k, (int)(uint32_t)v);
+    // every lane polls one word; the warp leaves the loop together (a vote keeps the control flow convergent, so the
+    // shuffles and reductions further down need no divergence checks)
+    auto receive = [&](uint32_t boff, int tag) {
+        const uint32_t src = rcv_addr + boff;
+        int key, got;
+        unsigned spins = 0;
+        for (;;) {
+            asm volatile("ld.volatile.shared.v2.b32 {%0, %1}, [%2];" : "=r"(key), "=r"(got) : "r"(src) : "memory");
+            if (__all_sync(0xffffffffu, got == tag)) break;
+            if (++spins > (1u << 22)) { *a.error = 1; break; }                  // a partner died: fail instead of hanging
         }
-        return __reduce_max_sync(0xffffffffu, k);
+        return __reduce_max_sync(0xffffffffu, key);
     };
 
     constexpr int CQ2 = (2 * C + 3) / 4;                 // uint4 per profile row
     constexpr int QP_END = (C + 3) / 4;                  // uint4 [0, QP_END) hold p
     constexpr int QT_BEG = C / 4;                        // uint4 [QT_BEG, CQ2) hold PT
     uint32_t X[C], pw[C], pt[C];
-    auto load_p = [&](int sym) {
-        const uint4 *pp = myprof + sym * sym_stride;
+    auto load_p = [&](const uint4 *pp) {
 #pragma unroll
         for (int q = 0; q < QP_END; ++q) {
             const uint4 v = pp[q];
@@ -193,8 +199,7 @@ __global__ void sweep_lat_kernel(const LatArgs a)
             if (4 * q + 3 < C) pw[4 * q + 3] = v.w;
         }
     };
-    auto load_pt = [&](int sym) {
-        const uint4 *pp = myprof + sym * sym_stride;
+    auto load_pt = [&](const uint4 *pp) {
 #pragma unroll
         for (int q = QT_BEG; q < CQ2; ++q) {
             const uint4 v = pp[q];
@@ -221,25 +226,23 @@ __global__ void sweep_lat_kernel(const LatArgs a)
     // ---- column 0 in the classic form: its jump base (row-0 rule, main.cpp:171-182) needs no exchange -------------
 #pragma unroll
     for (int kk = 0; kk < C; ++kk) X[kk] = deadu;
-    load_p(schar[0]);
+    load_p(myprof + schar[0] * sym_stride);
     if (t == 0 && L > 1) pw[0] = P::add(pw[0], P::splat(4 * a.del));
     if (t == T - 1 && L == 1) pw[C - 1] = P::add(pw[C - 1], P::splat(4 * a.del));
     lane_pre<P, C>(X, deadu, pw, deadu, kill_first, kill_last);
     {
         const uint32_t E = lane_post<P, C>(X, pw, P::splat(1), deadu, tr);
-        uint32_t carry = __shfl_up_sync(0xffffffffu, E, 1);
-        if (t == 0) carry = deadu;
-#pragma unroll
-        for (int d = 1; d < T; d <<= 1) {
-            const uint32_t oth = __shfl_up_sync(0xffffffffu, carry, d);
-            if (t >= d) carry = P::max2(carry, oth);
-        }
-        load_p(schar[1]);
-        load_pt(schar[1]);
+        const uint32_t carry = window_carry<P, T, 0>(E, t, deadu);
+        const uint4 *pn = myprof + schar[1] * sym_stride;
+        load_p(pn);
+        load_pt(pn);
         uint32_t ufirst;
         const uint32_t uend = lane_pass2_pre<P, C>(X, carry, cw, tr, pw, deadu, kill_last, &ufirst);
         store_codes();
-        publish(0, __reduce_max_sync(0xffffffffu, row_end_key(uend, 0x800)));
+        int key;
+        if (P::ROWS == 2) key = max(((int)(uend << 16) >> 6) + kc_lo - 0x800, ((int)(uend & 0xffff0000u) >> 6) + kc_hi - 0x800);
+        else key = ((int)uend << 10) + kc_lo - 0x800;
+        publish(0u, 1, __reduce_max_sync(0xffffffffu, key));
         uint32_t prevU = deadu;
         if (T > 1) { prevU = __shfl_up_sync(0xffffffffu, uend, 1); if (t == 0) prevU = deadu; }
         X[0] = lane_pre_first<P>(prevU, pw[0], ufirst, deadu, kill_first, C == 1 && kill_last);
@@ -248,60 +251,108 @@ __global__ void sweep_lat_kernel(const LatArgs a)
     int jbase = a.ins;            // Bref + (i-1)*ins when J[i] is formed
     int jump0 = 0;                // 4*(B[i] - Bref)
     int kjprev = INT_MIN;         // key of the best jump-derived row end of the previous column (none in column 0)
-    int adj = 0;                  // rebase after the key in flight was published: that key is still in the old frame
-    const int th = a.lat_th;
+    int adjk = 0;                 // rebase after the key in flight was published: that key is still in the old frame
+    // loop invariants pinned in registers (ptxas would otherwise re-read them from the constant bank every column)
+    int th, th2, del4p1, ins;
+    TagRegs trr;
+    asm volatile("mov.b32 %0, %1;" : "=r"(th) : "r"(a.lat_th));
+    asm volatile("mov.b32 %0, %1;" : "=r"(th2) : "r"(2 * a.lat_th));
+    asm volatile("mov.b32 %0, %1;" : "=r"(del4p1) : "r"(4 * a.del + 1));
+    asm volatile("mov.b32 %0, %1;" : "=r"(ins) : "r"(a.ins));
+    asm volatile("mov.b32 %0, %1;" : "=r"(trr.mask3) : "r"(tr.mask3));
+    asm volatile("mov.b32 %0, %1;" : "=r"(trr.one) : "r"(tr.one));
+    long long tacc[7] = {0, 0, 0, 0, 0, 0, 0}, tprev = 0;
+    auto tick = [&](int ph) { if (TM) { const long long c = clock64(); tacc[ph] += c - tprev; tprev = c; } };
+    if (TM) tprev = clock64();
+    const uint8_t *sp = schar + 2;
+    int sym = schar[1];
+    uint32_t boff = 256u, boff_prev = 0u;                  // 256 * (i & 3), 256 * ((i-1) & 3)
 #pragma unroll 1
-    for (int i = 1; i < n; ++i) {
+    for (int i = 1; i < n; ++i, ++sp) {
         // J-independent part of column i (X holds max(diag, up))
-        const uint32_t total = lat_total<P, C>(X, tr);
-        const int sym = schar[i], symn = schar[i + 1];
-        const uint32_t carry = window_carry<P, T>(total, t, a.scanw, deadu);
-        load_p(symn);                                     // flies during the chain
-        const uint32_t g = lat_chain<P, C>(X, carry, tr);
-        publish(i, __reduce_max_sync(0xffffffffu, row_end_key(g, 0xC00)));
+        const uint32_t total = lat_total<P, C>(X, trr);
+        const int symn = sp[0];
+        const uint4 *pn = myprof + symn * sym_stride;
+        const uint32_t carry = window_carry<P, T, WN>(total, t, deadu);
+        tick(0);
+        load_p(pn);                                       // flies during the chain
+        const uint32_t g = lat_chain<P, C>(X, carry, trr);
+        tick(1);
+        int key;
+        if (P::ROWS == 2) key = max(((int)(g << 16) >> 6) + kc3_lo, ((int)(g & 0xffff0000u) >> 6) + kc3_hi);
+        else key = (key_floor((int)g) << 10) + kc3_lo;
+        publish(boff, i + 1, __reduce_max_sync(0xffffffffu, key));
+        tick(2);
 
         // J[i] from the key of column i-1, published one column ago
-        const int k2 = max(receive(i - 1) - adj * SD_KEY_ROWS, kjprev);
-        adj = 0;
+        const int k2 = max(receive(boff_prev, i) - adjk, kjprev);
+        tick(3);
+        boff_prev = boff; boff = (boff + 256u) & 0x300u;
+        adjk = 0;
         const int vmax = k2 >> 12;
-        if (j_writer) jptr[i] = JR{vmax + jbase, SD_KEY_ROWS - 1 - (k2 & (SD_KEY_ROWS - 1))};
-        jbase += a.ins;
-        jump0 = 4 * (vmax + a.del);
+        ++jptr;                                            // J[i], lowest row attaining it: one predicated 8-byte store
+        asm volatile("{ .reg .pred q; setp.ne.b32 q, %0, 0; @q st.global.v2.b32 [%1], {%2, %3}; }"
+                     ::"r"((int)j_writer), "l"(jptr), "r"(vmax + jbase), "r"(~k2 & (SD_KEY_ROWS - 1)) : "memory");
+        jbase += ins;
+        const int j1 = 4 * vmax + del4p1;                 // jump0 + 1
+        jump0 = j1 - 1;
         kjprev = (jump0 >> 2) * SD_KEY_ROWS + skj[sym];
 
-        lat_merge<P, C>(X, pt, P::splat(jump0 + 1), cw, tr);
+        lat_merge<P, C>(X, pt, P::splat(j1), cw, trr);
         store_codes();
-        load_pt(symn);
-        if (jump0 > th || jump0 < -th) {
+        tick(4);
+        load_pt(pn);
+        if ((unsigned)(jump0 + th) > (unsigned)th2) {
             lane_rebase<P, C>(X, jump0);
-            jbase += jump0 >> 2; adj = jump0 >> 2; jump0 = 0;
+            jbase += jump0 >> 2; adjk = (jump0 >> 2) * SD_KEY_ROWS; jump0 = 0;
             kjprev = skj[sym];
         }
+        sym = symn;
         // candidates of column i+1
         uint32_t prevU = deadu;
-        if (T > 1) { prevU = __shfl_up_sync(0xffffffffu, X[C - 1], 1); if (t == 0) prevU = deadu; }
+        if (T > 1 && (T & (T - 1)) == 0) {
+            constexpr int cseg = (32 - T) << 8;
+            asm volatile("{ .reg .pred q; .reg .b32 v; shfl.sync.up.b32 v|q, %1, 1, %2, 0xffffffff; selp.b32 %0, v, %3, q; }"
+                         : "=r"(prevU) : "r"(X[C - 1]), "r"(cseg), "r"(deadu));
+        } else if (T > 1) {
+            prevU = __shfl_up_sync(0xffffffffu, X[C - 1], 1);
+            if (t == 0) prevU = deadu;
+        }
         lane_pre<P, C>(X, prevU, pw, deadu, kill_first, kill_last);
+        tick(5);
+    }
+    if (TM && a.dbg && lane == 0) {
+#pragma unroll
+        for (int q = 0; q < 6; ++q) a.dbg[((size_t)blockIdx.x * wpc + warp) * 8 + q] = tacc[q];
+        a.dbg[((size_t)blockIdx.x * wpc + warp) * 8 + 6] = n - 1;
     }
     {
-        const int k2 = max(receive(n - 1) - adj * SD_KEY_ROWS, kjprev);
-        if (j_writer) jptr[n] = JR{(k2 >> 12) + jbase, SD_KEY_ROWS - 1 - (k2 & (SD_KEY_ROWS - 1))};
+        const int k2 = max(receive(256u * (uint32_t)((n - 1) & (LAT_NBUF - 1)), n) - adjk, kjprev);
+        if (j_writer) jptr[1] = JR{(k2 >> 12) + jbase, ~k2 & (SD_KEY_ROWS - 1)};          // jptr points at J[n-1]
     }
     if (NG > 1) cluster_sync_all();                      // no CTA may retire while partners still store into it
 }
 
-const void *sweep_lat_lookup_p16(int C, int T);
-const void *sweep_lat_lookup_s32(int C, int T);
+// WN: carry window the kernel is compiled for (0 = any, log-depth scan)
+const void *sweep_lat_lookup_p16(int C, int T, int W);
+const void *sweep_lat_lookup_s32(int C, int T, int W);
+const void *sweep_lat_timing_lookup_p16(int C, int T, int W);            // instrumented twins (SD_LAT_TIMING=1, exploration only)
+
+// smallest compiled window >= W
+#define SD_LAT_PICK(POLICY, CC, TT, TMF)                                                                             \
+    if (C == CC && T == TT) {                                                                                         \
+        if (W <= 2) return (const void *)sweep_lat_kernel<POLICY, CC, TT, 2, TMF>;                                    \
+        if (W <= 4) return (const void *)sweep_lat_kernel<POLICY, CC, TT, 4, TMF>;                                    \
+        if (W <= 8) return (const void *)sweep_lat_kernel<POLICY, CC, TT, 8, TMF>;                                    \
+        return (const void *)sweep_lat_kernel<POLICY, CC, TT, 0, TMF>;                                                \
+    }
 
 #define SD_INSTANTIATE_LAT(NAME, POLICY)                                                                             \
-    const void *NAME(int C, int T)                                                                                    \
+    const void *NAME(int C, int T, int W)                                                                             \
     {                                                                                                                 \
-        if (C == 6 && T == 32) return (const void *)sweep_lat_kernel<POLICY, 6, 32>;                                  \
-        if (C == 12 && T == 16) return (const void *)sweep_lat_kernel<POLICY, 12, 16>;                                \
-        if (C == 12 && T == 32) return (const void *)sweep_lat_kernel<POLICY, 12, 32>;                                \
-        if (C == 24 && T == 8) return (const void *)sweep_lat_kernel<POLICY, 24, 8>;                                  \
-        if (C == 24 && T == 16) return (const void *)sweep_lat_kernel<POLICY, 24, 16>;                                \
-        if (C == 24 && T == 32) return (const void *)sweep_lat_kernel<POLICY, 24, 32>;                                \
-        if (C == 48 && T == 32) return (const void *)sweep_lat_kernel<POLICY, 48, 32>;                                \
+        SD_LAT_PICK(POLICY, 6, 32, false) SD_LAT_PICK(POLICY, 12, 16, false) SD_LAT_PICK(POLICY, 12, 32, false)       \
+        SD_LAT_PICK(POLICY, 24, 8, false) SD_LAT_PICK(POLICY, 24, 16, false) SD_LAT_PICK(POLICY, 24, 32, false)       \
+        SD_LAT_PICK(POLICY, 48, 32, false)                                                                            \
         return nullptr;                                                                                               \
     }
 

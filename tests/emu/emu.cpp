@@ -16,6 +16,7 @@ namespace sdb {
 namespace {
 
 bool &bad_symbol() { static thread_local bool f = false; return f; }
+bool &window_violation() { static thread_local bool f = false; return f; }
 
 template <class P, int C, int T>
 void emu_cta(const Plan &p, const Batch &b, int seg_first, int nseg_cta, int nmax,
@@ -78,10 +79,14 @@ void emu_cta(const Plan &p, const Batch &b, int seg_first, int nseg_cta, int nma
             const LaneId l = lane_id(tid);
             E[tid] = lane_post<P, C>(X[tid], PW[tid], P::splat(jump0[l.seg_local] + 1), deadu, tag_regs<P>());
         }
-        // exclusive prefix max of E inside each slot (slot_scan on the device)
+        // exclusive prefix max of E inside each slot, restricted to the carry window (slot_scan_window on the device);
+        // the full prefix maximum is formed too and any difference on a live lane is reported
         for (int tid = 0; tid < NT; ++tid) {
             const LaneId l = lane_id(tid);
-            carry[tid] = (l.t == 0) ? deadu : P::max2(carry[tid - 1], E[tid - 1]);
+            uint32_t full = deadu, win = deadu;
+            for (int d = 1; d <= l.t; ++d) { full = P::max2(full, E[tid - d]); if (d <= std::max(g.scanw, 2)) win = P::max2(win, E[tid - d]); }
+            if (full != win && l.active) window_violation() = true;
+            carry[tid] = win;
         }
         std::fill(key.begin(), key.end(), INT_MIN);
         for (int tid = 0; tid < NT; ++tid) {
@@ -129,7 +134,6 @@ void emu_cta(const Plan &p, const Batch &b, int seg_first, int nseg_cta, int nma
 
 // Deferred-jump sweep (sweep_lat_kernel): the CTAs of the segment's cluster side by side; the only coupling between
 // the warps is the column key, published at column i and consumed at column i+1 (sweep_core.cuh: lat_*).
-bool &window_violation() { static thread_local bool f = false; return f; }
 const int *&emu_kj() { static thread_local const int *p = nullptr; return p; }
 
 template <class P, int C, int T>
@@ -229,7 +233,7 @@ void emu_cta_lat(const Plan &p, const Batch &b, int seg_first, int nseg_cta, int
             const LaneId l = lane_id(tid);
             gout[tid] = lat_chain<P, C>(X[tid], carry[tid], tr);
             if (l.active && l.t == T - 1) {
-                if (tie_lo(l) >= 0) knew = std::max(knew, make_key(P::lo(gout[tid]), p.slot_endadd[l.slot], tie_lo(l)));
+                if (tie_lo(l) >= 0) knew = std::max(knew, make_key(P::ROWS == 2 ? P::lo(gout[tid]) : key_floor(P::lo(gout[tid])), p.slot_endadd[l.slot], tie_lo(l)));
                 if (tie_hi(l) >= 0) knew = std::max(knew, make_key(P::hi(gout[tid]), p.slot_endadd[l.slot], tie_hi(l)));
             }
         }
