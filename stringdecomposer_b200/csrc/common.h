@@ -105,6 +105,12 @@ public:
     virtual void stage(const Batch &b, int seg_begin, int seg_end) = 0;
     virtual void execute() = 0;
     virtual void fetch(BatchResult &out) = 0;       // appends to out.recs / out.rec_off (out.rec_off starts as {0})
+    // Pipelined form: submit() enqueues copy-in, kernels and copy-out of one wave on wave slot `slot` and returns at
+    // once; collect() waits for that wave and appends its records.  A backend with wave_slots() == 2 overlaps the
+    // copies of one wave with the kernels of the other.  Default: the synchronous three-step path.
+    virtual int wave_slots() const { return 1; }
+    virtual void submit(int slot, const Batch &b, int seg_begin, int seg_end) { (void)slot; stage(b, seg_begin, seg_end); execute(); }
+    virtual void collect(int slot, BatchResult &out) { (void)slot; fetch(out); }
     double sweep_ms = 0, traceback_ms = 0, h2d_ms = 0, d2h_ms = 0;     // accumulated since reset_stats()
     int64_t h2d_bytes = 0, d2h_bytes = 0, launches = 0;
     int ed_thr_ = -1;

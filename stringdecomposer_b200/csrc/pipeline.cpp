@@ -6,7 +6,9 @@
 #include <cstring>
 #include <fstream>
 #include <chrono>
+#include <condition_variable>
 #include <future>
+#include <mutex>
 #include <thread>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -103,11 +105,75 @@ void postprocess(const std::vector<Record> &in, std::vector<Record> &out)
 }
 
 // ---------------------------------------------------------------------------------------------
+// One host thread per device, kept for the life of the engine: with kernels in the millisecond range the cost of
+// spawning and joining a thread per device and call (tens of microseconds each) would show in the multi-GPU numbers.
+class DevicePool {
+public:
+    explicit DevicePool(int n) : jobs_((size_t)n), state_((size_t)n, 0)
+    {
+        for (int d = 0; d < n; ++d) th_.emplace_back([this, d] { loop(d); });
+    }
+    ~DevicePool()
+    {
+        { std::lock_guard<std::mutex> l(mu_); stop_ = true; }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+    // runs fn(d) for every device d on that device's thread and waits for all of them
+    void run(const std::function<void(int)> &fn)
+    {
+        {
+            std::lock_guard<std::mutex> l(mu_);
+            for (size_t d = 0; d < jobs_.size(); ++d) { jobs_[d] = &fn; state_[d] = 1; }
+            pending_ = (int)jobs_.size();
+        }
+        cv_.notify_all();
+        std::unique_lock<std::mutex> l(mu_);
+        done_.wait(l, [this] { return pending_ == 0; });
+    }
+
+private:
+    void loop(int d)
+    {
+        for (;;) {
+            const std::function<void(int)> *fn;
+            {
+                std::unique_lock<std::mutex> l(mu_);
+                cv_.wait(l, [&] { return stop_ || state_[(size_t)d] == 1; });
+                if (stop_) return;
+                fn = jobs_[(size_t)d]; state_[(size_t)d] = 2;
+            }
+            (*fn)(d);
+            {
+                std::lock_guard<std::mutex> l(mu_);
+                state_[(size_t)d] = 0;
+                if (--pending_ == 0) done_.notify_all();
+            }
+        }
+    }
+    std::vector<std::thread> th_;
+    std::vector<const std::function<void(int)> *> jobs_;
+    std::vector<int> state_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    int pending_ = 0;
+    bool stop_ = false;
+};
+
 Engine::Engine(const std::vector<std::string> &forward_monomers, const Scoring &sc, std::vector<std::unique_ptr<Backend>> devs)
     : sc_(sc), devs_(std::move(devs))
 {
     build_monomer_set(forward_monomers, ms_);
     if (devs_.empty()) throw PlanError{"no device backend"};
+    if (devs_.size() > 1) pool_.reset(new DevicePool((int)devs_.size()));
+}
+
+Engine::~Engine() {}
+
+void Engine::on_devices(const std::function<void(int)> &fn)
+{
+    if (ndev() == 1) fn(0);
+    else pool_->run(fn);
 }
 
 void Engine::set_ed_thr(int ed_thr)
@@ -173,15 +239,14 @@ void Engine::decompose(const Batch &b, BatchResult &out)
             Backend &dev = *devs_[d];
             dev.reset_stats();
             part[d].rec_off.assign(1, 0);
-            int s0 = bounds[d];
             const int s_end = bounds[d + 1];
-            const int64_t budget = dev.wave_budget();
+            const int nsl = dev.wave_slots();
+            // waves: as many segments as fit the budget of one wave slot (with two slots each gets half the memory, and
+            // the copies of one wave overlap the kernels of the other)
+            const int64_t budget = dev.wave_budget() / nsl;
             const bool prof = getenv("SD_PROFILE") != nullptr;
-            auto now = [] { return std::chrono::steady_clock::now(); };
-            auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
-            while (s0 < s_end) {
-                const auto t0 = now();
-                // largest wave that fits the budget: grow geometrically, then shrink by bisection
+            std::vector<std::pair<int, int>> waves;
+            for (int s0 = bounds[d]; s0 < s_end;) {
                 int lo = std::min(s_end, s0 + plan_.g.NS), hi = s_end;
                 if (dev.wave_bytes(b, s0, hi) > budget) {
                     while (hi - lo > plan_.g.NS) {
@@ -191,25 +256,24 @@ void Engine::decompose(const Batch &b, BatchResult &out)
                     }
                     hi = lo;
                 }
-                const auto t1 = now();
-                dev.stage(b, s0, hi);
-                const auto t2 = now();
-                dev.execute();
-                const auto t3 = now();
-                dev.fetch(part[d]);
-                const auto t4 = now();
-                if (prof) fprintf(stderr, "[sd_b200 profile] dev %d wave [%d,%d): plan %.3f stage %.3f execute %.3f fetch %.3f ms\n", d, s0, hi, ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4));
+                waves.emplace_back(s0, hi);
                 s0 = hi;
             }
+            auto now = [] { return std::chrono::steady_clock::now(); };
+            auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+            const auto t0 = now();
+            for (size_t w = 0; w < waves.size(); ++w) {
+                dev.submit((int)(w % (size_t)nsl), b, waves[w].first, waves[w].second);
+                if (nsl == 1) dev.collect(0, part[d]);
+                else if (w >= 1) dev.collect((int)((w - 1) % (size_t)nsl), part[d]);
+            }
+            if (nsl > 1 && !waves.empty()) dev.collect((int)((waves.size() - 1) % (size_t)nsl), part[d]);
+            if (prof) fprintf(stderr, "[sd_b200 profile] dev %d: %zu wave(s), segments [%d,%d): %.3f ms host wall (sweep %.3f traceback %.3f h2d %.3f ms on the device)\n",
+                              d, waves.size(), bounds[d], s_end, ms(t0, now()), dev.sweep_ms, dev.traceback_ms, dev.h2d_ms);
         } catch (PlanError &e) { errs[d] = e.msg.empty() ? "error" : e.msg; }
         catch (std::exception &e) { errs[d] = e.what(); }
     };
-    if (nd == 1) work(0);
-    else {
-        std::vector<std::thread> th;
-        for (int d = 0; d < nd; ++d) th.emplace_back(work, d);
-        for (auto &t : th) t.join();
-    }
+    on_devices(work);
     for (int d = 0; d < nd; ++d) if (!errs[d].empty()) throw PlanError{errs[d]};
     double sw = 0, tb = 0, h2d = 0, d2h = 0;
     for (int d = 0; d < nd; ++d) {
@@ -245,12 +309,7 @@ void Engine::stage(const Batch &b)
         catch (PlanError &e) { errs[d] = e.msg.empty() ? "error" : e.msg; }
         catch (std::exception &e) { errs[d] = e.what(); }
     };
-    if (ndev() == 1) work(0);
-    else {
-        std::vector<std::thread> th;
-        for (int d = 0; d < ndev(); ++d) th.emplace_back(work, d);
-        for (auto &t : th) t.join();
-    }
+    on_devices(work);
     for (auto &e : errs) if (!e.empty()) throw PlanError{e};
 }
 
@@ -265,12 +324,7 @@ double Engine::run_staged()
         } catch (PlanError &e) { errs[d] = e.msg.empty() ? "error" : e.msg; }
         catch (std::exception &e) { errs[d] = e.what(); }
     };
-    if (ndev() == 1) work(0);
-    else {
-        std::vector<std::thread> th;
-        for (int d = 0; d < ndev(); ++d) th.emplace_back(work, d);
-        for (auto &t : th) t.join();
-    }
+    on_devices(work);
     for (auto &e : errs) if (!e.empty()) throw PlanError{e};
     double ms = 0, sw = 0, tb = 0;
     for (auto &d : devs_) { ms = std::max(ms, d->sweep_ms + d->traceback_ms); sw = std::max(sw, d->sweep_ms); tb = std::max(tb, d->traceback_ms); stats.launches += d->launches; }

@@ -31,9 +31,12 @@ struct EngineStats {
 };
 
 // Owns the monomer set, the scoring and one backend per device; decomposes batches of segments.
+class DevicePool;
+
 class Engine {
 public:
     Engine(const std::vector<std::string> &forward_monomers, const Scoring &sc, std::vector<std::unique_ptr<Backend>> devs);
+    ~Engine();
     void decompose(const Batch &b, BatchResult &out);          // throws PlanError
     void stage(const Batch &b);                                 // whole batch resident, one wave per device
     double run_staged();                                        // returns kernel ms (max over devices)
@@ -47,6 +50,8 @@ private:
     void plan_for(const Batch &b);
     void split(const Batch &b, std::vector<int> &bounds) const;
     void note_split(const Batch &b, const std::vector<int> &bounds);
+    void on_devices(const std::function<void(int)> &fn);      // fn(d) on every device's own host thread
+    std::unique_ptr<DevicePool> pool_;
     MonomerSet ms_;
     Scoring sc_;
     std::vector<std::unique_ptr<Backend>> devs_;

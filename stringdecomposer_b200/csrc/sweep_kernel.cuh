@@ -25,49 +25,34 @@ struct SweepArgs {
     int scanw;              // carry window of the deletion scan (plan.cpp: scan_window)
 };
 
-// Exclusive prefix max of the lane maxima over the T lanes of a slot (deletion chain carried across lanes).
+// Carry of the deletion chain into a lane: exclusive prefix maximum of the lane maxima over the lanes of its slot.
+// Only the W nearest lanes on the left can matter (W = plan.cpp: scan_window, a property of the monomer set, so the
+// branches below are uniform over the whole launch): W independent shuffles and a small max tree -- one shuffle
+// latency -- instead of a scan over all T lanes.  Windows wider than 8 fall back to a log-depth scan.
+template <class P, int T, int N>
+__device__ __forceinline__ uint32_t flat_window(uint32_t E, int t, uint32_t dead)
+{
+    uint32_t r[N];
+#pragma unroll
+    for (int d = 1; d <= N; ++d) { r[d - 1] = __shfl_up_sync(0xffffffffu, E, d); if (t < d) r[d - 1] = dead; }
+    return tree_max<P, N>(r);
+}
 template <class P, int T>
-__device__ __forceinline__ uint32_t slot_scan(uint32_t E, int t, const int (&srcl)[T > 2 ? T - 2 : 1], uint32_t dead)
+__device__ __forceinline__ uint32_t slot_scan_window(uint32_t E, int t, uint32_t dead, int W)
 {
     if (T == 1) return dead;
+    if (T == 2) { const uint32_t pv = __shfl_up_sync(0xffffffffu, E, 1); return t == 0 ? dead : pv; }
+    if (T >= 3 && W <= 2) return flat_window<P, T, 2>(E, t, dead);
+    if (T >= 5 && W <= 4) return flat_window<P, T, (T >= 5 ? 4 : 1)>(E, t, dead);
+    if (T >= 9 && W <= 8) return flat_window<P, T, (T >= 9 ? 8 : 1)>(E, t, dead);
     uint32_t pv = __shfl_up_sync(0xffffffffu, E, 1);
     if (t == 0) pv = dead;
-    if (T == 2) return pv;
-    if (T <= 10) {
-        // flat: every lane pulls the (already exclusive) value of each lane further left in one round of independent
-        // shuffles; lanes without such a neighbour re-read lane 0 of their slot, whose value is "dead" (harmless)
-        uint32_t acc = pv;
-#pragma unroll
-        for (int d = 1; d <= T - 2; ++d) acc = P::max2(acc, __shfl_sync(0xffffffffu, pv, srcl[d - 1]));
-        return acc;
-    }
 #pragma unroll
     for (int d = 1; d < T; d <<= 1) {
         const uint32_t o = __shfl_up_sync(0xffffffffu, pv, d);
         if (t >= d) pv = P::max2(pv, o);
     }
     return pv;
-}
-
-// The same carry restricted to the W nearest lanes on the left (exact for W >= plan.cpp: scan_window): W independent
-// shuffles and a small max tree instead of T-1 shuffles or a log-depth scan.  W is a property of the monomer set, so
-// the branch is uniform over the whole launch.
-template <class P, int T>
-__device__ __forceinline__ uint32_t slot_scan_window(uint32_t E, int t, const int (&srcl)[T > 2 ? T - 2 : 1], uint32_t dead, int W)
-{
-    if (T >= 4 && W <= 2) {
-        uint32_t r[2];
-#pragma unroll
-        for (int d = 1; d <= 2; ++d) { r[d - 1] = __shfl_up_sync(0xffffffffu, E, d); if (t < d) r[d - 1] = dead; }
-        return P::max2(r[0], r[1]);
-    }
-    if (T >= 8 && W <= 4) {
-        uint32_t r[4];
-#pragma unroll
-        for (int d = 1; d <= 4; ++d) { r[d - 1] = __shfl_up_sync(0xffffffffu, E, d); if (t < d) r[d - 1] = dead; }
-        return tree_max<P, 4>(r);
-    }
-    return slot_scan<P, T>(E, t, srcl, dead);
 }
 
 // FAST: every warp serves exactly one segment and a segment has <= 4 warps: the per-column (score,row) key is
@@ -138,9 +123,6 @@ __global__ void sweep_kernel(const SweepArgs a)
     const uint8_t *cp = schar + seg_local * a.seg_stride;               // symbol of the column being prepared
     const uint4 *myprof = sprof + (size_t)(slot * T + t) * a.qp;
     const int sym_stride = a.nsl * a.qp;
-    int srcl[T > 2 ? T - 2 : 1];
-#pragma unroll
-    for (int d = 1; d <= T - 2; ++d) srcl[d - 1] = lane - min(d, t);
     // FAST: segment s of the CTA owns int4 row s of each key buffer, its warps write one int each.  Raw shared-space
     // addresses keep the exchange to one STS / one LDS.128 (no generic-address arithmetic in the loop).
     const int wseg = FAST ? warp / a.wps : 0;
@@ -178,7 +160,7 @@ __global__ void sweep_kernel(const SweepArgs a)
         // profile of the next column (the symbol buffer is 0-padded, so the round after the last column is harmless);
         // issued here so that the loads fly during the scan
         load_profile(*cp++);
-        const uint32_t carry = slot_scan_window<P, T>(E, t, srcl, deadu, a.scanw);
+        const uint32_t carry = slot_scan_window<P, T>(E, t, deadu, a.scanw);
         constexpr int NW = (C + P::CELLS_PER_WORD - 1) / P::CELLS_PER_WORD;
         uint32_t cw[NW];
         uint32_t ufirst;
@@ -312,9 +294,6 @@ __global__ void sweep_group_kernel(const GroupArgs a)
     const bool kill_first = (t == 0), kill_last = (t == T - 1 && L == 1);
     const uint4 *myprof = sprof + (size_t)(ginst * T + t) * a.qp;
     const int sym_stride = sgt * a.qp;
-    int srcl[T > 2 ? T - 2 : 1];
-#pragma unroll
-    for (int d = 1; d <= T - 2; ++d) srcl[d - 1] = lane - min(d, t);
     unsigned long long *xbuf = a.xbuf + (size_t)gslot * 2 * NG * NS;
     unsigned gcol = 0;                                   // columns this CTA group has exchanged so far
     __syncthreads();
@@ -374,7 +353,7 @@ __global__ void sweep_group_kernel(const GroupArgs a)
             const uint32_t E = lane_post<P, C>(X, pw, P::splat(jump0 + 1), deadu, tr);
             load_profile(sym_next);
             sym_next = symbol(i + 2);
-            const uint32_t carry = slot_scan_window<P, T>(E, t, srcl, deadu, a.scanw);
+            const uint32_t carry = slot_scan_window<P, T>(E, t, deadu, a.scanw);
             constexpr int NW = (C + P::CELLS_PER_WORD - 1) / P::CELLS_PER_WORD;
             uint32_t cw[NW];
             uint32_t ufirst;

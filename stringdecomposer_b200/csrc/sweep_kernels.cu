@@ -208,16 +208,46 @@ __global__ void hw_distance_kernel(const uint8_t *bases, const int64_t *seg_off,
     dist[x] = hw_distance(rows + row_off[r], row_off[r + 1] - row_off[r], bases + seg_off[s], (int)(seg_off[s + 1] - seg_off[s]));
 }
 
-// dense[out_off[s] + x] = scratch[seg_rec_off[s] + cnt-1-x]   (reversal of main.cpp:268)
-__global__ void gather_kernel(const Record *scratch, const int64_t *seg_rec_off, const int *counts, const int64_t *out_off,
-                              Record *dense, int nseg)
+// Compaction of the per-segment records into one dense array (in segment order, each segment reversed: main.cpp:268)
+// plus the total, so that one device->host copy brings a whole wave back.  One CTA: the exclusive prefix of the counts
+// is formed chunk by chunk with a block scan, then every warp copies segments.
+//   dense[prefix[s] + x] = scratch[seg_rec_off[s] + cnt[s]-1-x];   *total = sum of counts, or -1 if a traceback overflowed
+__global__ void __launch_bounds__(1024) gather_kernel(const Record *scratch, const int64_t *seg_rec_off, const int *counts, Record *dense,
+                                                      int nseg, int *total)
 {
-    const int s = blockIdx.x;
-    if (s >= nseg) return;
-    const int c = counts[s];
-    const Record *src = scratch + seg_rec_off[s];
-    Record *dst = dense + out_off[s];
-    for (int x = threadIdx.x; x < c; x += blockDim.x) dst[x] = src[c - 1 - x];
+    __shared__ int s_warp[32];
+    __shared__ int s_base, s_bad;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { s_base = 0; s_bad = 0; }
+    __syncthreads();
+    for (int c0 = 0; c0 < nseg; c0 += 1024) {
+        const int s = c0 + tid;
+        const int c = s < nseg ? counts[s] : 0;
+        if (c < 0) s_bad = 1;
+        int v = c < 0 ? 0 : c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += o; }
+        if (lane == 31) s_warp[warp] = v;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_warp[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, w, d); if (lane >= d) w += o; }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const int start = s_base + (warp ? s_warp[warp - 1] : 0) + v - (c < 0 ? 0 : c);     // exclusive prefix of segment s
+        // every thread copies its own segment (a few dozen 16-byte records)
+        if (s < nseg && c > 0) {
+            const Record *src = scratch + seg_rec_off[s];
+            Record *dst = dense + start;
+            for (int x = 0; x < c; ++x) dst[x] = src[c - 1 - x];
+        }
+        __syncthreads();
+        if (tid == 0) s_base += s_warp[31];
+        __syncthreads();
+    }
+    if (tid == 0) *total = s_bad ? -1 : s_base;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -264,6 +294,42 @@ struct DevBuf {
     template <class U> U *as() { return reinterpret_cast<U *>(p); }
     ~DevBuf() { if (p) cudaFree(p); }
 };
+struct PinnedBuf {          // page-locked host memory: the result block of a wave lands here with one asynchronous copy
+    void *p = nullptr; size_t cap = 0;
+    void need(size_t bytes)
+    {
+        if (bytes <= cap) return;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 4096;
+        SD_CUDA(cudaHostAlloc(&p, want, cudaHostAllocDefault));
+        cap = want;
+    }
+    template <class U> U *as() { return reinterpret_cast<U *>(p); }
+    ~PinnedBuf() { if (p) cudaFreeHost(p); }
+};
+struct MetaView { void *p = nullptr; template <class U> U *as() { return reinterpret_cast<U *>(p); } };
+
+// Result block of a wave in device memory: header, per-segment counts, then the dense records.
+//   int32 flag[2] (bad symbol, exchange time-out), int32 total, int32 pad, int32 counts[nseg] (padded to 16 B), Record dense[]
+constexpr size_t OUT_HDR = 16;
+inline size_t out_counts_bytes(int nseg) { return ((size_t)nseg * 4 + 15) & ~size_t(15); }
+
+// One wave in flight: its device buffers, its layout and its events.  Two slots per device let the host->device copy of
+// wave w+1 and the device->host copy of wave w-1 run while wave w computes (three streams: in, compute, out).
+struct WaveSlot {
+    DevBuf d_bases, d_meta, d_codes, d_jr, d_scratch, d_out, d_dist, d_rank, d_r2r, d_segkj, d_xchg, d_dbg;
+    MetaView d_segoff, d_ctanmax, d_ctacode, d_segj, d_segrec;     // slices of d_meta
+    PinnedBuf h_out;
+    std::vector<char> hmeta;
+    std::vector<int64_t> hoff;
+    std::vector<int> hdist, hrank, hr2r, hsegkj;
+    CtaLayout lay;
+    int s0 = 0, s1 = 0, nseg = 0, nmax = 0;
+    bool filter_on = false, staged = false;
+    size_t nb = 0, rec_guess = 0;
+    cudaEvent_t ev[6]{};            // 0 h2d begin, 1 h2d end, 2 sweep begin, 3 sweep end, 4 traceback end, 5 d2h end
+};
 
 class CudaBackend : public Backend {
 public:
@@ -271,7 +337,9 @@ public:
     {
         DeviceScope scope_(dev_); SD_CUDA(scope_.status);
         SD_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
-        for (auto &e : ev_) SD_CUDA(cudaEventCreate(&e));
+        SD_CUDA(cudaStreamCreateWithFlags(&st_in_, cudaStreamNonBlocking));
+        SD_CUDA(cudaStreamCreateWithFlags(&st_out_, cudaStreamNonBlocking));
+        for (auto &w : slot_) for (auto &e : w.ev) SD_CUDA(cudaEventCreate(&e));
         SD_CUDA(cudaGetDeviceProperties(&prop_, dev_));
         if (prop_.major != 10) throw PlanError{"CUDA device is not sm_100 class: this library carries sm_100a code only (no PTX for other architectures)"};
         size_t fr = 0, tot = 0;
@@ -281,8 +349,8 @@ public:
     ~CudaBackend() override
     {
         DeviceScope scope_(dev_);
-        for (auto &e : ev_) cudaEventDestroy(e);
-        cudaStreamDestroy(st_);
+        for (auto &w : slot_) for (auto &e : w.ev) cudaEventDestroy(e);
+        cudaStreamDestroy(st_); cudaStreamDestroy(st_in_); cudaStreamDestroy(st_out_);
     }
     const char *name() const override { return "cuda"; }
 
@@ -305,7 +373,8 @@ public:
         if (!kernel_) throw PlanError{"no sweep kernel compiled for this geometry"};
         cudaFuncAttributes fa;
         SD_CUDA(cudaFuncGetAttributes(&fa, kernel_));
-        if ((int64_t)fa.numRegs * g.NT * (g.NG > 1 ? g.NS : 1) > 65536) throw PlanError{"sweep geometry exceeds the register file (regs*threads > 64K)"};
+        // registers are handed out per warp in units of 8 per thread
+        if ((int64_t)((fa.numRegs + 7) / 8 * 8) * g.NT * (g.NG > 1 && !g.lat ? g.NS : 1) > 65536) throw PlanError{"sweep geometry exceeds the register file (regs*threads > 64K)"};
         const std::vector<uint32_t> &table = g.lat ? p.prof2 : p.prof;
         d_prof_.need(table.size() * 4);
         SD_CUDA(cudaMemcpyAsync(d_prof_.p, table.data(), table.size() * 4, cudaMemcpyHostToDevice, st_));
@@ -316,8 +385,6 @@ public:
         rows_ascii_.resize(ms.rows.size());           // the traceback compares row and segment symbols as text
         for (size_t x = 0; x < ms.rows.size(); ++x) rows_ascii_[x] = (uint8_t)"ACGTN"[ms.rows[x]];
         SD_CUDA(cudaMemcpyAsync(d_rows_.p, rows_ascii_.data(), rows_ascii_.size(), cudaMemcpyHostToDevice, st_));
-        d_flag_.need(16);
-        SD_CUDA(cudaMemsetAsync(d_flag_.p, 0, 16, st_));
         SD_CUDA(cudaMemcpyAsync(d_rowoff_.p, ms.row_off.data(), ms.row_off.size() * 4, cudaMemcpyHostToDevice, st_));
         SD_CUDA(cudaStreamSynchronize(st_));
     }
@@ -325,89 +392,95 @@ public:
     int64_t wave_bytes(const Batch &b, int s0, int s1) const override
     {
         CtaLayout l = make_cta_layout(plan_, b, s0, s1);
-        return l.cta_code_off.back() * 4 + l.seg_j_off.back() * 8 + l.seg_rec_off.back() * 32 + (b.off[s1] - b.off[s0]);
+        int64_t bytes = l.cta_code_off.back() * 4 + l.seg_j_off.back() * 8 + l.seg_rec_off.back() * 32 + (b.off[s1] - b.off[s0]);
+        if (ed_thr_ >= 0) bytes += (int64_t)(s1 - s0) * ms_.nrows() * 12;      // pre-filter tables: distance, rank, rank -> row
+        return bytes;
     }
     int64_t wave_budget() const override
     {
         if (const char *e = getenv("SD_WAVE_BYTES")) if (atoll(e) > 0) return atoll(e);
         return budget_;        // 85 % of the memory that was free when the backend was created (cudaMemGetInfo costs ms)
     }
+    int wave_slots() const override { return 2; }
 
-    void stage(const Batch &b, int s0, int s1) override
+    // ---- the three stages of a wave, each asynchronous on its own stream ----------------------------------------
+    void enqueue_h2d(WaveSlot &w, const Batch &b, int s0, int s1)
     {
-        DeviceScope scope_(dev_); SD_CUDA(scope_.status);
-        const Geometry &g = plan_.g;
-        s0_ = s0; s1_ = s1; nseg_ = s1 - s0;
-        lay_ = make_cta_layout(plan_, b, s0, s1);
-        nmax_ = 0;
-        for (int v : lay_.cta_nmax) nmax_ = std::max(nmax_, v);
+        w.s0 = s0; w.s1 = s1; w.nseg = s1 - s0;
+        w.lay = make_cta_layout(plan_, b, s0, s1);
+        w.nmax = 0;
+        for (int v : w.lay.cta_nmax) w.nmax = std::max(w.nmax, v);
         // inputs: bases of [s0,s1) and their offsets rebased to the staged buffer
         const int64_t base = b.off[s0];
-        const size_t nb = (size_t)(b.off[s1] - base);
-        hoff_.resize((size_t)nseg_ + 1);
-        for (int s = 0; s <= nseg_; ++s) hoff_[s] = b.off[s0 + s] - base;
-        d_bases_.need(nb + 16);
-        // the five small per-wave tables travel as one block: one pageable copy instead of five
-        const size_t msz[5] = {hoff_.size() * 8, lay_.cta_nmax.size() * 4, lay_.cta_code_off.size() * 8, lay_.seg_j_off.size() * 8,
-                               lay_.seg_rec_off.size() * 8};
-        const void *msrc[5] = {hoff_.data(), lay_.cta_nmax.data(), lay_.cta_code_off.data(), lay_.seg_j_off.data(), lay_.seg_rec_off.data()};
-        MetaView *mdst[5] = {&d_segoff_, &d_ctanmax_, &d_ctacode_, &d_segj_, &d_segrec_};
+        w.nb = (size_t)(b.off[s1] - base);
+        w.hoff.resize((size_t)w.nseg + 1);
+        for (int s = 0; s <= w.nseg; ++s) w.hoff[s] = b.off[s0 + s] - base;
+        w.d_bases.need(w.nb + 16);
+        // the five small per-wave tables travel as one block
+        const size_t msz[5] = {w.hoff.size() * 8, w.lay.cta_nmax.size() * 4, w.lay.cta_code_off.size() * 8, w.lay.seg_j_off.size() * 8,
+                               w.lay.seg_rec_off.size() * 8};
+        const void *msrc[5] = {w.hoff.data(), w.lay.cta_nmax.data(), w.lay.cta_code_off.data(), w.lay.seg_j_off.data(), w.lay.seg_rec_off.data()};
+        MetaView *mdst[5] = {&w.d_segoff, &w.d_ctanmax, &w.d_ctacode, &w.d_segj, &w.d_segrec};
         size_t mtotal = 0, moff[5];
         for (int x = 0; x < 5; ++x) { moff[x] = mtotal; mtotal += (msz[x] + 255) & ~size_t(255); }
-        d_meta_.need(mtotal + 16);
-        hmeta_.resize(mtotal);
-        for (int x = 0; x < 5; ++x) { memcpy(hmeta_.data() + moff[x], msrc[x], msz[x]); mdst[x]->p = d_meta_.as<char>() + moff[x]; }
-        d_codes_.need((size_t)lay_.cta_code_off.back() * 4 + 16);
-        d_jr_.need((size_t)lay_.seg_j_off.back() * sizeof(JR) + 16);
-        d_scratch_.need((size_t)lay_.seg_rec_off.back() * sizeof(Record) + 16);
-        d_counts_.need((size_t)nseg_ * 4 + 16); d_outoff_.need(((size_t)nseg_ + 1) * 8);
-        SD_CUDA(cudaEventRecord(ev_[0], st_));
-        SD_CUDA(cudaMemcpyAsync(d_bases_.p, b.text + base, nb, cudaMemcpyHostToDevice, st_));
-        SD_CUDA(cudaMemcpyAsync(d_meta_.p, hmeta_.data(), mtotal, cudaMemcpyHostToDevice, st_));
-        SD_CUDA(cudaEventRecord(ev_[1], st_));
-        SD_CUDA(cudaStreamSynchronize(st_));
-        float ms = 0; SD_CUDA(cudaEventElapsedTime(&ms, ev_[0], ev_[1]));
-        h2d_ms += ms;
-        h2d_bytes += (int64_t)(nb + hoff_.size() * 8 + lay_.cta_nmax.size() * 4 + lay_.cta_code_off.size() * 8 + lay_.seg_j_off.size() * 16);
-        filter_on_ = ed_thr_ >= 0;
-        if (filter_on_) {
-            // FilterMonomersForRead (main.cpp:135-149): distances on the device, (distance,row) sort on the host
-            const int R = ms_.nrows();
-            const size_t np = (size_t)nseg_ * R;
-            d_dist_.need(np * 4); d_rank_.need(np * 4); d_r2r_.need(np * 4);
-            hw_distance_kernel<<<(unsigned)((np + 63) / 64), 64, 0, st_>>>(d_bases_.as<uint8_t>(), d_segoff_.as<int64_t>(), nseg_,
-                                                                        d_rows_.as<uint8_t>(), d_rowoff_.as<int>(), R, d_dist_.as<int>());
-            SD_CUDA(cudaGetLastError());
-            hdist_.resize(np); hrank_.resize(np); hr2r_.resize(np);
-            SD_CUDA(cudaMemcpyAsync(hdist_.data(), d_dist_.p, np * 4, cudaMemcpyDeviceToHost, st_));
-            SD_CUDA(cudaStreamSynchronize(st_));
-            for (int s = 0; s < nseg_; ++s)
-                build_filter_tables(hdist_.data() + (size_t)s * R, R, ed_thr_, hrank_.data() + (size_t)s * R, hr2r_.data() + (size_t)s * R);
-            if (plan_.g.lat) {
-                hsegkj_.resize((size_t)nseg_ * 5);
-                for (int s = 0; s < nseg_; ++s) lat_jump_keys(ms_, plan_.sc, hrank_.data() + (size_t)s * R, hsegkj_.data() + (size_t)s * 5);
-                d_segkj_.need(hsegkj_.size() * 4);
-                SD_CUDA(cudaMemcpyAsync(d_segkj_.p, hsegkj_.data(), hsegkj_.size() * 4, cudaMemcpyHostToDevice, st_));
-            }
-            SD_CUDA(cudaMemcpyAsync(d_rank_.p, hrank_.data(), np * 4, cudaMemcpyHostToDevice, st_));
-            SD_CUDA(cudaMemcpyAsync(d_r2r_.p, hr2r_.data(), np * 4, cudaMemcpyHostToDevice, st_));
-            SD_CUDA(cudaStreamSynchronize(st_));
-            launches += 1;
-        }
-        (void)g;
+        w.d_meta.need(mtotal + 16);
+        w.hmeta.resize(mtotal);
+        for (int x = 0; x < 5; ++x) { memcpy(w.hmeta.data() + moff[x], msrc[x], msz[x]); mdst[x]->p = w.d_meta.as<char>() + moff[x]; }
+        w.d_codes.need((size_t)w.lay.cta_code_off.back() * 4 + 16);
+        w.d_jr.need((size_t)w.lay.seg_j_off.back() * sizeof(JR) + 16);
+        w.d_scratch.need((size_t)w.lay.seg_rec_off.back() * sizeof(Record) + 16);
+        // result block: counts + a guess of the dense records (an alignment per ~64 columns plus slack); fetch copies the
+        // rest in a second step in the rare case the guess was too small
+        w.rec_guess = (size_t)(w.nb / 48) + (size_t)w.nseg * 4 + 64;
+        w.d_out.need(OUT_HDR + out_counts_bytes(w.nseg) + (size_t)w.lay.seg_rec_off.back() * sizeof(Record) + 64);
+        SD_CUDA(cudaEventRecord(w.ev[0], st_in_));
+        SD_CUDA(cudaMemcpyAsync(w.d_bases.p, b.text + base, w.nb, cudaMemcpyHostToDevice, st_in_));
+        SD_CUDA(cudaMemcpyAsync(w.d_meta.p, w.hmeta.data(), mtotal, cudaMemcpyHostToDevice, st_in_));
+        SD_CUDA(cudaMemsetAsync(w.d_out.p, 0, OUT_HDR, st_in_));
+        SD_CUDA(cudaEventRecord(w.ev[1], st_in_));
+        h2d_bytes += (int64_t)(w.nb + mtotal);
+        w.filter_on = ed_thr_ >= 0;
+        if (w.filter_on) build_filter(w);
+        w.staged = true;
     }
 
-    void launch_single(int seg_stride)
+    // FilterMonomersForRead (main.cpp:135-149): distances on the device, (distance,row) sort on the host
+    void build_filter(WaveSlot &w)
+    {
+        const int R = ms_.nrows();
+        const size_t np = (size_t)w.nseg * R;
+        w.d_dist.need(np * 4); w.d_rank.need(np * 4); w.d_r2r.need(np * 4);
+        hw_distance_kernel<<<(unsigned)((np + 63) / 64), 64, 0, st_in_>>>(w.d_bases.as<uint8_t>(), w.d_segoff.as<int64_t>(), w.nseg,
+                                                                       d_rows_.as<uint8_t>(), d_rowoff_.as<int>(), R, w.d_dist.as<int>());
+        SD_CUDA(cudaGetLastError());
+        w.hdist.resize(np); w.hrank.resize(np); w.hr2r.resize(np);
+        SD_CUDA(cudaMemcpyAsync(w.hdist.data(), w.d_dist.p, np * 4, cudaMemcpyDeviceToHost, st_in_));
+        SD_CUDA(cudaStreamSynchronize(st_in_));
+        for (int s = 0; s < w.nseg; ++s)
+            build_filter_tables(w.hdist.data() + (size_t)s * R, R, ed_thr_, w.hrank.data() + (size_t)s * R, w.hr2r.data() + (size_t)s * R);
+        if (plan_.g.lat) {
+            w.hsegkj.resize((size_t)w.nseg * 5);
+            for (int s = 0; s < w.nseg; ++s) lat_jump_keys(ms_, plan_.sc, w.hrank.data() + (size_t)s * R, w.hsegkj.data() + (size_t)s * 5);
+            w.d_segkj.need(w.hsegkj.size() * 4);
+            SD_CUDA(cudaMemcpyAsync(w.d_segkj.p, w.hsegkj.data(), w.hsegkj.size() * 4, cudaMemcpyHostToDevice, st_in_));
+        }
+        SD_CUDA(cudaMemcpyAsync(w.d_rank.p, w.hrank.data(), np * 4, cudaMemcpyHostToDevice, st_in_));
+        SD_CUDA(cudaMemcpyAsync(w.d_r2r.p, w.hr2r.data(), np * 4, cudaMemcpyHostToDevice, st_in_));
+        SD_CUDA(cudaEventRecord(w.ev[1], st_in_));
+        launches += 1;
+    }
+
+    void launch_single(WaveSlot &w, int seg_stride)
     {
         const Geometry &g = plan_.g;
         SweepArgs a;
         a.prof = d_prof_.as<uint4>(); a.prof_u4 = (int)(plan_.prof.size() / 4);
-        a.bases = d_bases_.as<uint8_t>(); a.seg_off = d_segoff_.as<int64_t>();
-        a.nseg = nseg_;
-        a.cta_nmax = d_ctanmax_.as<int>(); a.cta_code_off = d_ctacode_.as<int64_t>(); a.seg_j_off = d_segj_.as<int64_t>();
-        a.codes = d_codes_.as<uint32_t>(); a.jr = d_jr_.as<JR>();
-        a.bad_symbol = d_flag_.as<int>();
-        a.rank = filter_on_ ? d_rank_.as<int>() : nullptr;
+        a.bases = w.d_bases.as<uint8_t>(); a.seg_off = w.d_segoff.as<int64_t>();
+        a.nseg = w.nseg;
+        a.cta_nmax = w.d_ctanmax.as<int>(); a.cta_code_off = w.d_ctacode.as<int64_t>(); a.seg_j_off = w.d_segj.as<int64_t>();
+        a.codes = w.d_codes.as<uint32_t>(); a.jr = w.d_jr.as<JR>();
+        a.bad_symbol = w.d_out.as<int>();
+        a.rank = w.filter_on ? w.d_rank.as<int>() : nullptr;
         a.slot_len = d_slotlen_.as<int>(); a.slot_endadd = d_slotend_.as<int>();
         a.nslots = g.nslots; a.M = g.M; a.NS = g.NS; a.NT = g.NT; a.CW = g.CW; a.nsl = plan_.nsl; a.qp = plan_.qp;
         a.ins = plan_.sc.ins; a.del = plan_.sc.del; a.deadz = plan_.deadz;
@@ -420,27 +493,26 @@ public:
         const size_t smem = plan_.prof.size() * 4 + (size_t)3 * a.kstride * 4 + (size_t)g.NS * a.seg_stride;
         if (smem > (size_t)prop_.sharedMemPerBlockOptin) throw PlanError{"sweep geometry needs more shared memory than the SM has"};
         SD_CUDA(cudaFuncSetAttribute(kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int nctas = (int)lay_.cta_nmax.size();
+        const int nctas = (int)w.lay.cta_nmax.size();
         void *args[] = {(void *)&a};
         SD_CUDA(cudaLaunchKernel(kernel_, dim3(nctas), dim3(g.NT), args, smem, st_));
     }
 
-    void launch_group(int seg_stride)
+    void launch_group(WaveSlot &w)
     {
-        (void)seg_stride;
         const Geometry &g = plan_.g;
         GroupArgs a;
         a.prof = d_prof_.as<uint4>(); a.nsl_total = plan_.nsl; a.qp = plan_.qp;
-        a.bases = d_bases_.as<uint8_t>(); a.seg_off = d_segoff_.as<int64_t>(); a.nseg = nseg_;
-        a.cta_code_off = d_ctacode_.as<int64_t>(); a.seg_j_off = d_segj_.as<int64_t>();
-        a.codes = d_codes_.as<uint32_t>(); a.jr = d_jr_.as<JR>();
+        a.bases = w.d_bases.as<uint8_t>(); a.seg_off = w.d_segoff.as<int64_t>(); a.nseg = w.nseg;
+        a.cta_code_off = w.d_ctacode.as<int64_t>(); a.seg_j_off = w.d_segj.as<int64_t>();
+        a.codes = w.d_codes.as<uint32_t>(); a.jr = w.d_jr.as<JR>();
         a.slot_len = d_slotlen_.as<int>(); a.slot_endadd = d_slotend_.as<int>();
         a.nslots = g.nslots; a.M = g.M; a.NT = g.NT; a.CW = g.CW; a.NG = g.NG; a.SG = g.SG; a.NS = g.NS;
         a.ins = plan_.sc.ins; a.del = plan_.sc.del; a.deadz = plan_.deadz;
         a.tr = g.packed ? tag_regs<Packed16>() : tag_regs<Scalar32>();
         a.scanw = getenv("SD_FULL_SCAN") ? 64 : g.scanw;
-        a.bad_symbol = d_flag_.as<int>(); a.error = d_flag_.as<int>() + 1;
-        a.rank = filter_on_ ? d_rank_.as<int>() : nullptr;
+        a.bad_symbol = w.d_out.as<int>(); a.error = w.d_out.as<int>() + 1;
+        a.rank = w.filter_on ? w.d_rank.as<int>() : nullptr;
         const int spw = 32 / g.T, wps = g.NT / 32;
         const size_t sgt = (size_t)wps * spw * g.T;
         const size_t smem = (size_t)5 * sgt * plan_.qp * 16 + ((size_t)g.NS * wps + g.NS + 8) * 4;
@@ -450,42 +522,42 @@ public:
         SD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel_, g.NS * g.NT, smem));
         const int capacity = per_sm * prop_.multiProcessorCount;
         if (capacity < g.NG) throw PlanError{"monomer set too large: the CTAs of one segment cannot be co-resident on this GPU"};
-        const int nblocks = (nseg_ + g.NS - 1) / g.NS;
+        const int nblocks = (w.nseg + g.NS - 1) / g.NS;
         a.ngslots = std::min(nblocks, capacity / g.NG);
         const size_t xwords = (size_t)a.ngslots * 2 * g.NG * g.NS;
-        d_xchg_.need(xwords * 8);
-        a.xbuf = d_xchg_.as<unsigned long long>();
+        w.d_xchg.need(xwords * 8);
+        a.xbuf = w.d_xchg.as<unsigned long long>();
         SD_CUDA(cudaMemsetAsync(a.xbuf, 0, xwords * 8, st_));    // epoch 0 = nothing published
         void *args[] = {(void *)&a};
         SD_CUDA(cudaLaunchCooperativeKernel(kernel_, dim3(a.ngslots * g.NG), dim3(g.NS * g.NT), args, smem, st_));
     }
 
-    void launch_lat(int seg_stride)
+    void launch_lat(WaveSlot &w, int seg_stride)
     {
         const Geometry &g = plan_.g;
         LatArgs a;
         a.prof2 = d_prof_.as<uint4>(); a.nsl_total = plan_.nsl; a.qp2 = plan_.qp2;
-        a.bases = d_bases_.as<uint8_t>(); a.seg_off = d_segoff_.as<int64_t>(); a.nseg = nseg_;
-        a.cta_code_off = d_ctacode_.as<int64_t>(); a.seg_j_off = d_segj_.as<int64_t>();
-        a.codes = d_codes_.as<uint32_t>(); a.jr = d_jr_.as<JR>();
+        a.bases = w.d_bases.as<uint8_t>(); a.seg_off = w.d_segoff.as<int64_t>(); a.nseg = w.nseg;
+        a.cta_code_off = w.d_ctacode.as<int64_t>(); a.seg_j_off = w.d_segj.as<int64_t>();
+        a.codes = w.d_codes.as<uint32_t>(); a.jr = w.d_jr.as<JR>();
         a.slot_len = d_slotlen_.as<int>(); a.slot_endadd = d_slotend_.as<int>();
         a.nslots = g.nslots; a.M = g.M; a.NT = g.NT; a.CW = g.CW; a.NG = g.NG; a.SG = g.SG;
         a.ins = plan_.sc.ins; a.del = plan_.sc.del; a.deadz = plan_.deadz; a.lat_th = plan_.lat_th; a.scanw = g.scanw;
         for (int q = 0; q < 5; ++q) a.kj[q] = plan_.kj[q];
-        a.seg_kj = filter_on_ ? d_segkj_.as<int>() : nullptr;
-        a.rank = filter_on_ ? d_rank_.as<int>() : nullptr;
+        a.seg_kj = w.filter_on ? w.d_segkj.as<int>() : nullptr;
+        a.rank = w.filter_on ? w.d_rank.as<int>() : nullptr;
         a.seg_stride = seg_stride;
         a.tr = g.packed ? tag_regs<Packed16>() : tag_regs<Scalar32>();
-        a.bad_symbol = d_flag_.as<int>(); a.error = d_flag_.as<int>() + 1;
+        a.bad_symbol = w.d_out.as<int>(); a.error = w.d_out.as<int>() + 1;
         const int spw = 32 / g.T, wpc = g.NT / 32;
         a.dbg = nullptr;
-        if (lat_timing_) { d_dbg_.need((size_t)nseg_ * g.NG * wpc * 64); a.dbg = d_dbg_.as<long long>(); SD_CUDA(cudaMemsetAsync(a.dbg, 0, (size_t)nseg_ * g.NG * wpc * 64, st_)); }
+        if (lat_timing_) { w.d_dbg.need((size_t)w.nseg * g.NG * wpc * 64); a.dbg = w.d_dbg.as<long long>(); SD_CUDA(cudaMemsetAsync(a.dbg, 0, (size_t)w.nseg * g.NG * wpc * 64, st_)); }
         const size_t sgt = (size_t)wpc * spw * g.T;
         const size_t smem = (size_t)5 * sgt * plan_.qp2 * 16 + (size_t)LAT_NBUF * 32 * 8 + 32 + (size_t)seg_stride;
         if (smem > (size_t)prop_.sharedMemPerBlockOptin) throw PlanError{"deferred-jump sweep needs more shared memory than the SM has"};
         SD_CUDA(cudaFuncSetAttribute(kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3((unsigned)(nseg_ * g.NG)); cfg.blockDim = dim3((unsigned)g.NT);
+        cfg.gridDim = dim3((unsigned)(w.nseg * g.NG)); cfg.blockDim = dim3((unsigned)g.NT);
         cfg.dynamicSmemBytes = smem; cfg.stream = st_;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -494,105 +566,159 @@ public:
         void *args[] = {(void *)&a};
         SD_CUDA(cudaLaunchKernelExC(&cfg, kernel_, args));
         if (lat_timing_) {
-            const size_t nw = (size_t)nseg_ * g.NG * wpc;
+            const size_t nw = (size_t)w.nseg * g.NG * wpc;
             std::vector<long long> h(nw * 8);
             SD_CUDA(cudaMemcpyAsync(h.data(), a.dbg, nw * 64, cudaMemcpyDeviceToHost, st_));
             SD_CUDA(cudaStreamSynchronize(st_));
             double acc[6] = {0, 0, 0, 0, 0, 0}, cols = 0;
-            for (size_t w = 0; w < nw; ++w) { for (int q = 0; q < 6; ++q) acc[q] += (double)h[w * 8 + q]; cols += (double)h[w * 8 + 6]; }
+            for (size_t x = 0; x < nw; ++x) { for (int q = 0; q < 6; ++q) acc[q] += (double)h[x * 8 + q]; cols += (double)h[x * 8 + 6]; }
             fprintf(stderr, "[sd_b200 lat timing] cycles per column and warp: scan %.1f chain %.1f key+publish %.1f receive %.1f J+merge+store %.1f pre %.1f  (total %.1f)\n",
                     acc[0] / cols, acc[1] / cols, acc[2] / cols, acc[3] / cols, acc[4] / cols, acc[5] / cols,
                     (acc[0] + acc[1] + acc[2] + acc[3] + acc[4] + acc[5]) / cols);
         }
     }
 
-    void execute() override
+    // sweep + traceback + compaction of the records into the result block; waits (on the device) for the wave's inputs
+    void enqueue_kernels(WaveSlot &w)
     {
-        DeviceScope scope_(dev_); SD_CUDA(scope_.status);
         const Geometry &g = plan_.g;
-        const int seg_stride = (nmax_ + 16) / 16 * 16;
-        SD_CUDA(cudaEventRecord(ev_[0], st_));
-        if (g.lat) launch_lat(seg_stride); else if (g.NG > 1) launch_group(seg_stride); else launch_single(seg_stride);
-        SD_CUDA(cudaEventRecord(ev_[1], st_));
+        const int seg_stride = (w.nmax + 16) / 16 * 16;
+        SD_CUDA(cudaStreamWaitEvent(st_, w.ev[1], 0));
+        SD_CUDA(cudaEventRecord(w.ev[2], st_));
+        if (g.lat) launch_lat(w, seg_stride); else if (g.NG > 1) launch_group(w); else launch_single(w, seg_stride);
+        SD_CUDA(cudaEventRecord(w.ev[3], st_));
         TbArgs t;
-        t.g = g; t.codes = d_codes_.as<uint32_t>(); t.cta_code_off = d_ctacode_.as<int64_t>(); t.jr = d_jr_.as<JR>();
-        t.seg_j_off = d_segj_.as<int64_t>();
-        t.bases = d_bases_.as<uint8_t>(); t.seg_off = d_segoff_.as<int64_t>(); t.nseg = nseg_;
+        t.g = g; t.codes = w.d_codes.as<uint32_t>(); t.cta_code_off = w.d_ctacode.as<int64_t>(); t.jr = w.d_jr.as<JR>();
+        t.seg_j_off = w.d_segj.as<int64_t>();
+        t.bases = w.d_bases.as<uint8_t>(); t.seg_off = w.d_segoff.as<int64_t>(); t.nseg = w.nseg;
         t.rows = d_rows_.as<uint8_t>(); t.row_off = d_rowoff_.as<int>();
         t.ins = plan_.sc.ins; t.del = plan_.sc.del; t.mismatch = plan_.sc.mismatch; t.match = plan_.sc.match;
-        t.scratch = d_scratch_.as<Record>(); t.seg_rec_off = d_segrec_.as<int64_t>(); t.counts = d_counts_.as<int>();
-        t.rank2row = filter_on_ ? d_r2r_.as<int>() : nullptr;
+        t.scratch = w.d_scratch.as<Record>(); t.seg_rec_off = w.d_segrec.as<int64_t>();
+        t.counts = reinterpret_cast<int *>(w.d_out.as<char>() + OUT_HDR);
+        t.rank2row = w.filter_on ? w.d_r2r.as<int>() : nullptr;
         t.invC = (65536 + g.C - 1) / g.C;
         for (int pos = 0; pos < g.C * g.T; ++pos)
             if (((pos * t.invC) >> 16) != pos / g.C) throw PlanError{"internal: reciprocal division inexact"};
-        traceback_kernel<<<(nseg_ + TB_WARPS - 1) / TB_WARPS, TB_WARPS * 32, 0, st_>>>(t);
+        traceback_kernel<<<(w.nseg + TB_WARPS - 1) / TB_WARPS, TB_WARPS * 32, 0, st_>>>(t);
         SD_CUDA(cudaGetLastError());
-        SD_CUDA(cudaEventRecord(ev_[2], st_));
-        int flag[2] = {0, 0};
-        SD_CUDA(cudaMemcpyAsync(flag, d_flag_.p, 8, cudaMemcpyDeviceToHost, st_));
-        SD_CUDA(cudaStreamSynchronize(st_));
-        if (flag[0] || flag[1]) {
-            SD_CUDA(cudaMemsetAsync(d_flag_.p, 0, 16, st_));
-            if (flag[1]) throw PlanError{"CUDA: sweep timed out waiting for a partner CTA (internal error)"};
-            throw PlanError{"segment contains a symbol outside ACGTN"};
-        }
-        float ms = 0;
-        SD_CUDA(cudaEventElapsedTime(&ms, ev_[0], ev_[1])); sweep_ms += ms;
-        SD_CUDA(cudaEventElapsedTime(&ms, ev_[1], ev_[2])); traceback_ms += ms;
+        SD_CUDA(cudaEventRecord(w.ev[4], st_));
         launches += 2;
     }
 
+    void enqueue_gather(WaveSlot &w)
+    {
+        char *ob = w.d_out.as<char>();
+        Record *dense = reinterpret_cast<Record *>(ob + OUT_HDR + out_counts_bytes(w.nseg));
+        gather_kernel<<<1, 1024, 0, st_>>>(w.d_scratch.as<Record>(), w.d_segrec.as<int64_t>(), reinterpret_cast<int *>(ob + OUT_HDR),
+                                          dense, w.nseg, reinterpret_cast<int *>(ob) + 2);
+        SD_CUDA(cudaGetLastError());
+        launches += 1;
+    }
+
+    // device -> host: header + counts + the guessed share of the records in one copy into page-locked memory
+    void enqueue_d2h(WaveSlot &w)
+    {
+        const size_t first = OUT_HDR + out_counts_bytes(w.nseg) + w.rec_guess * sizeof(Record);
+        const size_t cap = OUT_HDR + out_counts_bytes(w.nseg) + (size_t)w.lay.seg_rec_off.back() * sizeof(Record);
+        w.h_out.need(std::min(first, cap));
+        SD_CUDA(cudaEventRecord(w.ev[5], st_));                                    // compute done ...
+        SD_CUDA(cudaStreamWaitEvent(st_out_, w.ev[5], 0));                        // ... before the copy starts
+        SD_CUDA(cudaMemcpyAsync(w.h_out.p, w.d_out.p, std::min(first, cap), cudaMemcpyDeviceToHost, st_out_));
+        SD_CUDA(cudaEventRecord(w.ev[5], st_out_));
+    }
+
+    // wait for the wave, check its flags, append its records
+    void finish(WaveSlot &w, BatchResult &out)
+    {
+        SD_CUDA(cudaEventSynchronize(w.ev[5]));
+        const int *hdr = w.h_out.as<int>();
+        if (hdr[0] || hdr[1]) {
+            if (hdr[1]) throw PlanError{"CUDA: sweep timed out waiting for a partner CTA (internal error)"};
+            throw PlanError{"segment contains a symbol outside ACGTN"};
+        }
+        const int64_t total = hdr[2];
+        if (total < 0) throw PlanError{"traceback overflowed its record buffer (internal error)"};
+        const size_t rec_off = OUT_HDR + out_counts_bytes(w.nseg);
+        const size_t base = out.recs.size();
+        out.recs.resize(base + (size_t)total);
+        const size_t have = std::min<size_t>((size_t)total, w.rec_guess);
+        if (have) memcpy(out.recs.data() + base, w.h_out.as<char>() + rec_off, have * sizeof(Record));
+        if ((size_t)total > have) {              // the guess was too small (very short monomers): fetch the rest
+            SD_CUDA(cudaMemcpyAsync(out.recs.data() + base + have, w.d_out.as<char>() + rec_off + have * sizeof(Record),
+                                    ((size_t)total - have) * sizeof(Record), cudaMemcpyDeviceToHost, st_out_));
+            SD_CUDA(cudaStreamSynchronize(st_out_));
+        }
+        const int *cnt = reinterpret_cast<const int *>(w.h_out.as<char>() + OUT_HDR);
+        int64_t run = (int64_t)base;
+        for (int s = 0; s < w.nseg; ++s) { run += cnt[s]; out.rec_off.push_back(run); }
+        float ms = 0;
+        SD_CUDA(cudaEventElapsedTime(&ms, w.ev[0], w.ev[1])); h2d_ms += ms;
+        SD_CUDA(cudaEventElapsedTime(&ms, w.ev[2], w.ev[3])); sweep_ms += ms;
+        SD_CUDA(cudaEventElapsedTime(&ms, w.ev[3], w.ev[4])); traceback_ms += ms;
+        d2h_bytes += (int64_t)(rec_off + (size_t)total * sizeof(Record));
+        w.staged = false;
+    }
+
+    // ---- Backend interface --------------------------------------------------------------------------------------
+    void submit(int slot, const Batch &b, int s0, int s1) override
+    {
+        DeviceScope scope_(dev_); SD_CUDA(scope_.status);
+        WaveSlot &w = slot_[slot & 1];
+        enqueue_h2d(w, b, s0, s1);
+        enqueue_kernels(w);
+        enqueue_gather(w);
+        enqueue_d2h(w);
+    }
+    void collect(int slot, BatchResult &out) override
+    {
+        DeviceScope scope_(dev_); SD_CUDA(scope_.status);
+        finish(slot_[slot & 1], out);
+    }
+    // the resident path (sd_stage / sd_run_staged / sd_fetch_staged): one wave on slot 0, each step synchronous
+    void stage(const Batch &b, int s0, int s1) override
+    {
+        DeviceScope scope_(dev_); SD_CUDA(scope_.status);
+        enqueue_h2d(slot_[0], b, s0, s1);
+        SD_CUDA(cudaStreamSynchronize(st_in_));
+        float ms = 0; SD_CUDA(cudaEventElapsedTime(&ms, slot_[0].ev[0], slot_[0].ev[1])); h2d_ms += ms;
+    }
+    void execute() override
+    {
+        DeviceScope scope_(dev_); SD_CUDA(scope_.status);
+        WaveSlot &w = slot_[0];
+        SD_CUDA(cudaMemsetAsync(w.d_out.p, 0, OUT_HDR, st_));
+        enqueue_kernels(w);
+        int flag[2] = {0, 0};
+        SD_CUDA(cudaMemcpyAsync(flag, w.d_out.p, 8, cudaMemcpyDeviceToHost, st_));
+        SD_CUDA(cudaStreamSynchronize(st_));
+        if (flag[1]) throw PlanError{"CUDA: sweep timed out waiting for a partner CTA (internal error)"};
+        if (flag[0]) throw PlanError{"segment contains a symbol outside ACGTN"};
+        float ms = 0;
+        SD_CUDA(cudaEventElapsedTime(&ms, w.ev[2], w.ev[3])); sweep_ms += ms;
+        SD_CUDA(cudaEventElapsedTime(&ms, w.ev[3], w.ev[4])); traceback_ms += ms;
+    }
     void fetch(BatchResult &out) override
     {
         DeviceScope scope_(dev_); SD_CUDA(scope_.status);
-        hcnt_.resize((size_t)nseg_);
-        SD_CUDA(cudaEventRecord(ev_[0], st_));
-        SD_CUDA(cudaMemcpyAsync(hcnt_.data(), d_counts_.p, (size_t)nseg_ * 4, cudaMemcpyDeviceToHost, st_));
-        SD_CUDA(cudaStreamSynchronize(st_));
-        houtoff_.assign((size_t)nseg_ + 1, 0);
-        for (int s = 0; s < nseg_; ++s) {
-            if (hcnt_[s] < 0) throw PlanError{"traceback overflowed its record buffer (internal error)"};
-            houtoff_[s + 1] = houtoff_[s] + hcnt_[s];
-        }
-        const int64_t total = houtoff_[nseg_];
-        d_dense_.need((size_t)total * sizeof(Record) + 16);
-        SD_CUDA(cudaMemcpyAsync(d_outoff_.p, houtoff_.data(), houtoff_.size() * 8, cudaMemcpyHostToDevice, st_));
-        gather_kernel<<<nseg_, 64, 0, st_>>>(d_scratch_.as<Record>(), d_segrec_.as<int64_t>(), d_counts_.as<int>(),
-                                             d_outoff_.as<int64_t>(), d_dense_.as<Record>(), nseg_);
-        SD_CUDA(cudaGetLastError());
-        const size_t base = out.recs.size();
-        out.recs.resize(base + (size_t)total);
-        if (total) SD_CUDA(cudaMemcpyAsync(out.recs.data() + base, d_dense_.p, (size_t)total * sizeof(Record), cudaMemcpyDeviceToHost, st_));
-        SD_CUDA(cudaEventRecord(ev_[1], st_));
-        SD_CUDA(cudaStreamSynchronize(st_));
-        float ms = 0; SD_CUDA(cudaEventElapsedTime(&ms, ev_[0], ev_[1]));
-        d2h_ms += ms; d2h_bytes += (int64_t)nseg_ * 4 + total * (int64_t)sizeof(Record);
-        launches += 1;
-        for (int s = 0; s < nseg_; ++s) out.rec_off.push_back((int64_t)base + houtoff_[s + 1]);
+        WaveSlot &w = slot_[0];
+        const double sw = sweep_ms, tb = traceback_ms, h2 = h2d_ms;
+        enqueue_gather(w);
+        enqueue_d2h(w);
+        finish(w, out);
+        sweep_ms = sw; traceback_ms = tb; h2d_ms = h2;          // already accounted for by stage() / execute()
     }
 
 private:
     int dev_;
-    cudaStream_t st_{};
-    cudaEvent_t ev_[3]{};
+    cudaStream_t st_{}, st_in_{}, st_out_{};
     cudaDeviceProp prop_{};
     Plan plan_; MonomerSet ms_;
     const void *kernel_ = nullptr;
     bool fast_ = false, lat_timing_ = false;
-    CtaLayout lay_;
-    int s0_ = 0, s1_ = 0, nseg_ = 0, nmax_ = 0;
-    std::vector<int64_t> hoff_, houtoff_;
-    std::vector<int> hcnt_;
     std::vector<uint8_t> rows_ascii_;
-    std::vector<int> hdist_, hrank_, hr2r_, hsegkj_;
-    bool filter_on_ = false;
     int64_t budget_ = 0;
     DevBuf d_prof_, d_slotlen_, d_slotend_, d_rows_, d_rowoff_;
-    struct MetaView { void *p = nullptr; template <class U> U *as() { return reinterpret_cast<U *>(p); } };
-    DevBuf d_bases_, d_meta_;
-    MetaView d_segoff_, d_ctanmax_, d_ctacode_, d_segj_, d_segrec_;     // slices of d_meta_
-    std::vector<char> hmeta_;
-    DevBuf d_dbg_, d_segkj_, d_flag_, d_xchg_, d_dist_, d_rank_, d_r2r_, d_codes_, d_jr_, d_scratch_, d_counts_, d_outoff_, d_dense_;
+    WaveSlot slot_[2];
 };
 
 } // namespace
