@@ -20,7 +20,7 @@ import sys
 import time
 
 from . import _lib
-from .convert import load_fasta, add_rc_monomers, convert_tsv_native
+from .convert import load_fasta, add_rc_monomers, convert_raw_file_native
 
 
 def get_logger(filename, logger_name="StringDecomposer"):
@@ -41,7 +41,8 @@ def honor_scoring():
 
 
 def run(sequences, monomers, num_threads, scoring, batch_size, raw_file, ed_thr, overlap, logger, flavour="cuda"):
-    """main.py:186-197: run the DP on the two FASTA files, leave its stdout in raw_file and return it as text."""
+    """main.py:186-197: run the DP on the two FASTA files and leave its stdout in raw_file.  The reference then reads
+    that file back into one string (main.py:195-197); here the rescoring stage streams it in chunks of whole reads."""
     ins, dels, mm, match = (int(x) for x in scoring.split(","))
     if not honor_scoring():
         if (ins, dels, mm, match) != (-1, -1, -1, 1):
@@ -59,8 +60,7 @@ def run(sequences, monomers, num_threads, scoring, batch_size, raw_file, ed_thr,
     if st != 0:                                       # subprocess.run(..., check=True) raises at main.py:194
         lib = _lib.load_library(flavour)
         raise _lib.SdError(st, "dp failed with status %d: %s" % (st, (lib.sd_last_error(None) or b"").decode()))
-    with open(raw_file, "r") as f:
-        return f.read()
+    return raw_file
 
 
 def main(argv=None, flavour="cuda"):
@@ -88,7 +88,7 @@ def main(argv=None, flavour="cuda"):
 
     raw_fn = os.path.join(args.out_dir, args.out_file + "_raw.tsv")
     t0 = time.time()
-    raw = run(args.sequences, args.monomers, args.threads, args.scoring, args.batch_size, raw_fn, args.ed_thr, args.overlap,
+    run(args.sequences, args.monomers, args.threads, args.scoring, args.batch_size, raw_fn, args.ed_thr, args.overlap,
               logger, flavour=flavour)
     t1 = time.time()
     logger.info("Saved raw decomposition to " + raw_fn)
@@ -98,8 +98,8 @@ def main(argv=None, flavour="cuda"):
     logger.info("Transforming raw alignments...")
     out_fn = os.path.join(args.out_dir, args.out_file + ".tsv")
     stats = {}
-    convert_tsv_native(raw, reads, monomers, out_fn, int(args.min_identity), not args.second_best, device=args.device,
-                       flavour=flavour, stats=stats)
+    convert_raw_file_native(raw_fn, reads, monomers, out_fn, int(args.min_identity), not args.second_best, device=args.device,
+                            flavour=flavour, stats=stats)
     t2 = time.time()
     if stats.get("hirschberg_pairs"):
         logger.info("NOTE: %d interval/monomer pairs are large enough for edlib to leave its traceback for Hirschberg "

@@ -297,5 +297,38 @@ def convert_tsv_native(decomposition, reads, monomers, outfile, identity_th, lig
     return st
 
 
+def raw_chunks(path, max_bytes=32 << 20):
+    """The raw `dp` file in pieces of whole reads (the lines of a read are consecutive, main.py:173-184), so that the final
+    TSV can be produced without holding the whole raw text in memory the way main.py:195-197 does."""
+    with open(path, "r") as f:
+        buf, size, last = [], 0, None
+        for ln in f:
+            name = ln.split("\t", 1)[0].split()[0] if ln.strip() else last
+            if size >= max_bytes and name != last:
+                yield "".join(buf)
+                buf, size = [], 0
+            buf.append(ln)
+            size += len(ln)
+            last = name
+        if buf:
+            yield "".join(buf)
+
+
+def convert_raw_file_native(raw_path, reads, monomers, outfile, identity_th, light, device=0, flavour="cuda", stats=None,
+                            max_bytes=32 << 20):
+    """convert_tsv_native() fed from the raw file in bounded chunks of whole reads; same two output files."""
+    tot = {}
+    with open(outfile[:-len(".tsv")] + "_alt.tsv", "w") as fout_alt, open(outfile, "w") as fout:
+        fout.flush(); fout_alt.flush()
+        for chunk in raw_chunks(raw_path, max_bytes):
+            st = convert_raw(chunk, reads, monomers, fout.fileno(), fout_alt.fileno(), identity_th, light, device=device, flavour=flavour)
+            for k, v in st.items():
+                tot[k] = tot.get(k, 0) + v
+    if stats is not None:
+        for k in ("pairs", "kernel_ms", "hirschberg_pairs"):
+            stats[k] = stats.get(k, 0) + tot.get(k, 0)
+    return tot
+
+
 __all__ = ["LR_MODEL_COEF", "load_fasta", "add_rc_monomers", "convert_to_homo", "aai", "classify", "convert_read",
-           "print_read", "convert_tsv", "convert_tsv_native", "SdError"]
+           "print_read", "convert_tsv", "convert_tsv_native", "convert_raw_file_native", "raw_chunks", "SdError"]

@@ -9,6 +9,7 @@
 #include <condition_variable>
 #include <future>
 #include <mutex>
+#include <stdexcept>
 #include <thread>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -22,46 +23,89 @@ namespace sdb {
 // appended verbatim (main.cpp:327) -- the toupper in Seq's constructor only ever sees "" (main.cpp:29,325),
 // so lower case and '\r' are illegal symbols; alphabet check and messages main.cpp:330-344.
 // ---------------------------------------------------------------------------------------------
+// Chunked reader: the file is read in 4 MiB pieces and handed on line by line, so that neither pass over a reads file
+// needs more memory than one chunk (plus, in the second pass, the read being assembled).
+//   on_header(first, last)   a '>' line: [first,last) is the text after '>'
+//   on_line(first, last)     any other line (the reference appends it to the current record verbatim, main.cpp:327)
+template <class OnHeader, class OnLine>
+static bool scan_fasta(const std::string &path, OnHeader on_header, OnLine on_line)
+{
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) return false;                                   // the reference reads nothing from a missing file (main.cpp:315-319)
+    std::vector<char> buf((size_t)4 << 20);
+    std::string carry;                                      // unfinished last line of the previous chunk
+    auto emit = [&](const char *p, const char *le) { if (le > p && *p == '>') on_header(p + 1, le); else on_line(p, le); };
+    size_t got;
+    while ((got = fread(buf.data(), 1, buf.size(), f)) > 0) {
+        const char *p = buf.data(), *end = p + got;
+        while (p < end) {
+            const char *nl = static_cast<const char *>(memchr(p, '\n', (size_t)(end - p)));
+            if (!nl) { carry.append(p, end); break; }
+            if (!carry.empty()) { carry.append(p, nl); emit(carry.data(), carry.data() + carry.size()); carry.clear(); }
+            else emit(p, nl);
+            p = nl + 1;
+        }
+    }
+    if (!carry.empty()) emit(carry.data(), carry.data() + carry.size());      // last line without a newline, like getline
+    fclose(f);
+    return true;
+}
+
+static inline bool is_space(char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\n' || c == '\v' || c == '\f'; }
+static std::string header_name(const char *a, const char *le)      // name = first token (main.cpp:321-325)
+{
+    while (a < le && is_space(*a)) ++a;
+    const char *b = a;
+    while (b < le && !is_space(*b)) ++b;
+    return std::string(a, b);
+}
+
+// First pass over a FASTA file: names, lengths, the alphabet check and the N warning of load_fasta (main.cpp:330-344)
+// without keeping any sequence.  Returns 0, or 255 after writing the reference's error line to diag.
+struct FastaIndex { std::vector<std::string> names; std::vector<int64_t> lens; };
+static int index_fasta(const std::string &path, FastaIndex &out, std::string &diag)
+{
+    out.names.clear(); out.lens.clear();
+    bool has_n = false;
+    int bad_seq = -1; char bad_char = 0;
+    scan_fasta(path,
+        [&](const char *a, const char *le) { out.names.push_back(header_name(a, le)); out.lens.push_back(0); },
+        [&](const char *p, const char *le) {
+            if (out.lens.empty()) return;                   // text before the first header belongs to no record
+            if (bad_seq < 0)
+                for (const char *c = p; c < le; ++c) {
+                    if (base_code(*c) < 0) { bad_seq = (int)out.lens.size() - 1; bad_char = *c; break; }
+                    has_n |= *c == 'N';
+                }
+            out.lens.back() += le - p;
+        });
+    if (bad_seq >= 0) {
+        // the reference reports the first offending sequence in file order, and in it the first offending symbol
+        diag += "ERROR: Sequence " + out.names[(size_t)bad_seq] + " contains undefined symbol (not ACGT): " + std::string(1, bad_char) + "\n";
+        return 255;
+    }
+    if (has_n) diag += "WARNING: sequences in " + path + " contain N symbol. It will be counted as a separate symbol in scoring!\n";
+    return 0;
+}
+
 int load_fasta(const std::string &path, FastaSet &out, std::string &diag)
 {
     out.names.clear(); out.seqs.clear();
-    // whole file in one read, lines found with memchr: at GPU speed the reference's getline loop would dominate
-    std::string buf;
-    if (FILE *f = fopen(path.c_str(), "rb")) {
-        char chunk[1 << 16];
-        struct stat sb;
-        if (fstat(fileno(f), &sb) == 0 && sb.st_size > 0) buf.reserve((size_t)sb.st_size);
-        size_t got;
-        while ((got = fread(chunk, 1, sizeof chunk, f)) > 0) buf.append(chunk, got);
-        fclose(f);
-    }
-    auto ws = [](char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\n' || c == '\v' || c == '\f'; };
     bool has_n = false;
     int bad_seq = -1; char bad_char = 0;
-    const char *p = buf.data(), *end = p + buf.size();
-    while (p < end) {
-        const char *nl = static_cast<const char *>(memchr(p, '\n', (size_t)(end - p)));
-        const char *le = nl ? nl : end;                     // the line is [p, le), like getline
-        if (le > p && *p == '>') {                         // name = first token (main.cpp:321-325)
-            const char *a = p + 1;
-            while (a < le && ws(*a)) ++a;
-            const char *b = a;
-            while (b < le && !ws(*b)) ++b;
-            out.names.emplace_back(a, b);
-            out.seqs.emplace_back();
-        } else if (!out.seqs.empty()) {                     // lines appended raw (main.cpp:327), checked at :330-341
+    scan_fasta(path,
+        [&](const char *a, const char *le) { out.names.push_back(header_name(a, le)); out.seqs.emplace_back(); },
+        [&](const char *p, const char *le) {
+            if (out.seqs.empty()) return;
             if (bad_seq < 0)
                 for (const char *c = p; c < le; ++c) {
                     if (base_code(*c) < 0) { bad_seq = (int)out.seqs.size() - 1; bad_char = *c; break; }
                     has_n |= *c == 'N';
                 }
-            out.seqs.back().append(p, le);
-        }
-        p = nl ? nl + 1 : end;
-    }
+            out.seqs.back().append(p, le);                  // lines appended raw (main.cpp:327), checked at :330-341
+        });
     if (bad_seq >= 0) {
-        // the reference reports the first offending sequence in file order, and in it the first offending symbol
-        diag += "ERROR: Sequence " + out.names[bad_seq] + " contains undefined symbol (not ACGT): " + std::string(1, bad_char) + "\n";
+        diag += "ERROR: Sequence " + out.names[(size_t)bad_seq] + " contains undefined symbol (not ACGT): " + std::string(1, bad_char) + "\n";
         return 255;
     }
     if (has_n) diag += "WARNING: sequences in " + path + " contain N symbol. It will be counted as a separate symbol in scoring!\n";
@@ -182,11 +226,15 @@ void Engine::set_ed_thr(int ed_thr)
     for (auto &d : devs_) d->set_filter(ed_thr < 0 ? -1 : ed_thr);
 }
 
+void Engine::set_plan_hint(int max_seg_len, int64_t nseg_total) { hint_maxlen_ = max_seg_len; hint_nseg_ = nseg_total; }
+
 void Engine::plan_for(const Batch &b)
 {
     int maxlen = 0;
     for (int s = 0; s < b.nseg(); ++s) maxlen = std::max(maxlen, b.len(s));
-    const int64_t per_dev = (b.nseg() + ndev() - 1) / ndev();
+    int64_t per_dev = (b.nseg() + ndev() - 1) / ndev();
+    // a streamed run (run_files) announces the shape of the whole job: one plan for all its chunks
+    if (hint_nseg_ > 0 && maxlen <= hint_maxlen_) { maxlen = hint_maxlen_; per_dev = std::max<int64_t>(per_dev, std::min<int64_t>((hint_nseg_ + ndev() - 1) / ndev(), 1 << 20)); }
     // re-plan only when the shape changes enough to matter (geometry depends on segment count and length)
     if (have_plan_ && maxlen <= plan_maxlen_ && maxlen * 2 > plan_maxlen_ && per_dev == plan_nseg_) return;
     plan_ = make_plan(ms_, sc_, maxlen, per_dev);
@@ -371,6 +419,46 @@ struct FdWriter {
 
 } // namespace
 
+// A bounded hand-over between two stages of the host pipeline (reader -> device -> writer).
+template <class T> class Handoff {
+public:
+    explicit Handoff(size_t cap) : cap_(cap) {}
+    void push(T v)
+    {
+        std::unique_lock<std::mutex> l(mu_);
+        room_.wait(l, [&] { return q_.size() < cap_ || closed_; });
+        if (closed_) return;
+        q_.push_back(std::move(v));
+        item_.notify_one();
+    }
+    bool pop(T &out)                                        // false once the producer has finished and the queue is empty
+    {
+        std::unique_lock<std::mutex> l(mu_);
+        item_.wait(l, [&] { return !q_.empty() || done_ || closed_; });
+        if (q_.empty()) return false;
+        out = std::move(q_.front()); q_.erase(q_.begin());
+        room_.notify_one();
+        return true;
+    }
+    void finish() { std::lock_guard<std::mutex> l(mu_); done_ = true; item_.notify_all(); }
+    void close() { std::lock_guard<std::mutex> l(mu_); closed_ = true; q_.clear(); item_.notify_all(); room_.notify_all(); }   // a stage failed
+
+private:
+    size_t cap_;
+    std::vector<T> q_;
+    std::mutex mu_;
+    std::condition_variable item_, room_;
+    bool done_ = false, closed_ = false;
+};
+
+// A chunk of work: whole segments of consecutive reads (a long read may straddle chunks), packed for the device.
+struct Chunk {
+    Batch b;
+    std::vector<int> seg_read;              // read index of each segment
+    std::vector<int> seg_off;               // offset of each segment in its read
+    BatchResult res;
+};
+
 int run_files(const std::string &reads_path, const std::string &monomers_path, int threads, int part_size, int overlap,
               const Scoring &sc, int ed_thr, DeviceOpener open_devices, int out_fd, int err_fd, std::string &error)
 {
@@ -386,9 +474,14 @@ int run_files(const std::string &reads_path, const std::string &monomers_path, i
     auto tnow = [] { return std::chrono::steady_clock::now(); };
     auto tms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
     const auto t_begin = tnow();
-    FastaSet reads, mons;
+
+    // Pass 1 over the reads (while the devices are being opened): names, lengths, alphabet check.  The reference loads and
+    // checks both files completely before it aligns anything (main.cpp:394-395), so an illegal symbol anywhere means no
+    // output at all; the sequences themselves are only read in pass 2, chunk by chunk.
+    FastaIndex ridx;
+    FastaSet mons;
     std::string diag;
-    int st = load_fasta(reads_path, reads, diag);
+    int st = index_fasta(reads_path, ridx, diag);
     err.add(diag); err.flush(); diag.clear();
     if (st) return st;
     st = load_fasta(monomers_path, mons, diag);
@@ -396,130 +489,168 @@ int run_files(const std::string &reads_path, const std::string &monomers_path, i
     if (st) return st;
     if (part_size <= 0) { error = "part-size must be positive"; err.add("ERROR: " + error + "\n"); return 1; }
 
-    // segmentation of all reads, in read order (main.cpp:70-81)
-    std::vector<int64_t> first(reads.seqs.size() + 1, 0);
-    std::vector<std::pair<int, int>> segs;       // (offset in read, length)
-    std::vector<int> seg_read;
-    for (size_t p = 0; p < reads.seqs.size(); ++p) {
-        first[p] = (int64_t)segs.size();
-        size_t before = segs.size();
-        segment_read((int64_t)reads.seqs[p].size(), part_size, overlap, &segs);
-        for (size_t s = before; s < segs.size(); ++s) seg_read.push_back((int)p);
+    // segmentation of all reads, in read order (main.cpp:70-81): counts only
+    const size_t nreads = ridx.lens.size();
+    std::vector<int64_t> read_nseg(nreads, 0);
+    int64_t nseg_total = 0;
+    int max_seg_len = 0;
+    for (size_t p = 0; p < nreads; ++p) {
+        read_nseg[p] = segment_read(ridx.lens[p], part_size, overlap, nullptr);
+        nseg_total += read_nseg[p];
+        if (read_nseg[p]) max_seg_len = (int)std::max<int64_t>(max_seg_len, std::min<int64_t>(ridx.lens[p], (int64_t)part_size + overlap));
     }
-    first[reads.seqs.size()] = (int64_t)segs.size();
     err.add("Prepared reads\n"); err.flush();                                                                    // main.cpp:82
-    if (segs.empty()) return 0;
+    if (nseg_total == 0) return 0;
     if (mons.seqs.empty()) { error = "no monomers"; err.add("ERROR: " + error + "\n"); return 1; }
+    const auto t_indexed = tnow();
 
-    const auto t_loaded = tnow();
-    // pack the segments while the devices are still being opened
-    Batch b;
-    b.off.reserve(segs.size() + 1); b.off.push_back(0);
-    {
-        size_t total = 0;
-        for (auto &s : segs) total += (size_t)s.second;
-        b.own.resize(total);
-        size_t o = 0;
-        for (size_t s = 0; s < segs.size(); ++s) {
-            const std::string &r = reads.seqs[seg_read[s]];
-            memcpy(b.own.data() + o, r.data() + segs[s].first, (size_t)segs[s].second);
-            o += (size_t)segs[s].second; b.off.push_back((int64_t)o);
-        }
-        b.text = b.own.data();
-    }
-    const auto t_batch = tnow();
-    auto t_engine = t_batch, t_done = t_batch;
     if (int dst = dev_ready.get()) {                 // no usable device: fail loudly, there is no CPU path
         error = dev_error;
         err.add("ERROR: " + error + "\n");
         return dst;
     }
-    BatchResult res;
+    const auto t_device = tnow();
     std::unique_ptr<Engine> eng;
     try {
         eng.reset(new Engine(mons.seqs, sc, std::move(devs)));
-        t_engine = tnow();
         eng->set_ed_thr(ed_thr);          // FilterMonomersForRead (main.cpp:91-93,135-149) when ed_thr > -1
-        eng->decompose(b, res);
-        t_done = tnow();
-        if (getenv("SD_VERBOSE")) {
-            const EngineStats &s = eng->stats;
-            char line[512];
-            snprintf(line, sizeof line, "[sd_b200] devices=%d geometry packed=%d C=%d T=%d NS=%d NT=%d segments=%ld cells=%ld sweep=%.3f ms traceback=%.3f ms -> %.1f GCUPS (kernels)\n",
-                     eng->ndev(), s.g.packed, s.g.C, s.g.T, s.g.NS, s.g.NT, (long)s.segments, (long)s.cells, s.sweep_ms, s.traceback_ms,
-                     s.cells / ((s.sweep_ms + s.traceback_ms) * 1e6 + 1e-9));
-            err.add(line);
-        }
+        eng->set_plan_hint(max_seg_len, nseg_total);
     } catch (PlanError &e) {
         error = e.msg;
         err.add("ERROR: " + error + "\n");
         return 3;
     }
-    // The `dp` process exits right after this call: its device buffers need no orderly release (dp_main.cpp).
-    if (getenv("SD_FAST_EXIT")) (void)eng.release();
 
-    // per read: add segment offsets (main.cpp:110), PostProcessing (:116), SaveBatch (:117, :272-285); reads are
-    // formatted in contiguous chunks on a few host threads and written in order
-    const int M = (int)mons.seqs.size();
-    const size_t nreads = reads.seqs.size();
-    const int nthr = (int)std::max<size_t>(1, std::min<size_t>({8, std::thread::hardware_concurrency(), (res.recs.size() >> 14) + 1}));
-    std::vector<std::string> out_part(nthr), err_part(nthr);
-    auto format_reads = [&](int t) {
-        std::string &ob = out_part[t], &eb = err_part[t];
-        FdWriter w(-1);
-        std::vector<Record> all, kept;
-        // chunk borders balanced by segment count
-        const int64_t s_lo = (int64_t)segs.size() * t / nthr, s_hi = (int64_t)segs.size() * (t + 1) / nthr;
-        for (size_t p = 0; p < nreads; ++p) {
-            if (first[p] < s_lo || first[p] >= s_hi) continue;
-            all.clear();
-            for (int64_t s = first[p]; s < first[p + 1]; ++s)
-                for (int64_t x = res.rec_off[s]; x < res.rec_off[s + 1]; ++x) {
-                    Record r = res.recs[x];
-                    r.start += segs[s].first; r.end += segs[s].first;
-                    all.push_back(r);
+    // Pass 2: reader thread -> device (this thread) -> writer thread.  A chunk holds up to chunk_cols read symbols;
+    // host memory is bounded by two chunks in flight plus the read being assembled, whatever the size of the file.
+    int64_t chunk_cols = (int64_t)256 << 20;
+    if (const char *e = getenv("SD_CHUNK_BASES")) if (atoll(e) > 0) chunk_cols = atoll(e);
+    Handoff<std::unique_ptr<Chunk>> to_device(2), to_writer(2);
+    std::string reader_error, writer_error;
+
+    std::thread reader([&] {
+        try {
+            std::unique_ptr<Chunk> cur(new Chunk);
+            cur->b.off.push_back(0);
+            int ridx_now = -1;
+            std::string seq;
+            std::vector<std::pair<int, int>> cuts;
+            auto flush_read = [&] {                                   // cut the finished read into segments (main.cpp:73-79)
+                if (ridx_now < 0) return;
+                cuts.clear();
+                segment_read((int64_t)seq.size(), part_size, overlap, &cuts);
+                for (auto &c : cuts) {
+                    if ((int64_t)cur->b.own.size() + c.second > chunk_cols && !cur->seg_read.empty()) {
+                        cur->b.text = cur->b.own.data();
+                        to_device.push(std::move(cur));
+                        cur.reset(new Chunk); cur->b.off.push_back(0);
+                    }
+                    cur->b.own.insert(cur->b.own.end(), seq.begin() + c.first, seq.begin() + c.first + c.second);
+                    cur->b.off.push_back((int64_t)cur->b.own.size());
+                    cur->seg_read.push_back(ridx_now); cur->seg_off.push_back(c.first);
                 }
-            if (all.empty()) continue;     // the reference dereferences batch[0] of an empty vector here (UB)
-            eb += std::to_string((p + 1) * 100 / nreads) + "%: Aligned " + reads.names[p] + "\n";            // main.cpp:115
-            postprocess(all, kept);
-            int prev_end = 0;
-            for (const Record &r : kept) {
-                w.buf += reads.names[p]; w.buf.push_back('\t');
-                w.buf += mons.names[r.row < M ? r.row : r.row - M];
-                if (r.row >= M) w.buf.push_back('\'');
-                w.buf.push_back('\t'); w.add_int(r.start);
-                w.buf.push_back('\t'); w.add_int(r.end);
-                w.buf.push_back('\t'); w.add_int(r.score); w.buf += ".000000";      // to_string(float), main.cpp:279
-                w.buf.push_back('\t'); w.add_int(r.start - prev_end);
-                w.buf.push_back('\t'); w.add_int(r.end - r.start);
-                w.buf.push_back('\n');
-                prev_end = r.end;
-            }
-        }
-        ob.swap(w.buf);
-    };
-    {
-        std::vector<std::thread> pool;
-        for (int t = 1; t < nthr; ++t) pool.emplace_back(format_reads, t);
-        format_reads(0);
-        for (auto &th : pool) th.join();
-    }
+            };
+            scan_fasta(reads_path,
+                [&](const char *, const char *) { flush_read(); ++ridx_now; seq.clear(); if (ridx_now < (int)nreads) seq.reserve((size_t)ridx.lens[(size_t)ridx_now]); },
+                [&](const char *p, const char *le) { if (ridx_now >= 0) seq.append(p, le); });
+            flush_read();
+            if (!cur->seg_read.empty()) { cur->b.text = cur->b.own.data(); to_device.push(std::move(cur)); }
+        } catch (std::exception &e) { reader_error = e.what(); }
+        to_device.finish();
+    });
+
+    const int M = (int)mons.seqs.size();
     FdWriter outw(out_fd);
-    for (int t = 0; t < nthr; ++t) {
-        err.add(err_part[t]); err.flush();
-        outw.buf.swap(out_part[t]);
-        if (!outw.flush()) {                      // ENOSPC / EPIPE ...: a truncated raw TSV must not look like success
-            error = std::string("writing the raw decomposition failed: ") + strerror(errno);
-            err.add("ERROR: " + error + "\n");
-            return 5;
+    std::thread writer([&] {
+        // per read: add segment offsets (main.cpp:110), PostProcessing (:116), SaveBatch (:117, :272-285), in read order
+        try {
+            std::unique_ptr<Chunk> c;
+            std::vector<Record> all, kept;
+            int cur_read = -1; int64_t seen = 0;
+            auto finish_read = [&] {
+                if (cur_read < 0 || all.empty()) { all.clear(); return; }     // a read without alignments: the reference has UB here
+                err.add(std::to_string(((size_t)cur_read + 1) * 100 / nreads) + "%: Aligned " + ridx.names[(size_t)cur_read] + "\n");   // main.cpp:115
+                err.flush();
+                postprocess(all, kept);
+                int prev_end = 0;
+                const std::string &rname = ridx.names[(size_t)cur_read];
+                for (const Record &r : kept) {
+                    outw.buf += rname; outw.buf.push_back('\t');
+                    outw.buf += mons.names[(size_t)(r.row < M ? r.row : r.row - M)];
+                    if (r.row >= M) outw.buf.push_back('\'');
+                    outw.buf.push_back('\t'); outw.add_int(r.start);
+                    outw.buf.push_back('\t'); outw.add_int(r.end);
+                    outw.buf.push_back('\t'); outw.add_int(r.score); outw.buf += ".000000";      // to_string(float), main.cpp:279
+                    outw.buf.push_back('\t'); outw.add_int(r.start - prev_end);
+                    outw.buf.push_back('\t'); outw.add_int(r.end - r.start);
+                    outw.buf.push_back('\n');
+                    prev_end = r.end;
+                }
+                if (outw.buf.size() > (1 << 20) && !outw.flush()) throw std::runtime_error(std::string("writing the raw decomposition failed: ") + strerror(errno));
+                all.clear();
+            };
+            while (to_writer.pop(c)) {
+                for (size_t sgi = 0; sgi < c->seg_read.size(); ++sgi) {
+                    if (c->seg_read[sgi] != cur_read) { finish_read(); cur_read = c->seg_read[sgi]; seen = 0; }
+                    for (int64_t x = c->res.rec_off[sgi]; x < c->res.rec_off[sgi + 1]; ++x) {
+                        Record r = c->res.recs[(size_t)x];
+                        r.start += c->seg_off[sgi]; r.end += c->seg_off[sgi];
+                        all.push_back(r);
+                    }
+                    if (++seen == read_nseg[(size_t)cur_read]) { finish_read(); cur_read = -1; }
+                }
+            }
+            finish_read();
+            if (!outw.flush()) throw std::runtime_error(std::string("writing the raw decomposition failed: ") + strerror(errno));
+        } catch (std::exception &e) { writer_error = e.what(); to_writer.close(); }
+    });
+
+    std::string engine_error;
+    double dev_ms = 0;
+    {
+        std::unique_ptr<Chunk> c;
+        while (to_device.pop(c)) {
+            if (!engine_error.empty() || !writer_error.empty()) continue;          // drain
+            try {
+                const auto t0 = tnow();
+                eng->decompose(c->b, c->res);
+                dev_ms += tms(t0, tnow());
+                c->b.own.clear(); c->b.own.shrink_to_fit();
+                to_writer.push(std::move(c));
+            } catch (PlanError &e) { engine_error = e.msg.empty() ? "error" : e.msg; to_device.close(); }
+            catch (std::exception &e) { engine_error = e.what(); to_device.close(); }
         }
     }
-    if (prof) {
-        char line[256];
-        snprintf(line, sizeof line, "[sd_b200 profile] run_files: fasta %.1f batch %.1f wait-for-device %.1f decompose %.1f output %.1f ms (%d threads)\n",
-                 tms(t_begin, t_loaded), tms(t_loaded, t_batch), tms(t_batch, t_engine), tms(t_engine, t_done), tms(t_done, tnow()), nthr);
+    to_writer.finish();
+    reader.join();
+    writer.join();
+    const auto t_done = tnow();
+    if (!engine_error.empty() || !reader_error.empty()) {
+        error = !engine_error.empty() ? engine_error : reader_error;
+        err.add("ERROR: " + error + "\n");
+        return 3;
+    }
+    if (!writer_error.empty()) {                    // ENOSPC / EPIPE ...: a truncated raw TSV must not look like success
+        error = writer_error;
+        err.add("ERROR: " + error + "\n");
+        return 5;
+    }
+    if (getenv("SD_VERBOSE")) {
+        const EngineStats &es = eng->stats;
+        char line[512];
+        snprintf(line, sizeof line, "[sd_b200] devices=%d geometry packed=%d lat=%d C=%d T=%d NS=%d NT=%d NG=%d segments=%ld cells=%ld sweep=%.3f ms traceback=%.3f ms -> %.1f GCUPS (kernels)\n",
+                 eng->ndev(), es.g.packed, es.g.lat, es.g.C, es.g.T, es.g.NS, es.g.NT, es.g.NG, (long)es.segments, (long)es.cells, es.sweep_ms, es.traceback_ms,
+                 es.cells / ((es.sweep_ms + es.traceback_ms) * 1e6 + 1e-9));
         err.add(line);
     }
+    if (prof) {
+        char line[320];
+        snprintf(line, sizeof line, "[sd_b200 profile] run_files: index %.1f wait-for-device %.1f stream+decompose+write %.1f ms (device calls %.1f ms; %ld segments)\n",
+                 tms(t_begin, t_indexed), tms(t_indexed, t_device), tms(t_device, t_done), dev_ms, (long)nseg_total);
+        err.add(line);
+    }
+    // The `dp` process exits right after this call: its device buffers need no orderly release (dp_main.cpp).
+    if (getenv("SD_FAST_EXIT")) (void)eng.release();
     return 0;
 }
 

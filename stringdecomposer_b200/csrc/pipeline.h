@@ -42,6 +42,7 @@ public:
     double run_staged();                                        // returns kernel ms (max over devices)
     void fetch_staged(BatchResult &out);
     void set_ed_thr(int ed_thr);                                // --ed_thr monomer pre-filter, -1 = off (main.cpp:135-149)
+    void set_plan_hint(int max_seg_len, int64_t nseg_total);    // shape of a job that arrives in chunks (run_files)
     const MonomerSet &monomers() const { return ms_; }
     EngineStats stats;
     int ndev() const { return (int)devs_.size(); }
@@ -56,6 +57,7 @@ private:
     Scoring sc_;
     std::vector<std::unique_ptr<Backend>> devs_;
     Plan plan_; bool have_plan_ = false; int plan_maxlen_ = -1; int64_t plan_nseg_ = -1;
+    int hint_maxlen_ = 0; int64_t hint_nseg_ = 0;
     Batch staged_; std::vector<int> staged_bounds_;
 };
 

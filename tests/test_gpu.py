@@ -96,6 +96,16 @@ def test_segment_records_and_staged_api():
     d.close()
 
 
+@pytest.mark.parametrize("chunk,wave", [("1", ""), ("5000", "300000"), ("100000", "")])
+def test_streamed_chunks_and_waves_do_not_change_the_result(chunk, wave):
+    picked = [c for c in cases.load_cases() if c["name"] in ("multi_read", "len_10000_default", "part700_ov50", "blank_lines", "ed_thr_12")]
+    env = {"SD_CHUNK_BASES": chunk}
+    if wave:
+        env["SD_WAVE_BYTES"] = wave
+    for case in picked:
+        cases.check_case(cases.DP_CUDA, case, env=env)
+
+
 def test_waves_do_not_change_the_result():
     rn, rr, mn, mm = synth.random_case(77, read_len=(2000, 3000), n_reads=(3, 3))
     want = sd_oracle.decompose_reads(rn, rr, mn, mm, part_size=300, overlap=100)

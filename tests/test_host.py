@@ -127,6 +127,15 @@ def test_emulated_config1_full_golden():
     assert out == open(os.path.join(cases.GOLDEN, "config1_raw_default.tsv"), "rb").read()
 
 
+@pytest.mark.parametrize("chunk", ["1", "700", "5000", "100000"])
+def test_streamed_chunks_do_not_change_the_result(chunk):
+    # run_files streams the reads file in chunks (reader -> device -> writer); a read may straddle chunks
+    picked = [c for c in cases.load_cases() if c["name"] in ("multi_read", "len_10000_default", "part700_ov50", "blank_lines", "ed_thr_12")]
+    assert len(picked) == 5
+    for case in picked:
+        cases.check_case(cases.DP_EMU, case, env={"SD_CHUNK_BASES": chunk})
+
+
 def test_waves_do_not_change_the_result():
     rn, rr, mn, mm = synth.random_case(77, read_len=(2000, 3000), n_reads=(3, 3))
     want = sd_oracle.decompose_reads(rn, rr, mn, mm, part_size=300, overlap=100)
