@@ -357,6 +357,8 @@ def main():
         if ws == 1 and not args.no_extras:
             line["rescoring"] = rescoring(segs, mons, recs, roff, local, alu)
             line["process"] = process_boundary(rnames, reads, mnames, mons)
+            line["ed_thr"] = ed_thr_leg(dec, packed, cells_hl, args)
+            line["config3_waves"] = config3_waves(local)
         if not args.no_cpu_baseline and ws == 1:          # reported at N=1 only
             line["cpu_baseline"] = cpu_baseline(reads, rnames, mnames, mons)
         dec.close()
@@ -386,6 +388,54 @@ def main():
         dist.destroy_process_group()
 
 
+def ed_thr_leg(dec, packed, cells_hl, args):
+    """the same batch through sd_decompose with the --ed_thr pre-filter on (FilterMonomersForRead,
+    main.cpp:135-149): distances + ranks on the device, then the sweep on the re-ordered subset."""
+    out = {}
+    for thr in (40, 10 ** 6):
+        dec.set_ed_thr(thr)
+        for _ in range(2):
+            dec.decompose(packed)
+        dec.reset_stats()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            dec.decompose(packed)
+        dt = (time.perf_counter() - t0) / args.steps
+        st = dec.stats()
+        out["ed_thr_%s" % ("all" if thr > 10 ** 5 else thr)] = {"e2e_ms_per_step": 1e3 * dt, "e2e_gcups": cells_hl / dt / 1e9,
+                                                                  "copy_in_plus_filter_ms": st["h2d_ms"] / args.steps,
+                                                                  "sweep_ms": st["sweep_ms"] / args.steps}
+    dec.set_ed_thr(-1)
+    out["what"] = ("sd_decompose with the --ed_thr pre-filter: hw_distance_rows_kernel + filter_rank_kernel run on the copy-in stream "
+                   "(their time is inside copy_in_plus_filter_ms); ed_thr=40 keeps the closest rows, 'all' keeps every row re-ordered")
+    return out
+
+
+def config3_waves(device):
+    """BASELINE config 3 (ONT-like 100 kb reads) on a 600-read sample through sd_decompose: 12,000 segments, more than one
+    wave of backpointers, so that copy-in / kernels / copy-out of successive waves overlap (two wave slots)."""
+    from stringdecomposer_b200 import Decomposer, synth
+    from stringdecomposer_b200.hostpipe import segment_reads
+    rn, reads, mn, mons = synth.config3(n_reads=600, read_len=100_000)
+    segs, _ = segment_reads(reads, PART, OVERLAP)
+    packed = pack_segments(segs)
+    dec = Decomposer(mons, *SCORING, devices=[device])
+    dec.decompose(packed)
+    dec.reset_stats()
+    t0 = time.perf_counter()
+    dec.decompose(packed)
+    dt = time.perf_counter() - t0
+    st = dec.stats()
+    dec.close()
+    cells = float(cells_of(segs, mons))
+    kms = st["sweep_ms"] + st["traceback_ms"]
+    return {"what": "config 3 sample: 600 reads x 100 kb (60 Mb), one sd_decompose call with host buffers",
+            "segments": len(segs), "cells": cells, "kernel_ms": kms, "e2e_ms": 1e3 * dt, "e2e_over_kernels": 1e3 * dt / kms,
+            "kernel_gcups_actual_cells": cells / kms / 1e6, "e2e_gcups_actual_cells": cells / dt / 1e9,
+            "h2d_bytes": st["h2d_bytes"], "d2h_bytes": st["d2h_bytes"],
+            "geometry": {k: st[k] for k in ("C", "T", "NS", "NT", "NG", "lat")}}
+
+
 def process_boundary(rnames, reads, mnames, mons):
     """The boundary main.py:194 actually crosses is a process: wall time of `dp` on the config-2 contig, cold (CUDA
     context creation, module load, FASTA ingest, TSV) -- not the warm-handle number `e2e` reports."""
@@ -401,8 +451,17 @@ def process_boundary(rnames, reads, mnames, mons):
             with open(os.path.join(td, "out.tsv"), "wb") as out:
                 subprocess.run([dp, rp, mp, "1", str(PART), str(OVERLAP)], stdout=out, stderr=subprocess.DEVNULL, check=True)
             walls.append(time.perf_counter() - t0)
-    return {"what": "wall time of the drop-in `dp` process on the config-2 contig (2 Mb), including CUDA start-up",
-            "dp_process_s": min(walls), "dp_process_s_all": walls,
+    ctx = None
+    probe = os.path.join(ROOT, "tools", "probes", "ctx_time")
+    if os.path.exists(probe):
+        try:
+            outp = subprocess.run([probe], stdout=subprocess.PIPE, timeout=60).stdout.decode()
+            ctx = float(outp.split("context")[1].split("ms")[0]) / 1e3
+        except Exception:
+            ctx = None
+    return {"what": "wall time of the drop-in `dp` process on the config-2 contig (2 Mb), including CUDA start-up; "
+                    "cuda_context_s is what an empty CUDA program needs on this box for cudaFree(0) (tools/probes/ctx_time.cu)",
+            "dp_process_s": min(walls), "dp_process_s_all": walls, "cuda_context_s": ctx,
             "gcups": headline_cells(reads, mons) / min(walls) / 1e9}
 
 

@@ -643,6 +643,23 @@ int run_files(const std::string &reads_path, const std::string &monomers_path, i
                  es.cells / ((es.sweep_ms + es.traceback_ms) * 1e6 + 1e-9));
         err.add(line);
     }
+    if (const char *pj = getenv("SD_PERF_JSON")) {
+        // machine-readable summary of the run, appended to a side file (stdout is the data channel)
+        if (FILE *f = fopen(pj, "a")) {
+            const EngineStats &es = eng->stats;
+            int64_t read_bp = 0;
+            for (int64_t l : ridx.lens) read_bp += l;
+            const double kms = es.sweep_ms + es.traceback_ms, wall = tms(t_begin, t_done);
+            fprintf(f, "{\"reads\": %zu, \"read_bp\": %ld, \"segments\": %ld, \"columns\": %ld, \"cells\": %ld, \"devices\": %d, "
+                       "\"sweep_ms\": %.3f, \"traceback_ms\": %.3f, \"h2d_ms\": %.3f, \"device_calls_ms\": %.3f, \"wall_ms\": %.3f, "
+                       "\"wait_for_device_ms\": %.3f, \"kernel_gcups\": %.2f, \"wall_mbp_per_s\": %.3f, "
+                       "\"geometry\": {\"packed\": %d, \"lat\": %d, \"C\": %d, \"T\": %d, \"NS\": %d, \"NT\": %d, \"NG\": %d, \"scanw\": %d}}\n",
+                    nreads, (long)read_bp, (long)es.segments, (long)es.columns, (long)es.cells, eng->ndev(), es.sweep_ms, es.traceback_ms, es.h2d_ms,
+                    dev_ms, wall, tms(t_indexed, t_device), es.cells / (kms * 1e6 + 1e-9), read_bp / (wall * 1e3 + 1e-9),
+                    es.g.packed, es.g.lat, es.g.C, es.g.T, es.g.NS, es.g.NT, es.g.NG, es.g.scanw);
+            fclose(f);
+        }
+    }
     if (prof) {
         char line[320];
         snprintf(line, sizeof line, "[sd_b200 profile] run_files: index %.1f wait-for-device %.1f stream+decompose+write %.1f ms (device calls %.1f ms; %ld segments)\n",

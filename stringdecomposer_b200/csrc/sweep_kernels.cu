@@ -12,6 +12,7 @@
 //
 // Reference semantics: stringdecomposer/src/main.cpp:151-270 (AlignPartClassicDP); see sweep_core.cuh.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>      // header-only; ranges cost nothing unless a profiler is attached
 
 #include <algorithm>
 #include <climits>
@@ -198,7 +199,8 @@ __global__ void __launch_bounds__(TB_WARPS * 32) traceback_kernel(const TbArgs a
     if (lane == 0) a.counts[s] = cnt;
 }
 
-// --ed_thr pre-filter: infix edit distance of every DP row against every staged segment (one thread per pair)
+// --ed_thr pre-filter (FilterMonomersForRead, main.cpp:135-149), step 1: infix edit distance of every DP row against
+// every staged segment.  Generic form: one thread per pair, state in local memory (rows of up to 1536 symbols).
 __global__ void hw_distance_kernel(const uint8_t *bases, const int64_t *seg_off, int nseg, const uint8_t *rows, const int *row_off,
                                    int R, int *dist)
 {
@@ -206,6 +208,101 @@ __global__ void hw_distance_kernel(const uint8_t *bases, const int64_t *seg_off,
     if (x >= (int64_t)nseg * R) return;
     const int s = (int)(x / R), r = (int)(x - (int64_t)s * R);
     dist[x] = hw_distance(rows + row_off[r], row_off[r + 1] - row_off[r], bases + seg_off[s], (int)(seg_off[s + 1] - seg_off[s]));
+}
+
+// The same for rows of at most 64*NB symbols (NB <= 4: alpha-satellite monomers need 3): a CTA takes one segment and 128
+// rows, one row per thread.  The segment's symbols are staged in shared memory once and broadcast; the match masks of the
+// CTA's rows live in shared memory as [symbol][word][thread] (conflict-free 8-byte loads); the Myers/Hyyro column state
+// stays in registers.  Same recurrence as sweep_core.cuh: hw_distance (edlib's HW mode, distance only).
+constexpr int HWF_ROWS = 128;
+template <int NB>
+__global__ void __launch_bounds__(HWF_ROWS) hw_distance_rows_kernel(const uint8_t *bases, const int64_t *seg_off, const uint8_t *rows,
+                                                                    const int *row_off, int R, int *dist, int text_stride)
+{
+    extern __shared__ unsigned long long hwf_smem[];
+    unsigned long long *peq = hwf_smem;                                  // [5][NB][HWF_ROWS]
+    uint8_t *stext = reinterpret_cast<uint8_t *>(peq + 5 * NB * HWF_ROWS);
+    const int s = blockIdx.x, tid = threadIdx.x;
+    const int r = blockIdx.y * HWF_ROWS + tid;
+    const int64_t o = seg_off[s];
+    const int n = (int)(seg_off[s + 1] - o);
+    (void)text_stride;
+    for (int x = tid; x < n; x += HWF_ROWS) { const int c = ascii_code(bases[o + x]); stext[x] = (uint8_t)(c > 4 ? 4 : c); }
+#pragma unroll
+    for (int q = 0; q < 5 * NB; ++q) peq[q * HWF_ROWS + tid] = 0ull;
+    int m = 0;
+    if (r < R) {
+        const uint8_t *pat = rows + row_off[r];
+        m = row_off[r + 1] - row_off[r];
+        for (int i = 0; i < m; ++i) {
+            const unsigned ch = pat[i];
+            const int c = ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : 4;
+            peq[(c * NB + (i >> 6)) * HWF_ROWS + tid] |= 1ull << (i & 63);
+        }
+    }
+    __syncthreads();
+    if (r >= R) return;
+    const int B = (m + 63) >> 6;
+    unsigned long long pv[NB], mv[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) { pv[b] = ~0ull; mv[b] = 0ull; }
+    const unsigned long long last_bit = 1ull << ((m - 1) & 63);
+    int score = m, best = m;
+    for (int j = 0; j < n; ++j) {
+        const int c = stext[j];
+        int hin = 0;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            if (b < B) {
+                unsigned long long eq = peq[(c * NB + b) * HWF_ROWS + tid];
+                const unsigned long long p = pv[b], mm = mv[b];
+                const unsigned long long xv = eq | mm;
+                if (hin < 0) eq |= 1ull;
+                const unsigned long long xh = (((eq & p) + p) ^ p) | eq;
+                unsigned long long ph = mm | ~(xh | p);
+                unsigned long long mh = p & xh;
+                const unsigned long long top = (b == B - 1) ? last_bit : (1ull << 63);
+                const int hout = (ph & top) ? 1 : ((mh & top) ? -1 : 0);
+                ph <<= 1; mh <<= 1;
+                if (hin < 0) mh |= 1ull; else if (hin > 0) ph |= 1ull;
+                pv[b] = mh | ~(xv | ph);
+                mv[b] = ph & xv;
+                hin = hout;
+            }
+        }
+        score += hin;
+        best = min(best, score);
+    }
+    dist[(size_t)s * R + r] = best;
+}
+
+// Step 2: per segment, the rows sorted by (distance, row); the closest row and every row within ed_thr are kept
+// (main.cpp:141-147).  rank_of_row[r] = position in the kept list or -1; row_of_rank[pos] = r or -1.  The position is
+// found by counting (R is at most 4096), so no sort and no trip to the host.  For the deferred-jump sweep the best
+// jump-derived row-end key per symbol of the kept rows is formed on the way (plan.cpp: lat_jump_keys):
+// kjbase[r][sym] = key of row r with tie-break index 0, the rank is subtracted here.
+__global__ void __launch_bounds__(256) filter_rank_kernel(const int *dist, int R, int ed_thr, int *rank_of_row, int *row_of_rank,
+                                                          const int *kjbase, int *seg_kj)
+{
+    extern __shared__ int frk_d[];
+    __shared__ int s_kj[5];
+    const int s = blockIdx.x, tid = threadIdx.x;
+    const int *d = dist + (size_t)s * R;
+    for (int r = tid; r < R; r += 256) frk_d[r] = d[r];
+    if (tid < 5) s_kj[tid] = INT_MIN;
+    __syncthreads();
+    for (int r = tid; r < R; r += 256) {
+        const int dr = frk_d[r];
+        int pos = 0;
+        for (int q = 0; q < R; ++q) { const int dq = frk_d[q]; pos += (dq < dr) || (dq == dr && q < r); }
+        const bool keep = pos == 0 || dr <= ed_thr;
+        rank_of_row[(size_t)s * R + r] = keep ? pos : -1;
+        row_of_rank[(size_t)s * R + pos] = keep ? r : -1;
+        if (keep && kjbase)
+            for (int sym = 0; sym < 5; ++sym) atomicMax(&s_kj[sym], kjbase[r * 5 + sym] - pos);
+    }
+    __syncthreads();
+    if (seg_kj && tid < 5) seg_kj[(size_t)s * 5 + tid] = s_kj[tid];
 }
 
 // Compaction of the per-segment records into one dense array (in segment order, each segment reversed: main.cpp:268)
@@ -323,7 +420,6 @@ struct WaveSlot {
     PinnedBuf h_out;
     std::vector<char> hmeta;
     std::vector<int64_t> hoff;
-    std::vector<int> hdist, hrank, hr2r, hsegkj;
     CtaLayout lay;
     int s0 = 0, s1 = 0, nseg = 0, nmax = 0;
     bool filter_on = false, staged = false;
@@ -386,6 +482,20 @@ public:
         for (size_t x = 0; x < ms.rows.size(); ++x) rows_ascii_[x] = (uint8_t)"ACGTN"[ms.rows[x]];
         SD_CUDA(cudaMemcpyAsync(d_rows_.p, rows_ascii_.data(), rows_ascii_.size(), cudaMemcpyHostToDevice, st_));
         SD_CUDA(cudaMemcpyAsync(d_rowoff_.p, ms.row_off.data(), ms.row_off.size() * 4, cudaMemcpyHostToDevice, st_));
+        if (g.lat) {
+            // per row and symbol: the key of its best jump-derived row end with tie-break index 0 (plan.cpp: lat_jump_keys);
+            // the --ed_thr pre-filter subtracts the row's rank on the device
+            const int R = ms.nrows();
+            kjbase_.assign((size_t)R * 5, 0);
+            std::vector<int> one((size_t)R, -1);
+            for (int r = 0; r < R; ++r) {
+                one[(size_t)r] = 0;
+                lat_jump_keys(ms, p.sc, one.data(), kjbase_.data() + (size_t)r * 5);
+                one[(size_t)r] = -1;
+            }
+            d_kjbase_.need(kjbase_.size() * 4);
+            SD_CUDA(cudaMemcpyAsync(d_kjbase_.p, kjbase_.data(), kjbase_.size() * 4, cudaMemcpyHostToDevice, st_));
+        }
         SD_CUDA(cudaStreamSynchronize(st_));
     }
 
@@ -444,30 +554,38 @@ public:
         w.staged = true;
     }
 
-    // FilterMonomersForRead (main.cpp:135-149): distances on the device, (distance,row) sort on the host
+    // FilterMonomersForRead (main.cpp:135-149): distances, ranks and (deferred-jump sweep) the per-segment jump keys, all
+    // on the device and all asynchronous on the copy-in stream
     void build_filter(WaveSlot &w)
     {
         const int R = ms_.nrows();
         const size_t np = (size_t)w.nseg * R;
         w.d_dist.need(np * 4); w.d_rank.need(np * 4); w.d_r2r.need(np * 4);
-        hw_distance_kernel<<<(unsigned)((np + 63) / 64), 64, 0, st_in_>>>(w.d_bases.as<uint8_t>(), w.d_segoff.as<int64_t>(), w.nseg,
-                                                                       d_rows_.as<uint8_t>(), d_rowoff_.as<int>(), R, w.d_dist.as<int>());
-        SD_CUDA(cudaGetLastError());
-        w.hdist.resize(np); w.hrank.resize(np); w.hr2r.resize(np);
-        SD_CUDA(cudaMemcpyAsync(w.hdist.data(), w.d_dist.p, np * 4, cudaMemcpyDeviceToHost, st_in_));
-        SD_CUDA(cudaStreamSynchronize(st_in_));
-        for (int s = 0; s < w.nseg; ++s)
-            build_filter_tables(w.hdist.data() + (size_t)s * R, R, ed_thr_, w.hrank.data() + (size_t)s * R, w.hr2r.data() + (size_t)s * R);
-        if (plan_.g.lat) {
-            w.hsegkj.resize((size_t)w.nseg * 5);
-            for (int s = 0; s < w.nseg; ++s) lat_jump_keys(ms_, plan_.sc, w.hrank.data() + (size_t)s * R, w.hsegkj.data() + (size_t)s * 5);
-            w.d_segkj.need(w.hsegkj.size() * 4);
-            SD_CUDA(cudaMemcpyAsync(w.d_segkj.p, w.hsegkj.data(), w.hsegkj.size() * 4, cudaMemcpyHostToDevice, st_in_));
+        const int NB = (ms_.Lmax + 63) / 64;
+        if (NB <= 4) {
+            const int text_stride = (w.nmax + 16) / 16 * 16;
+            const size_t smem = (size_t)5 * NB * HWF_ROWS * 8 + (size_t)text_stride;
+            const void *k = NB == 1 ? (const void *)hw_distance_rows_kernel<1> : NB == 2 ? (const void *)hw_distance_rows_kernel<2>
+                          : NB == 3 ? (const void *)hw_distance_rows_kernel<3> : (const void *)hw_distance_rows_kernel<4>;
+            if (smem > (size_t)prop_.sharedMemPerBlockOptin) throw PlanError{"--ed_thr: segment too long for the pre-filter kernel"};
+            SD_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const uint8_t *bases = w.d_bases.as<uint8_t>(); const int64_t *so = w.d_segoff.as<int64_t>();
+            const uint8_t *rows = d_rows_.as<uint8_t>(); const int *ro = d_rowoff_.as<int>(); int *dist = w.d_dist.as<int>();
+            int Rv = R, ts = text_stride;
+            void *args[] = {(void *)&bases, (void *)&so, (void *)&rows, (void *)&ro, (void *)&Rv, (void *)&dist, (void *)&ts};
+            SD_CUDA(cudaLaunchKernel(k, dim3((unsigned)w.nseg, (unsigned)((R + HWF_ROWS - 1) / HWF_ROWS)), dim3(HWF_ROWS), args, smem, st_in_));
+        } else {
+            hw_distance_kernel<<<(unsigned)((np + 63) / 64), 64, 0, st_in_>>>(w.d_bases.as<uint8_t>(), w.d_segoff.as<int64_t>(), w.nseg,
+                                                                           d_rows_.as<uint8_t>(), d_rowoff_.as<int>(), R, w.d_dist.as<int>());
+            SD_CUDA(cudaGetLastError());
         }
-        SD_CUDA(cudaMemcpyAsync(w.d_rank.p, w.hrank.data(), np * 4, cudaMemcpyHostToDevice, st_in_));
-        SD_CUDA(cudaMemcpyAsync(w.d_r2r.p, w.hr2r.data(), np * 4, cudaMemcpyHostToDevice, st_in_));
+        int *segkj = nullptr;
+        if (plan_.g.lat) { w.d_segkj.need((size_t)w.nseg * 5 * 4); segkj = w.d_segkj.as<int>(); }
+        filter_rank_kernel<<<(unsigned)w.nseg, 256, (size_t)R * 4, st_in_>>>(w.d_dist.as<int>(), R, ed_thr_, w.d_rank.as<int>(), w.d_r2r.as<int>(),
+                                                                           plan_.g.lat ? d_kjbase_.as<int>() : nullptr, segkj);
+        SD_CUDA(cudaGetLastError());
         SD_CUDA(cudaEventRecord(w.ev[1], st_in_));
-        launches += 1;
+        launches += 2;
     }
 
     void launch_single(WaveSlot &w, int seg_stride)
@@ -664,15 +782,23 @@ public:
     {
         DeviceScope scope_(dev_); SD_CUDA(scope_.status);
         WaveSlot &w = slot_[slot & 1];
+        nvtxRangePushA("sd_b200: wave copy-in");
         enqueue_h2d(w, b, s0, s1);
+        nvtxRangePop();
+        nvtxRangePushA("sd_b200: wave sweep + traceback");
         enqueue_kernels(w);
         enqueue_gather(w);
+        nvtxRangePop();
+        nvtxRangePushA("sd_b200: wave copy-out");
         enqueue_d2h(w);
+        nvtxRangePop();
     }
     void collect(int slot, BatchResult &out) override
     {
         DeviceScope scope_(dev_); SD_CUDA(scope_.status);
-        finish(slot_[slot & 1], out);
+        nvtxRangePushA("sd_b200: wave collect");
+        try { finish(slot_[slot & 1], out); } catch (...) { nvtxRangePop(); throw; }
+        nvtxRangePop();
     }
     // the resident path (sd_stage / sd_run_staged / sd_fetch_staged): one wave on slot 0, each step synchronous
     void stage(const Batch &b, int s0, int s1) override
@@ -717,7 +843,8 @@ private:
     bool fast_ = false, lat_timing_ = false;
     std::vector<uint8_t> rows_ascii_;
     int64_t budget_ = 0;
-    DevBuf d_prof_, d_slotlen_, d_slotend_, d_rows_, d_rowoff_;
+    DevBuf d_prof_, d_slotlen_, d_slotend_, d_rows_, d_rowoff_, d_kjbase_;
+    std::vector<int> kjbase_;
     WaveSlot slot_[2];
 };
 

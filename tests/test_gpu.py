@@ -295,3 +295,24 @@ def test_config5_large_monomer_set_sample():
     want = sd_oracle.decompose_reads(rn[:2], reads, mn, mons, part_size=2000, overlap=300, threads=4)
     got = decompose_reads(rn[:2], reads, mn, mons, part_size=2000, overlap=300)
     assert got == want
+
+
+def test_config5_full_monomer_set_against_the_reference_binary():
+    # BASELINE config 5 at its defining scale: 1,000 monomers -> 2,000 DP rows, sum(L) = 342 kb, which the planner spreads
+    # over 32 partner CTAs per segment (group sweep).  The reference needs n * sum(L) * 8 B per segment in flight
+    # (5.5 GB for a 2,000-column segment), so parity is checked on two 2,000-column segments plus a short tail, against
+    # the unmodified reference binary where it travelled with the snapshot (else against the oracle's C restatement).
+    rn, reads, mn, mons = synth.config5(n_monomers=1000, total=40_000)
+    read = reads[0][:3700]
+    binary = cases.DP_REF if os.path.exists(cases.DP_REF) else None
+    want = sd_oracle.decompose_reads(rn[:1], [read], mn, mons, part_size=1700, overlap=300, binary=binary, threads=2)
+    d = Decomposer(mons, devices=[0])
+    segs, _ = segment_reads([read], 1700, 300)
+    assert [len(x) for x in segs] == [2000, 2000, 300]
+    d.decompose(segs)
+    st = d.stats()
+    d.close()
+    assert st["NG"] >= 16 and st["lat"] == 0          # the many-CTA group geometry of the real config 5
+    got = decompose_reads(rn[:1], [read], mn, mons, part_size=1700, overlap=300)
+    assert got == want and got.count("\n") > 15
+
