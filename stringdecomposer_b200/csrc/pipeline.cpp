@@ -294,8 +294,13 @@ void Engine::decompose(const Batch &b, BatchResult &out)
             const int64_t budget = dev.wave_budget() / nsl;
             const bool prof = getenv("SD_PROFILE") != nullptr;
             std::vector<std::pair<int, int>> waves;
+            // a large share is cut into at least eight waves even if fewer would fit: the first copy-in and the last
+            // copy-out are the only ones that cannot hide behind kernels, so they should be short (2048 segments still
+            // saturate the sweep)
+            const int share = s_end - bounds[d];
+            const int cap_segs = (nsl > 1 && share > 4096) ? std::max(2048, (share + 7) / 8) / plan_.g.NS * plan_.g.NS : share;
             for (int s0 = bounds[d]; s0 < s_end;) {
-                int lo = std::min(s_end, s0 + plan_.g.NS), hi = s_end;
+                int lo = std::min(s_end, s0 + plan_.g.NS), hi = std::min(s_end, s0 + std::max(cap_segs, plan_.g.NS));
                 if (dev.wave_bytes(b, s0, hi) > budget) {
                     while (hi - lo > plan_.g.NS) {
                         int mid = lo + (hi - lo) / 2 / plan_.g.NS * plan_.g.NS;

@@ -50,7 +50,7 @@ def test_every_geometry_and_both_widths(geom, force32):
     picked = [c for c in cases.load_cases() if c["name"] in ("multi_read", "scoring_-3_-2_-4_2", "N_in_monomer", "dup_monomers_rev",
                                                              "len_5501_default")]
     for case in picked:
-        cases.check_case(cases.DP_CUDA, case, env={"SD_GEOM": geom, "SD_FORCE_S32": force32})
+        cases.check_case_inproc(case, env={"SD_GEOM": geom, "SD_FORCE_S32": force32})
 
 
 @pytest.mark.parametrize("geom", ["8,1,4", "8,2,2", "16,1,1", "24,1,2", "32,2,1", "48,1,1", "8,4,3", "48,32,1"])
@@ -103,7 +103,8 @@ def test_streamed_chunks_and_waves_do_not_change_the_result(chunk, wave):
     if wave:
         env["SD_WAVE_BYTES"] = wave
     for case in picked:
-        cases.check_case(cases.DP_CUDA, case, env=env)
+        cases.check_case_inproc(case, env=env, check_stderr=True)
+    cases.check_case(cases.DP_CUDA, picked[0], env=env)             # and once through the binary
 
 
 def test_waves_do_not_change_the_result():
@@ -226,7 +227,7 @@ def test_edge_cases_with_the_sweep_forced(lat):
     picked = [c for c in cases.load_cases() if c["name"] in LAT_SUBSET + extra or c["name"].startswith("fuzz_0")]
     assert len(picked) >= 25 and set(LAT_SUBSET + extra) <= names
     for case in picked:
-        cases.check_case(cases.DP_CUDA, case, env={"SD_LAT": lat})
+        cases.check_case_inproc(case, env={"SD_LAT": lat}, check_stderr=True)
 
 
 @pytest.mark.parametrize("geom,warps", [("6,32,1", "4"), ("6,32,1", "1"), ("6,32,1", "2"), ("12,16,1", "3"), ("12,16,1", "1"), ("24,8,1", "0"),
@@ -236,7 +237,7 @@ def test_deferred_jump_sweep_every_geometry(geom, warps, force32):
     # cluster shapes from one CTA per segment down to one warp per CTA (up to 8 CTAs exchanging keys through DSMEM)
     picked = [c for c in cases.load_cases() if c["name"] in ("multi_read", "scoring_-3_-2_-4_2", "N_in_monomer", "dup_monomers_rev")]
     for case in picked:
-        cases.check_case(cases.DP_CUDA, case, env={"SD_LAT": "1", "SD_GEOM": geom, "SD_LAT_WARPS": warps, "SD_FORCE_S32": force32})
+        cases.check_case_inproc(case, env={"SD_LAT": "1", "SD_GEOM": geom, "SD_LAT_WARPS": warps, "SD_FORCE_S32": force32})
 
 
 def test_deferred_jump_sweep_config1_and_config2_sample():
@@ -281,8 +282,8 @@ def test_int_peak_probe():
 def test_group_mode_forced_on_small_sets(sg):
     picked = [c for c in cases.load_cases() if c["name"] in ("multi_read", "dup_monomers_rev", "short_monomers", "N_in_monomer", "len_5501_default")]
     for case in picked:
-        cases.check_case(cases.DP_CUDA, case, env={"SD_GROUP_SLOTS": sg})
-    cases.check_case(cases.DP_CUDA, picked[0], env={"SD_GROUP_SLOTS": sg, "SD_FORCE_S32": "1"})
+        cases.check_case_inproc(case, env={"SD_GROUP_SLOTS": sg})
+    cases.check_case_inproc(picked[0], env={"SD_GROUP_SLOTS": sg, "SD_FORCE_S32": "1"})
     st, out, err = sd_oracle.run_cli(cases.DP_CUDA, os.path.join(cases.GOLDEN, "config1_read.fa"), os.path.join(cases.GOLDEN, "DXZ1_star_monomers.fa"))
     assert st == 0
 
