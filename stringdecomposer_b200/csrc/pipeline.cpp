@@ -294,11 +294,11 @@ void Engine::decompose(const Batch &b, BatchResult &out)
             const int64_t budget = dev.wave_budget() / nsl;
             const bool prof = getenv("SD_PROFILE") != nullptr;
             std::vector<std::pair<int, int>> waves;
-            // a large share is cut into at least eight waves even if fewer would fit: the first copy-in and the last
-            // copy-out are the only ones that cannot hide behind kernels, so they should be short (2048 segments still
-            // saturate the sweep)
+            // a large share is cut into at least four waves even if fewer would fit: the first copy-in and the last
+            // copy-out are the only ones that cannot hide behind kernels, so they should be short -- but not shorter than
+            // 8192 segments, below which the tail of a launch (CTAs per SM not a whole number) starts to cost
             const int share = s_end - bounds[d];
-            const int cap_segs = (nsl > 1 && share > 4096) ? std::max(2048, (share + 7) / 8) / plan_.g.NS * plan_.g.NS : share;
+            const int cap_segs = (nsl > 1 && share > 16384) ? std::max(8192, (share + 3) / 4) / plan_.g.NS * plan_.g.NS : share;
             for (int s0 = bounds[d]; s0 < s_end;) {
                 int lo = std::min(s_end, s0 + plan_.g.NS), hi = std::min(s_end, s0 + std::max(cap_segs, plan_.g.NS));
                 if (dev.wave_bytes(b, s0, hi) > budget) {

@@ -59,8 +59,10 @@ __device__ __forceinline__ uint32_t slot_scan_window(uint32_t E, int t, uint32_t
 // reduced with CREDUX inside the warp and exchanged through one aligned int4 row of shared memory.
 // MULTI (with FAST): several segments share the CTA and its profile table but synchronise separately (named barriers).
 // !FAST: arbitrary lane->segment mapping; keys meet in shared-memory atomicMax (three rotating buffers).
+// Register budget: up to C = 24 the kernel fits 80 registers, which lets two 384-thread CTAs (four segments each) share an
+// SM on saturated launches; ptxas would otherwise settle on 96 and halve the occupancy.
 template <class P, int C, int T, bool FAST, bool MULTI>
-__global__ void sweep_kernel(const SweepArgs a)
+__global__ void __maxnreg__(C <= 24 ? 80 : 255) sweep_kernel(const SweepArgs a)
 {
     extern __shared__ uint4 smem_u4[];
     uint4 *sprof = smem_u4;
