@@ -109,6 +109,7 @@ public:
     // once; collect() waits for that wave and appends its records.  A backend with wave_slots() == 2 overlaps the
     // copies of one wave with the kernels of the other.  Default: the synchronous three-step path.
     virtual int wave_slots() const { return 1; }
+    virtual void reserve(int slot, const Batch &b, int seg_begin, int seg_end) { (void)slot; (void)b; (void)seg_begin; (void)seg_end; }   // size a slot's buffers for its largest wave up front
     virtual void submit(int slot, const Batch &b, int seg_begin, int seg_end) { (void)slot; stage(b, seg_begin, seg_end); execute(); }
     virtual void collect(int slot, BatchResult &out) { (void)slot; fetch(out); }
     double sweep_ms = 0, traceback_ms = 0, h2d_ms = 0, d2h_ms = 0;     // accumulated since reset_stats()

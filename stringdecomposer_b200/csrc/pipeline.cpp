@@ -294,13 +294,14 @@ void Engine::decompose(const Batch &b, BatchResult &out)
             const int64_t budget = dev.wave_budget() / nsl;
             const bool prof = getenv("SD_PROFILE") != nullptr;
             std::vector<std::pair<int, int>> waves;
-            // a large share is cut into at least four waves even if fewer would fit: the first copy-in and the last
-            // copy-out are the only ones that cannot hide behind kernels, so they should be short -- but not shorter than
-            // 8192 segments, below which the tail of a launch (CTAs per SM not a whole number) starts to cost
+            // The copy-in of the first wave is the only one that cannot hide behind kernels (a segment takes ~10x longer to
+            // sweep than to copy), so a large share starts with a small wave and doubles from there: 1/16, 1/8, 1/4, ...
+            // of the share, each at most what the memory budget of a wave slot allows.
             const int share = s_end - bounds[d];
-            const int cap_segs = (nsl > 1 && share > 16384) ? std::max(8192, (share + 3) / 4) / plan_.g.NS * plan_.g.NS : share;
+            int ramp = (nsl > 1 && share >= 4096) ? std::max(1024, share / 16) / plan_.g.NS * plan_.g.NS : share;
             for (int s0 = bounds[d]; s0 < s_end;) {
-                int lo = std::min(s_end, s0 + plan_.g.NS), hi = std::min(s_end, s0 + std::max(cap_segs, plan_.g.NS));
+                int lo = std::min(s_end, s0 + plan_.g.NS), hi = std::min(s_end, s0 + std::max(ramp, plan_.g.NS));
+                if (s_end - hi < ramp / 2) hi = s_end;                 // no tiny last wave
                 if (dev.wave_bytes(b, s0, hi) > budget) {
                     while (hi - lo > plan_.g.NS) {
                         int mid = lo + (hi - lo) / 2 / plan_.g.NS * plan_.g.NS;
@@ -311,7 +312,17 @@ void Engine::decompose(const Batch &b, BatchResult &out)
                 }
                 waves.emplace_back(s0, hi);
                 s0 = hi;
+                if (ramp < share) ramp *= 2;
             }
+            if (waves.size() > 2)
+                for (int sl = 0; sl < nsl; ++sl) {              // each slot's buffers sized once, for the largest wave it will hold
+                    int best = -1; int64_t bytes = -1;
+                    for (size_t w = (size_t)sl; w < waves.size(); w += (size_t)nsl) {
+                        const int64_t wb = dev.wave_bytes(b, waves[w].first, waves[w].second);
+                        if (wb > bytes) { bytes = wb; best = (int)w; }
+                    }
+                    if (best >= 0) dev.reserve(sl, b, waves[(size_t)best].first, waves[(size_t)best].second);
+                }
             auto now = [] { return std::chrono::steady_clock::now(); };
             auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
             const auto t0 = now();

@@ -59,10 +59,8 @@ __device__ __forceinline__ uint32_t slot_scan_window(uint32_t E, int t, uint32_t
 // reduced with CREDUX inside the warp and exchanged through one aligned int4 row of shared memory.
 // MULTI (with FAST): several segments share the CTA and its profile table but synchronise separately (named barriers).
 // !FAST: arbitrary lane->segment mapping; keys meet in shared-memory atomicMax (three rotating buffers).
-// Register budget: up to C = 24 the kernel fits 80 registers, which lets two 384-thread CTAs (four segments each) share an
-// SM on saturated launches; ptxas would otherwise settle on 96 and halve the occupancy.
 template <class P, int C, int T, bool FAST, bool MULTI>
-__global__ void __maxnreg__(C <= 24 ? 80 : 255) sweep_kernel(const SweepArgs a)
+__device__ __forceinline__ void sweep_body(const SweepArgs &a)
 {
     extern __shared__ uint4 smem_u4[];
     uint4 *sprof = smem_u4;
@@ -235,6 +233,15 @@ __global__ void __maxnreg__(C <= 24 ? 80 : 255) sweep_kernel(const SweepArgs a)
     }
 }
 
+
+template <class P, int C, int T, bool FAST, bool MULTI>
+__global__ void sweep_kernel(const SweepArgs a) { sweep_body<P, C, T, FAST, MULTI>(a); }
+
+// The same kernel with its register budget pinned at 80: saturated launches (several segments per CTA, C <= 24) then fit
+// two 384-thread CTAs per SM; left alone ptxas settles on 96 registers and halves the occupancy (measured: 3.95 -> 4.11
+// TCUPS on 4,000 segments).  Only used for CTAs of at most 768 threads.
+template <class P, int C, int T, bool FAST, bool MULTI>
+__global__ void __maxnreg__(80) sweep_kernel_r80(const SweepArgs a) { sweep_body<P, C, T, FAST, MULTI>(a); }
 
 // ---------------------------------------------------------------------------------------------------------------
 // Group sweep: monomer sets that do not fit one CTA (threads, registers, or the shared-memory profile table).
@@ -436,36 +443,45 @@ __global__ void sweep_group_kernel(const GroupArgs a)
 }
 
 // lookup tables of the instantiations, one translation unit per (policy, FAST, MULTI) so that they build in parallel
-const void *sweep_lookup_p16_f1_m0(int C, int T);
-const void *sweep_lookup_p16_f1_m1(int C, int T);
-const void *sweep_lookup_p16_f0_m0(int C, int T);
-const void *sweep_lookup_s32_f1_m0(int C, int T);
-const void *sweep_lookup_s32_f1_m1(int C, int T);
-const void *sweep_lookup_s32_f0_m0(int C, int T);
+const void *sweep_lookup_p16_f1_m0(int C, int T, int NT);
+const void *sweep_lookup_p16_f1_m1(int C, int T, int NT);
+const void *sweep_lookup_p16_f0_m0(int C, int T, int NT);
+const void *sweep_lookup_s32_f1_m0(int C, int T, int NT);
+const void *sweep_lookup_s32_f1_m1(int C, int T, int NT);
+const void *sweep_lookup_s32_f0_m0(int C, int T, int NT);
 const void *sweep_group_lookup_p16(int C, int T);
 const void *sweep_group_lookup_s32(int C, int T);
 
+// the register-capped twin is instantiated only where it is used: several segments per CTA (LL) and C <= 24
+template <class POLICY, int CC, int TT, bool FAST, bool LL> static const void *sweep_pick(bool cap80)
+{
+    if constexpr (LL && CC <= 24) { if (cap80) return (const void *)sweep_kernel_r80<POLICY, CC, TT, FAST, LL>; }
+    (void)cap80;
+    return (const void *)sweep_kernel<POLICY, CC, TT, FAST, LL>;
+}
+#define SD_SWEEP_PICK(POLICY, CC, TT, FAST, LL) sweep_pick<POLICY, CC, TT, FAST, LL>(cap80)
 #define SD_INSTANTIATE_SWEEP(NAME, POLICY, FAST, LL)                                                                 \
-    template <int C> static const void *NAME##_t(int T)                                                              \
+    template <int C> static const void *NAME##_t(int T, bool cap80)                                                  \
     {                                                                                                                 \
         switch (T) {                                                                                                  \
-        case 1: return (const void *)sweep_kernel<POLICY, C, 1, FAST, LL>;                                            \
-        case 2: return (const void *)sweep_kernel<POLICY, C, 2, FAST, LL>;                                            \
-        case 4: return (const void *)sweep_kernel<POLICY, C, 4, FAST, LL>;                                            \
-        case 8: return (const void *)sweep_kernel<POLICY, C, 8, FAST, LL>;                                            \
-        case 10: return (const void *)sweep_kernel<POLICY, C, 10, FAST, LL>;                                          \
-        case 16: return (const void *)sweep_kernel<POLICY, C, 16, FAST, LL>;                                          \
-        case 32: return (const void *)sweep_kernel<POLICY, C, 32, FAST, LL>;                                          \
+        case 1: return SD_SWEEP_PICK(POLICY, C, 1, FAST, LL);                                                         \
+        case 2: return SD_SWEEP_PICK(POLICY, C, 2, FAST, LL);                                                         \
+        case 4: return SD_SWEEP_PICK(POLICY, C, 4, FAST, LL);                                                         \
+        case 8: return SD_SWEEP_PICK(POLICY, C, 8, FAST, LL);                                                         \
+        case 10: return SD_SWEEP_PICK(POLICY, C, 10, FAST, LL);                                                       \
+        case 16: return SD_SWEEP_PICK(POLICY, C, 16, FAST, LL);                                                       \
+        case 32: return SD_SWEEP_PICK(POLICY, C, 32, FAST, LL);                                                       \
         }                                                                                                             \
         return nullptr;                                                                                               \
     }                                                                                                                 \
-    const void *NAME(int C, int T)                                                                                    \
+    const void *NAME(int C, int T, int NT)                                                                            \
     {                                                                                                                 \
+        const bool cap80 = NT <= 768;                                                                                 \
         switch (C) {                                                                                                  \
-        case 8: return NAME##_t<8>(T); case 12: return NAME##_t<12>(T); case 16: return NAME##_t<16>(T);              \
-        case 19: return NAME##_t<19>(T); case 20: return NAME##_t<20>(T); case 24: return NAME##_t<24>(T);              \
-        case 32: return NAME##_t<32>(T);            \
-        case 48: return NAME##_t<48>(T);                                                                              \
+        case 8: return NAME##_t<8>(T, cap80); case 12: return NAME##_t<12>(T, cap80); case 16: return NAME##_t<16>(T, cap80);   \
+        case 19: return NAME##_t<19>(T, cap80); case 20: return NAME##_t<20>(T, cap80); case 24: return NAME##_t<24>(T, cap80); \
+        case 32: return NAME##_t<32>(T, cap80);                                                                       \
+        case 48: return NAME##_t<48>(T, cap80);                                                                       \
         }                                                                                                             \
         return nullptr;                                                                                               \
     }

@@ -369,10 +369,10 @@ template <int MODE> __global__ void int_peak_kernel(unsigned *out, unsigned seed
 }
 
 // ---------------------------------------------------------------------------------------------
-static const void *kern(int packed, int C, int T, bool fast, bool multi)
+static const void *kern(int packed, int C, int T, int NT, bool fast, bool multi)
 {
-    if (packed) return fast ? (multi ? sweep_lookup_p16_f1_m1(C, T) : sweep_lookup_p16_f1_m0(C, T)) : sweep_lookup_p16_f0_m0(C, T);
-    return fast ? (multi ? sweep_lookup_s32_f1_m1(C, T) : sweep_lookup_s32_f1_m0(C, T)) : sweep_lookup_s32_f0_m0(C, T);
+    if (packed) return fast ? (multi ? sweep_lookup_p16_f1_m1(C, T, NT) : sweep_lookup_p16_f1_m0(C, T, NT)) : sweep_lookup_p16_f0_m0(C, T, NT);
+    return fast ? (multi ? sweep_lookup_s32_f1_m1(C, T, NT) : sweep_lookup_s32_f1_m0(C, T, NT)) : sweep_lookup_s32_f0_m0(C, T, NT);
 }
 
 namespace {
@@ -465,12 +465,14 @@ public:
             if ((g.NT / 32) * g.NG > 32) throw PlanError{"internal: a deferred-jump cluster holds at most 32 warps"};
         }
         else kernel_ = g.NG > 1 ? (g.packed ? sweep_group_lookup_p16(g.C, g.T) : sweep_group_lookup_s32(g.C, g.T))
-                                : kern(g.packed, g.C, g.T, fast_, fast_ && g.NS > 1);
+                                : kern(g.packed, g.C, g.T, g.NT, fast_, fast_ && g.NS > 1);
         if (!kernel_) throw PlanError{"no sweep kernel compiled for this geometry"};
         cudaFuncAttributes fa;
         SD_CUDA(cudaFuncGetAttributes(&fa, kernel_));
         // registers are handed out per warp in units of 8 per thread
-        if ((int64_t)((fa.numRegs + 7) / 8 * 8) * g.NT * (g.NG > 1 && !g.lat ? g.NS : 1) > 65536) throw PlanError{"sweep geometry exceeds the register file (regs*threads > 64K)"};
+        const int nthreads = g.NT * (g.NG > 1 && !g.lat ? g.NS : 1);
+        if ((int64_t)((fa.numRegs + 7) / 8 * 8) * nthreads > 65536 || fa.maxThreadsPerBlock < nthreads)
+            throw PlanError{"sweep geometry exceeds the register file (regs*threads > 64K)"};
         const std::vector<uint32_t> &table = g.lat ? p.prof2 : p.prof;
         d_prof_.need(table.size() * 4);
         SD_CUDA(cudaMemcpyAsync(d_prof_.p, table.data(), table.size() * 4, cudaMemcpyHostToDevice, st_));
@@ -512,6 +514,22 @@ public:
         return budget_;        // 85 % of the memory that was free when the backend was created (cudaMemGetInfo costs ms)
     }
     int wave_slots() const override { return 2; }
+
+    // Buffers of a slot sized for the largest wave it will see: growing them later would mean cudaFree (a device-wide
+    // synchronisation) in the middle of the pipeline.
+    void reserve(int slot, const Batch &b, int s0, int s1) override
+    {
+        DeviceScope scope_(dev_); SD_CUDA(scope_.status);
+        WaveSlot &w = slot_[slot & 1];
+        const CtaLayout lay = make_cta_layout(plan_, b, s0, s1);
+        const int nseg = s1 - s0;
+        w.d_bases.need((size_t)(b.off[s1] - b.off[s0]) + 16);
+        w.d_codes.need((size_t)lay.cta_code_off.back() * 4 + 16);
+        w.d_jr.need((size_t)lay.seg_j_off.back() * sizeof(JR) + 16);
+        w.d_scratch.need((size_t)lay.seg_rec_off.back() * sizeof(Record) + 16);
+        w.d_out.need(OUT_HDR + out_counts_bytes(nseg) + (size_t)lay.seg_rec_off.back() * sizeof(Record) + 64);
+        w.h_out.need(OUT_HDR + out_counts_bytes(nseg) + ((size_t)(b.off[s1] - b.off[s0]) / 48 + (size_t)nseg * 4 + 64) * sizeof(Record));
+    }
 
     // ---- the three stages of a wave, each asynchronous on its own stream ----------------------------------------
     void enqueue_h2d(WaveSlot &w, const Batch &b, int s0, int s1)

@@ -146,8 +146,8 @@ __global__ void sweep_lat_kernel(const LatArgs a)
     JR *jptr = a.jr + a.seg_j_off[seg];
     uint32_t *cptr = a.codes + a.cta_code_off[(size_t)seg * NG + grp] + (size_t)tid * a.CW;
     const size_t cstride = (size_t)NT * a.CW;
-    const uint4 *myprof = sprof + (size_t)(ginst * T + t) * a.qp2;
-    const int sym_stride = sgt * a.qp2;
+    const uint32_t myprof = (uint32_t)__cvta_generic_to_shared(sprof + (size_t)(ginst * T + t) * a.qp2);
+    const uint32_t sym_stride = 16u * (uint32_t)(sgt * a.qp2);         // bytes between the rows of two symbols
 
     // exchange: warp w of CTA c owns word [buf][c*wpc + w] in EVERY CTA of the cluster; lane c of a warp stores to CTA c.
     // Lanes >= nwtot read (again) the word of warp lane % nwtot, so that all lanes of a warp run the same poll.
@@ -189,20 +189,26 @@ __global__ void sweep_lat_kernel(const LatArgs a)
     constexpr int QP_END = (C + 3) / 4;                  // uint4 [0, QP_END) hold p
     constexpr int QT_BEG = C / 4;                        // uint4 [QT_BEG, CQ2) hold PT
     uint32_t X[C], pw[C], pt[C];
-    auto load_p = [&](const uint4 *pp) {
+    // profile rows are addressed in the shared window directly (a generic pointer would be re-converted every column)
+    auto lds128 = [](uint32_t addr) {
+        uint4 v;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+        return v;
+    };
+    auto load_p = [&](uint32_t pp) {
 #pragma unroll
         for (int q = 0; q < QP_END; ++q) {
-            const uint4 v = pp[q];
+            const uint4 v = lds128(pp + 16u * q);
             if (4 * q + 0 < C) pw[4 * q + 0] = v.x;
             if (4 * q + 1 < C) pw[4 * q + 1] = v.y;
             if (4 * q + 2 < C) pw[4 * q + 2] = v.z;
             if (4 * q + 3 < C) pw[4 * q + 3] = v.w;
         }
     };
-    auto load_pt = [&](const uint4 *pp) {
+    auto load_pt = [&](uint32_t pp) {
 #pragma unroll
         for (int q = QT_BEG; q < CQ2; ++q) {
-            const uint4 v = pp[q];
+            const uint4 v = lds128(pp + 16u * q);
             if (4 * q + 0 >= C && 4 * q + 0 < 2 * C) pt[4 * q + 0 - C] = v.x;
             if (4 * q + 1 >= C && 4 * q + 1 < 2 * C) pt[4 * q + 1 - C] = v.y;
             if (4 * q + 2 >= C && 4 * q + 2 < 2 * C) pt[4 * q + 2 - C] = v.z;
@@ -233,7 +239,7 @@ __global__ void sweep_lat_kernel(const LatArgs a)
     {
         const uint32_t E = lane_post<P, C>(X, pw, P::splat(1), deadu, tr);
         const uint32_t carry = window_carry<P, T, 0>(E, t, deadu);
-        const uint4 *pn = myprof + schar[1] * sym_stride;
+        const uint32_t pn = myprof + schar[1] * sym_stride;
         load_p(pn);
         load_pt(pn);
         uint32_t ufirst;
@@ -272,7 +278,7 @@ __global__ void sweep_lat_kernel(const LatArgs a)
         // J-independent part of column i (X holds max(diag, up))
         const uint32_t total = lat_total<P, C>(X, trr);
         const int symn = sp[0];
-        const uint4 *pn = myprof + symn * sym_stride;
+        const uint32_t pn = myprof + (uint32_t)symn * sym_stride;
         const uint32_t carry = window_carry<P, T, WN>(total, t, deadu);
         tick(0);
         load_p(pn);                                       // flies during the chain
