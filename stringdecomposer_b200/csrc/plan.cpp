@@ -285,12 +285,16 @@ Plan make_plan(const MonomerSet &ms, const Scoring &sc, int max_seg_len, int64_t
                 const int qp2c = ((2 * C + 3) / 4) | 1;
                 const size_t smem = (size_t)5 * sg * T * qp2c * 16 + (size_t)max_seg_len + 4096;
                 if (smem > kSmemLimit) continue;
-                // measured on the B200 (tools/lat_probe.py, 12 DXZ1 monomers): a lone warp per scheduler needs
-                // 392 + 9 C cycles per column -- (6,32) 446, (12,16) 495, (24,8) 607 --; warps that share a scheduler
-                // serialise on issue (~2 cycles per ALU instruction, 6.5 C + 60 of them) and jitter against each other
-                const int ctas_sm = (int)((nseg * ng + 147) / 148), wsched = (ctas_sm * wc + 3) / 4;
-                const double cost = (double)std::max(max_seg_len, 1) * std::max(392.0 + 9.0 * C + 2.0 * W, wsched * 2.0 * (6.5 * C + 60.0)) *
-                                    (wsched > 1 ? 1.18 : 1.0);
+                // Measured on the B200 (tools/lat_probe.py, profiles/r02_lat_timing.txt, 12 DXZ1 monomers).  With one CTA
+                // per SM a column takes 415 cycles at (6,32), 510 at (12,16), 605 at (24,8); every further CTA that has
+                // to share the SM stretches it by 0.3 (C/6)^0.6 -- 520 / 690 / 855 cycles for 2 / 3 / 4 CTAs at (6,32),
+                // 705 for 2 at (12,16), 1080 for 2 at (24,8): the warps then compete for issue slots.
+                static const double kBaseC[] = {6, 12, 24, 48}, kBaseCycles[] = {415, 510, 605, 900};
+                double base = kBaseCycles[3];
+                for (int q = 0; q < 3; ++q)
+                    if (C <= kBaseC[q + 1]) { base = kBaseCycles[q] + (kBaseCycles[q + 1] - kBaseCycles[q]) * std::max(0.0, C - kBaseC[q]) / (kBaseC[q + 1] - kBaseC[q]); break; }
+                const int ctas_sm = (int)((nseg * ng + 147) / 148);
+                const double cost = (double)std::max(max_seg_len, 1) * base * (1.0 + 0.3 * std::pow(C / 6.0, 0.6) * (ctas_sm - 1));
                 if (cost < lbest) { lbest = cost; lC = C; lT = T; lNT = wc * 32; lNG = ng; lSG = sg; lW = W; }
             }
         const bool want = lat_mode > 0 || (lat_mode < 0 && lC && g.NG == 1 && nseg <= 2 * 148 && lbest < 0.97 * best);
