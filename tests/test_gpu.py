@@ -213,6 +213,10 @@ def test_multi_gpu_output_identical(ngpu):
     one = decompose_reads(rn3, reads3, mn3, mons3, devices=[0])
     allg = decompose_reads(rn3, reads3, mn3, mons3, devices=list(range(ngpu)))
     assert one == allg
+    # and the streamed dp binary itself with SD_DEVICES (chunks small enough that several are in flight)
+    picked = [c for c in cases.load_cases() if c["name"] in ("multi_read", "len_10000_default")]
+    for case in picked:
+        cases.check_case(cases.DP_CUDA, case, env={"SD_DEVICES": str(ngpu), "SD_CHUNK_BASES": "4000"})
 
 
 LAT_SUBSET = ("multi_read", "scoring_-3_-2_-4_2", "N_in_monomer", "dup_monomers_rev", "len_5501_default", "short_monomers", "N_in_read")
