@@ -386,3 +386,25 @@ def test_gpu_identity_full_size_properties():
     for i in samp:
         for j in (truth[i], (truth[i] + 5) % len(rows)):
             assert (d[i, j], m[i, j], c[i, j]) == O.nw_path_counts(qs[i], rows[j])
+
+
+def test_raw_file_is_streamed_in_chunks_of_whole_reads(tmp_path):
+    # main.py:195-197 reads the raw file into one string; the rescoring stage here streams it (convert.raw_chunks) and
+    # must produce the same two files whatever the chunk size
+    from stringdecomposer_b200 import convert as cv
+    G = cases.GOLDEN
+    raw = open(os.path.join(G, "config1_raw_default.tsv")).read()
+    lines = raw.splitlines(True)
+    two = "".join(lines[:300]) + "".join(ln.replace(lines[0].split("\t")[0], "second_read", 1) for ln in lines[:200])
+    rp = tmp_path / "raw.tsv"
+    rp.write_text(two)
+    chunks = list(cv.raw_chunks(str(rp), 4000))
+    assert "".join(chunks) == two and len(chunks) == 2            # cut only where the read name changes
+    reads = cv.load_fasta(os.path.join(G, "config1_read.fa"), "map")
+    reads["second_read"] = next(iter(reads.values()))
+    mons = cv.add_rc_monomers(cv.load_fasta(os.path.join(G, "DXZ1_star_monomers.fa")))
+    a, b = str(tmp_path / "a.tsv"), str(tmp_path / "b.tsv")
+    cv.convert_tsv_native(two, reads, mons, a, 0, True, flavour=cases.EMU_LIB)
+    cv.convert_raw_file_native(str(rp), reads, mons, b, 0, True, flavour=cases.EMU_LIB, max_bytes=4000)
+    assert open(a).read() == open(b).read() and open(a[:-4] + "_alt.tsv").read() == open(b[:-4] + "_alt.tsv").read()
+
