@@ -424,7 +424,7 @@ struct WaveSlot {
     int s0 = 0, s1 = 0, nseg = 0, nmax = 0;
     bool filter_on = false, staged = false;
     size_t nb = 0, rec_guess = 0;
-    cudaEvent_t ev[6]{};            // 0 h2d begin, 1 h2d end, 2 sweep begin, 3 sweep end, 4 traceback end, 5 d2h end
+    cudaEvent_t ev[7]{};            // 0 h2d begin, 1 h2d end, 2 sweep begin, 3 sweep end, 4 traceback end, 5 d2h end, 6 traceback begin
 };
 
 class CudaBackend : public Backend {
@@ -435,6 +435,7 @@ public:
         SD_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
         SD_CUDA(cudaStreamCreateWithFlags(&st_in_, cudaStreamNonBlocking));
         SD_CUDA(cudaStreamCreateWithFlags(&st_out_, cudaStreamNonBlocking));
+        SD_CUDA(cudaStreamCreateWithFlags(&st_tb_, cudaStreamNonBlocking));
         for (auto &w : slot_) for (auto &e : w.ev) SD_CUDA(cudaEventCreate(&e));
         SD_CUDA(cudaGetDeviceProperties(&prop_, dev_));
         if (prop_.major != 10) throw PlanError{"CUDA device is not sm_100 class: this library carries sm_100a code only (no PTX for other architectures)"};
@@ -446,7 +447,7 @@ public:
     {
         DeviceScope scope_(dev_);
         for (auto &w : slot_) for (auto &e : w.ev) cudaEventDestroy(e);
-        cudaStreamDestroy(st_); cudaStreamDestroy(st_in_); cudaStreamDestroy(st_out_);
+        cudaStreamDestroy(st_); cudaStreamDestroy(st_in_); cudaStreamDestroy(st_out_); cudaStreamDestroy(st_tb_);
     }
     const char *name() const override { return "cuda"; }
 
@@ -723,6 +724,10 @@ public:
         SD_CUDA(cudaEventRecord(w.ev[2], st_));
         if (g.lat) launch_lat(w, seg_stride); else if (g.NG > 1) launch_group(w); else launch_single(w, seg_stride);
         SD_CUDA(cudaEventRecord(w.ev[3], st_));
+        // the traceback (a latency-bound walk, one warp per segment) and the compaction run on their own stream: the
+        // sweep of the next wave starts as soon as this one's sweep is done and the two overlap
+        SD_CUDA(cudaStreamWaitEvent(st_tb_, w.ev[3], 0));
+        SD_CUDA(cudaEventRecord(w.ev[6], st_tb_));
         TbArgs t;
         t.g = g; t.codes = w.d_codes.as<uint32_t>(); t.cta_code_off = w.d_ctacode.as<int64_t>(); t.jr = w.d_jr.as<JR>();
         t.seg_j_off = w.d_segj.as<int64_t>();
@@ -735,9 +740,9 @@ public:
         t.invC = (65536 + g.C - 1) / g.C;
         for (int pos = 0; pos < g.C * g.T; ++pos)
             if (((pos * t.invC) >> 16) != pos / g.C) throw PlanError{"internal: reciprocal division inexact"};
-        traceback_kernel<<<(w.nseg + TB_WARPS - 1) / TB_WARPS, TB_WARPS * 32, 0, st_>>>(t);
+        traceback_kernel<<<(w.nseg + TB_WARPS - 1) / TB_WARPS, TB_WARPS * 32, 0, st_tb_>>>(t);
         SD_CUDA(cudaGetLastError());
-        SD_CUDA(cudaEventRecord(w.ev[4], st_));
+        SD_CUDA(cudaEventRecord(w.ev[4], st_tb_));
         launches += 2;
     }
 
@@ -745,7 +750,7 @@ public:
     {
         char *ob = w.d_out.as<char>();
         Record *dense = reinterpret_cast<Record *>(ob + OUT_HDR + out_counts_bytes(w.nseg));
-        gather_kernel<<<1, 1024, 0, st_>>>(w.d_scratch.as<Record>(), w.d_segrec.as<int64_t>(), reinterpret_cast<int *>(ob + OUT_HDR),
+        gather_kernel<<<1, 1024, 0, st_tb_>>>(w.d_scratch.as<Record>(), w.d_segrec.as<int64_t>(), reinterpret_cast<int *>(ob + OUT_HDR),
                                           dense, w.nseg, reinterpret_cast<int *>(ob) + 2);
         SD_CUDA(cudaGetLastError());
         launches += 1;
@@ -757,7 +762,7 @@ public:
         const size_t first = OUT_HDR + out_counts_bytes(w.nseg) + w.rec_guess * sizeof(Record);
         const size_t cap = OUT_HDR + out_counts_bytes(w.nseg) + (size_t)w.lay.seg_rec_off.back() * sizeof(Record);
         w.h_out.need(std::min(first, cap));
-        SD_CUDA(cudaEventRecord(w.ev[5], st_));                                    // compute done ...
+        SD_CUDA(cudaEventRecord(w.ev[5], st_tb_));                                 // compute done ...
         SD_CUDA(cudaStreamWaitEvent(st_out_, w.ev[5], 0));                        // ... before the copy starts
         SD_CUDA(cudaMemcpyAsync(w.h_out.p, w.d_out.p, std::min(first, cap), cudaMemcpyDeviceToHost, st_out_));
         SD_CUDA(cudaEventRecord(w.ev[5], st_out_));
@@ -790,7 +795,7 @@ public:
         float ms = 0;
         SD_CUDA(cudaEventElapsedTime(&ms, w.ev[0], w.ev[1])); h2d_ms += ms;
         SD_CUDA(cudaEventElapsedTime(&ms, w.ev[2], w.ev[3])); sweep_ms += ms;
-        SD_CUDA(cudaEventElapsedTime(&ms, w.ev[3], w.ev[4])); traceback_ms += ms;
+        SD_CUDA(cudaEventElapsedTime(&ms, w.ev[6], w.ev[4])); traceback_ms += ms;
         d2h_bytes += (int64_t)(rec_off + (size_t)total * sizeof(Record));
         w.staged = false;
     }
@@ -833,13 +838,13 @@ public:
         SD_CUDA(cudaMemsetAsync(w.d_out.p, 0, OUT_HDR, st_));
         enqueue_kernels(w);
         int flag[2] = {0, 0};
-        SD_CUDA(cudaMemcpyAsync(flag, w.d_out.p, 8, cudaMemcpyDeviceToHost, st_));
-        SD_CUDA(cudaStreamSynchronize(st_));
+        SD_CUDA(cudaMemcpyAsync(flag, w.d_out.p, 8, cudaMemcpyDeviceToHost, st_tb_));
+        SD_CUDA(cudaStreamSynchronize(st_tb_));
         if (flag[1]) throw PlanError{"CUDA: sweep timed out waiting for a partner CTA (internal error)"};
         if (flag[0]) throw PlanError{"segment contains a symbol outside ACGTN"};
         float ms = 0;
         SD_CUDA(cudaEventElapsedTime(&ms, w.ev[2], w.ev[3])); sweep_ms += ms;
-        SD_CUDA(cudaEventElapsedTime(&ms, w.ev[3], w.ev[4])); traceback_ms += ms;
+        SD_CUDA(cudaEventElapsedTime(&ms, w.ev[6], w.ev[4])); traceback_ms += ms;
     }
     void fetch(BatchResult &out) override
     {
@@ -854,7 +859,7 @@ public:
 
 private:
     int dev_;
-    cudaStream_t st_{}, st_in_{}, st_out_{};
+    cudaStream_t st_{}, st_in_{}, st_out_{}, st_tb_{};      // sweep, copy-in, copy-out, traceback + compaction
     cudaDeviceProp prop_{};
     Plan plan_; MonomerSet ms_;
     const void *kernel_ = nullptr;
