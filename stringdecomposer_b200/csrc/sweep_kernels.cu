@@ -1,14 +1,19 @@
 // sweep_kernels.cu -- sm_100a kernels of the string-decomposition DP and the CUDA backend that drives them.
 //
-//   sweep_kernel<P,C,T>   column-synchronous forward sweep.  A CTA owns NS segments; every DP row pair (Packed16:
-//                         forward monomer + reverse complement in the two s16 halves of a register) or row (Scalar32)
-//                         is a slot of T lanes x C cells held in registers.  Per column: pass 1 (chain-free
-//                         candidates, DPX VIADDMNMX), prefix-max scan of the deletion chain across the T lanes
-//                         (warp shuffles), pass 2 (chain + 2-bit backpointers), per-segment max/argmax of the row
-//                         ends through shared-memory atomicMax on a (score,row) key, one barrier.
-//   traceback_kernel      walks the 2-bit backpointers (sweep_core.cuh: traceback_segment).
-//   gather_kernel         compacts + reverses the per-segment records into one dense array for the D2H copy.
-//   int_peak_kernel       integer-pipe issue-rate probe the roofline is quoted against.
+//   sweep_kernel<P,C,T>       (sweep_kernel.cuh) column-synchronous forward sweep, one CTA per NS segments.  Every DP row
+//                             pair (Packed16: forward monomer + reverse complement in the two s16 halves of a register) or
+//                             row (Scalar32) is a slot of T lanes x C cells held in registers.  Per column: chain-free
+//                             candidates (DPX VIADDMNMX), windowed carry of the deletion chain across the lanes (warp
+//                             shuffles), chain + 2-bit backpointers, per-segment max/argmax of the row ends on a
+//                             (score,row) key (CREDUX + one shared-memory word per warp), one barrier.
+//   sweep_group_kernel        the same for monomer sets that need several CTAs per segment (keys meet in global memory).
+//   sweep_lat_kernel<P,C,T,W> (sweep_lat_kernel.cuh) deferred-jump form, one segment per thread-block cluster, keys
+//                             exchanged through distributed shared memory one column ahead of their use.
+//   traceback_kernel          walks the 2-bit backpointers (sweep_core.cuh: traceback_segment).
+//   hw_distance_rows_kernel, filter_rank_kernel    the --ed_thr pre-filter (distances, ranks) on the device.
+//   gather_kernel             compacts + reverses the per-segment records into the result block of a wave.
+//   int_peak_kernel           integer-pipe issue-rate probe the roofline is quoted against.
+// and the CUDA backend: two wave slots per device, streams for copy-in / sweep / traceback / copy-out.
 //
 // Reference semantics: stringdecomposer/src/main.cpp:151-270 (AlignPartClassicDP); see sweep_core.cuh.
 #include <cuda_runtime.h>
