@@ -257,16 +257,21 @@ def timed_resident(dec, packed, args, ws, flushes, sampler_gpu):
 
 
 def timed_e2e(dec, packed, args, ws):
-    """`e2e` leg: host buffers through sd_decompose, H2D + kernels + D2H inside the timed region."""
+    """`e2e` leg: host buffers through the C-ABI call sd_decompose, H2D + kernels + D2H inside the timed region.  The K
+    calls are issued back to back from native code (libsd_bench.so), as a C/C++ host application would; the same loop
+    from Python (ctypes + numpy copies of the result per call) is reported next to it."""
     for _ in range(args.warmup):
         dec.decompose(packed)
-    dec.reset_stats()
     barrier_sync(ws)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         r2, o2 = dec.decompose(packed)
+    py_s = time.perf_counter() - t0
+    dec.reset_stats()
+    sec, nrec = dec.decompose_timed(packed, 0, args.steps)
     barrier_sync(ws)
-    return time.perf_counter() - t0, dec.stats(), r2, o2
+    assert nrec == len(r2)
+    return sec, dec.stats(), r2, o2, py_s
 
 
 def pack_segments(segs):
@@ -317,7 +322,7 @@ def main():
         flushes = [torch.empty(256 << 20, dtype=torch.uint8, device="cuda:%d" % d) for d in range(ws)]
         dev_ms, wall, clocks, st = timed_resident(dec, packed, args, ws, flushes, local)
         recs, roff = dec.fetch_staged()
-        e2e_s, st2, r2, o2 = timed_e2e(dec, packed, args, ws)
+        e2e_s, st2, r2, o2, e2e_py_s = timed_e2e(dec, packed, args, ws)
         same = bool(len(r2) == len(recs) and (r2 == recs).all() and (o2 == roff).all())
         value = cells_hl * args.steps / (dev_ms * 1e-3) / 1e9
         sweep_ms = st["sweep_ms"] / args.steps
@@ -352,6 +357,9 @@ def main():
                 "wall_ms_per_step": 1e3 * wall / args.steps,
                 "e2e": {"value": cells_hl * args.steps / e2e_s / 1e9, "unit": UNIT, "h2d_bytes_per_step": st2["h2d_bytes"] // args.steps,
                         "d2h_bytes_per_step": st2["d2h_bytes"] // args.steps, "ms_per_step": 1e3 * e2e_s / args.steps,
+                        "python_caller_ms_per_step": 1e3 * e2e_py_s / args.steps,
+                        "caller": "sd_decompose called K times back to back from native code (libsd_bench.so); python_caller_ms_per_step "
+                                  "is the same loop through ctypes",
                         "matches_resident_run": same},
                 "gpu_launches": int(st["launches"]), "clocks": clocks, "roofline": roof}
         if ws == 1 and not args.no_extras:

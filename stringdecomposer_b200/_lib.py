@@ -193,6 +193,21 @@ class Decomposer:
             self._err(st)
         return self._take(recs, offs, self._staged)
 
+    def decompose_timed(self, segments, warmup, steps):
+        """sd_decompose() `steps` times back to back from native code (libsd_bench.so: a loop around the C-ABI call, no
+        Python between the calls); returns (seconds, records of the last call).  bench.py's end-to-end leg."""
+        bl = C.CDLL(os.path.join(_HERE, "libsd_bench.so"))
+        bl.sd_bench_decompose.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64), C.c_int64, C.c_int32, C.c_int32,
+                                          C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+        bl.sd_bench_decompose.restype = C.c_int
+        blob, off = segments if isinstance(segments, tuple) else _pack(segments)
+        sec, nrec = C.c_double(), C.c_int64()
+        st = bl.sd_bench_decompose(self._h, blob, off.ctypes.data_as(C.POINTER(C.c_int64)), len(off) - 1, warmup, steps,
+                                   C.byref(sec), C.byref(nrec))
+        if st:
+            self._err(st)
+        return sec.value, nrec.value
+
     def set_ed_thr(self, ed_thr):
         """--ed_thr monomer pre-filter (FilterMonomersForRead, main.cpp:135-149); -1 switches it off."""
         st = self._lib.sd_set_ed_thr(self._h, ed_thr)

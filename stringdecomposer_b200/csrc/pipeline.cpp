@@ -341,9 +341,12 @@ void Engine::decompose(const Batch &b, BatchResult &out)
     for (int d = 0; d < nd; ++d) if (!errs[d].empty()) throw PlanError{errs[d]};
     double sw = 0, tb = 0, h2d = 0, d2h = 0;
     for (int d = 0; d < nd; ++d) {
-        const int64_t base = (int64_t)out.recs.size();
-        out.recs.insert(out.recs.end(), part[d].recs.begin(), part[d].recs.end());
-        for (size_t x = 1; x < part[d].rec_off.size(); ++x) out.rec_off.push_back(base + part[d].rec_off[x]);
+        if (nd == 1) { out.recs.swap(part[0].recs); out.rec_off.swap(part[0].rec_off); }    // one device: no merge copy
+        else {
+            const int64_t base = (int64_t)out.recs.size();
+            out.recs.insert(out.recs.end(), part[d].recs.begin(), part[d].recs.end());
+            for (size_t x = 1; x < part[d].rec_off.size(); ++x) out.rec_off.push_back(base + part[d].rec_off[x]);
+        }
         sw = std::max(sw, devs_[d]->sweep_ms); tb = std::max(tb, devs_[d]->traceback_ms);
         h2d = std::max(h2d, devs_[d]->h2d_ms); d2h = std::max(d2h, devs_[d]->d2h_ms);
         stats.h2d_bytes += devs_[d]->h2d_bytes; stats.d2h_bytes += devs_[d]->d2h_bytes; stats.launches += devs_[d]->launches;

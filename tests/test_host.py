@@ -21,6 +21,9 @@ def test_cuda_library_loads_and_exports_every_declared_symbol():
     for s in declared:
         assert hasattr(lib, s), s
     assert "sm_100a" in _lib.load_library("cuda").sd_version().decode()
+    # the timing harness of bench.py's end-to-end leg: a loop around the C-ABI call, nothing else
+    bl = ctypes.CDLL(os.path.join(os.path.dirname(_lib.library_path("cuda")), "libsd_bench.so"))
+    assert hasattr(bl, "sd_bench_decompose")
 
 
 def test_product_library_has_no_cpu_path():
