@@ -260,15 +260,17 @@ def timed_e2e(dec, packed, args, ws):
     """`e2e` leg: host buffers through the C-ABI call sd_decompose, H2D + kernels + D2H inside the timed region.  The K
     calls are issued back to back from native code (libsd_bench.so), as a C/C++ host application would; the same loop
     from Python (ctypes + numpy copies of the result per call) is reported next to it."""
+    from stringdecomposer_b200._lib import HostBuffer
+    pinned = HostBuffer.pack(packed)                    # the step's inputs in page-locked host memory (sd_host_alloc)
     for _ in range(args.warmup):
-        dec.decompose(packed)
+        dec.decompose(pinned)
     barrier_sync(ws)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        r2, o2 = dec.decompose(packed)
+        r2, o2 = dec.decompose(pinned)
     py_s = time.perf_counter() - t0
     dec.reset_stats()
-    sec, nrec = dec.decompose_timed(packed, 0, args.steps)
+    sec, nrec = dec.decompose_timed(pinned, 0, args.steps)
     barrier_sync(ws)
     assert nrec == len(r2)
     return sec, dec.stats(), r2, o2, py_s
@@ -358,8 +360,8 @@ def main():
                 "e2e": {"value": cells_hl * args.steps / e2e_s / 1e9, "unit": UNIT, "h2d_bytes_per_step": st2["h2d_bytes"] // args.steps,
                         "d2h_bytes_per_step": st2["d2h_bytes"] // args.steps, "ms_per_step": 1e3 * e2e_s / args.steps,
                         "python_caller_ms_per_step": 1e3 * e2e_py_s / args.steps,
-                        "caller": "sd_decompose called K times back to back from native code (libsd_bench.so); python_caller_ms_per_step "
-                                  "is the same loop through ctypes",
+                        "caller": "sd_decompose called K times back to back from native code (libsd_bench.so) on segment text in "
+                                  "page-locked host memory (sd_host_alloc); python_caller_ms_per_step is the same loop through ctypes",
                         "matches_resident_run": same},
                 "gpu_launches": int(st["launches"]), "clocks": clocks, "roofline": roof}
         if ws == 1 and not args.no_extras:

@@ -143,6 +143,12 @@ int sd_get_stats(sd_handle *h, sd_stats *out);
 void sd_reset_stats(sd_handle *h);
 const char *sd_last_error(sd_handle *h);       /* h may be NULL: error of the last failed sd_create/sd_run_files */
 void sd_free(void *p);
+/* Optional page-locked host buffers for the caller's inputs (segment text of sd_decompose / sd_stage): copies from them
+ * are plain DMA, without the driver's staging pass that pageable memory needs (the reference has no counterpart: its
+ * reads live in std::string, main.cpp:283-330).  Any host pointer is accepted by every entry point; these only make
+ * the copy-in cheaper.  NULL when the allocation fails. */
+void *sd_host_alloc(int64_t bytes);
+void sd_host_free(void *p);
 void sd_destroy(sd_handle *h);
 int sd_device_count(void);
 const char *sd_version(void);

@@ -31,7 +31,7 @@ class _ConvertStats(C.Structure):
 
 
 SYMBOLS = ["sd_create", "sd_decompose", "sd_stage", "sd_run_staged", "sd_fetch_staged", "sd_segment_read",
-           "sd_postprocess", "sd_run_files", "sd_set_ed_thr", "sd_hw_distance", "sd_get_stats", "sd_reset_stats", "sd_last_error", "sd_free",
+           "sd_postprocess", "sd_run_files", "sd_set_ed_thr", "sd_hw_distance", "sd_get_stats", "sd_reset_stats", "sd_last_error", "sd_free", "sd_host_alloc", "sd_host_free",
            "sd_destroy", "sd_device_count", "sd_version", "sd_int_peak", "sd_identity", "sd_convert",
            "sd_convert_error"]
 
@@ -85,6 +85,10 @@ def load_library(flavour="cuda"):
     lib.sd_last_error.restype = C.c_char_p
     lib.sd_free.argtypes = [p]
     lib.sd_free.restype = None
+    lib.sd_host_alloc.argtypes = [C.c_int64]
+    lib.sd_host_alloc.restype = C.c_void_p
+    lib.sd_host_free.argtypes = [C.c_void_p]
+    lib.sd_host_free.restype = None
     lib.sd_destroy.argtypes = [p]
     lib.sd_destroy.restype = None
     lib.sd_device_count.restype = C.c_int
@@ -114,6 +118,36 @@ def _pack(seqs):
     if bs:
         np.cumsum([len(b) for b in bs], out=off[1:])
     return b"".join(bs), off
+
+
+class HostBuffer:
+    """Segment text in page-locked host memory (sd_host_alloc): accepted wherever a `blob` is, copied to the device by
+    plain DMA.  ``HostBuffer.pack(segments)`` -> (buffer, offsets)."""
+
+    def __init__(self, data, flavour="cuda"):
+        self._lib = load_library(flavour)
+        self.size = len(data)
+        self.ptr = self._lib.sd_host_alloc(self.size)
+        if not self.ptr:
+            raise MemoryError("sd_host_alloc(%d) failed" % self.size)
+        C.memmove(self.ptr, data, self.size)
+
+    @classmethod
+    def pack(cls, segments, flavour="cuda"):
+        blob, off = segments if isinstance(segments, tuple) else _pack(segments)
+        return cls(blob, flavour), off
+
+    def __len__(self):
+        return self.size
+
+    def __del__(self):
+        if getattr(self, "ptr", None):
+            self._lib.sd_host_free(self.ptr)
+            self.ptr = None
+
+
+def _text(blob):
+    return C.c_char_p(blob.ptr) if isinstance(blob, HostBuffer) else blob
 
 
 class Decomposer:
@@ -167,7 +201,7 @@ class Decomposer:
         blob, off = segments if isinstance(segments, tuple) else _pack(segments)
         nseg = len(off) - 1
         recs, offs = C.c_void_p(), C.c_void_p()
-        st = self._lib.sd_decompose(self._h, blob, off.ctypes.data_as(C.POINTER(C.c_int64)), nseg, C.byref(recs), C.byref(offs))
+        st = self._lib.sd_decompose(self._h, _text(blob), off.ctypes.data_as(C.POINTER(C.c_int64)), nseg, C.byref(recs), C.byref(offs))
         if st:
             self._err(st)
         return self._take(recs, offs, nseg)
@@ -175,7 +209,7 @@ class Decomposer:
     def stage(self, segments):
         blob, off = segments if isinstance(segments, tuple) else _pack(segments)
         self._staged = len(off) - 1
-        st = self._lib.sd_stage(self._h, blob, off.ctypes.data_as(C.POINTER(C.c_int64)), self._staged)
+        st = self._lib.sd_stage(self._h, _text(blob), off.ctypes.data_as(C.POINTER(C.c_int64)), self._staged)
         if st:
             self._err(st)
 
@@ -202,7 +236,7 @@ class Decomposer:
         bl.sd_bench_decompose.restype = C.c_int
         blob, off = segments if isinstance(segments, tuple) else _pack(segments)
         sec, nrec = C.c_double(), C.c_int64()
-        st = bl.sd_bench_decompose(self._h, blob, off.ctypes.data_as(C.POINTER(C.c_int64)), len(off) - 1, warmup, steps,
+        st = bl.sd_bench_decompose(self._h, _text(blob), off.ctypes.data_as(C.POINTER(C.c_int64)), len(off) - 1, warmup, steps,
                                    C.byref(sec), C.byref(nrec))
         if st:
             self._err(st)

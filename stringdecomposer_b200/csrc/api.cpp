@@ -33,6 +33,8 @@ static void set_global_error(const std::string &e) { std::lock_guard<std::mutex>
 #ifndef SD_EMULATOR_BUILD
 namespace sdb { Backend *make_emu_backend() { return nullptr; } }
 int cuda_device_count();
+void *cuda_host_alloc(size_t bytes);
+void cuda_host_free(void *p);
 int cuda_int_peak(int device, double *alu, double *both, double *mhz, std::string &err);
 namespace sdb { int cuda_identity(const IdentityArgs &h, int max_qlen, int max_tlen, int device, double *kernel_ms, std::string &err); }
 static int run_identity(const IdentityArgs &h, int mq, int mt, int device, double *ms, std::string &err) { return cuda_identity(h, mq, mt, device, ms, err); }
@@ -41,6 +43,8 @@ namespace sdb { int emu_identity(const IdentityArgs &h, int max_qlen, int max_tl
 static int run_identity(const IdentityArgs &h, int mq, int mt, int, double *ms, std::string &err) { return emu_identity(h, mq, mt, ms, err); }
 namespace sdb { Backend *make_cuda_backend(int, std::string &err) { err = "emulator build"; return nullptr; } }
 static int cuda_device_count() { return 1; }
+static void *cuda_host_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
+static void cuda_host_free(void *p) { free(p); }
 static int cuda_int_peak(int, double *, double *, double *, std::string &err) { err = "emulator build has no device"; return SD_ERR_NO_DEVICE; }
 #endif
 
@@ -299,6 +303,8 @@ const char *sd_last_error(sd_handle *h)
 }
 
 void sd_free(void *p) { free(p); }
+void *sd_host_alloc(int64_t bytes) { return bytes < 0 ? nullptr : cuda_host_alloc((size_t)bytes); }
+void sd_host_free(void *p) { if (p) cuda_host_free(p); }
 void sd_destroy(sd_handle *h) { delete h; }
 int sd_device_count(void) { return kEmu ? 0 : cuda_device_count(); }
 const char *sd_version(void) { return kEmu ? "stringdecomposer_b200 0.1 (host emulator, tests only)" : "stringdecomposer_b200 0.1 (sm_100a)"; }

@@ -893,6 +893,16 @@ int cuda_device_count()
     return n;
 }
 
+// page-locked host memory for callers that want their inputs to travel by DMA without the driver's staging copy
+void *cuda_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void cuda_host_free(void *p) { cudaFreeHost(p); }
+
 int cuda_int_peak(int device, double *alu, double *both, double *mhz, std::string &err)
 {
     using namespace sdb;

@@ -321,3 +321,14 @@ def test_config5_full_monomer_set_against_the_reference_binary():
     got = decompose_reads(rn[:1], [read], mn, mons, part_size=1700, overlap=300)
     assert got == want and got.count("\n") > 15
 
+
+
+def test_pinned_host_buffer_through_the_c_abi():
+    # sd_host_alloc: text in page-locked memory -> same records as from pageable memory
+    from stringdecomposer_b200._lib import HostBuffer
+    _, segs, _, mons = synth.random_case(12, n_reads=(3, 3))
+    dec = Decomposer(mons)
+    a = dec.decompose(segs)
+    b = dec.decompose(HostBuffer.pack(segs))
+    assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
+    dec.close()

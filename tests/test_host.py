@@ -210,3 +210,16 @@ def test_ed_thr_filter_through_the_api():
     assert len(set(one["row"])) == 1
     assert allr["start"][0] == 0 and allr["end"][-1] == len(seg) - 1
     d.close()
+
+
+def test_pinned_host_buffer_gives_the_same_records():
+    # sd_host_alloc / sd_host_free: the text may live in page-locked memory; results do not depend on where it lives
+    from stringdecomposer_b200._lib import HostBuffer
+    _, segs, _, mons = synth.random_case(11, n_reads=(3, 3))
+    dec = Decomposer(mons, flavour=cases.EMU_LIB)
+    a = dec.decompose(segs)
+    buf, off = HostBuffer.pack(segs, cases.EMU_LIB)
+    assert len(buf) == sum(len(s) for s in segs)
+    b = dec.decompose((buf, off))
+    assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
+    dec.close()
