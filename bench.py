@@ -230,7 +230,7 @@ def run_reference_arm(args, ws, rank):
                              "sample": "full config-2 contig (2,000,000 bp) per step, dp -t %d, wall time of the process" % cores},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "decomposed_mbp_per_s": sum(len(r) for r in reads) * len(times) / T / 1e6, "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def timed_resident(dec, packed, args, ws, flushes, sampler_gpu):
@@ -283,6 +283,15 @@ def pack_segments(segs):
     return blob, off
 
 
+_OUT = None
+
+
+def emit(line):
+    out = _OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -293,6 +302,12 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the rescoring / process / replica extras")
     ap.add_argument("--geom", default=None, help="override launch geometry C,T,NS (exploration)")
     args = ap.parse_args()
+    # stdout carries the one JSON line and nothing else: native libraries that write to file descriptor 1 (NCCL prints
+    # its version banner there when NCCL_DEBUG is set) are sent to stderr, the line goes to the saved descriptor
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.geom:
         os.environ["SD_GEOM"] = args.geom
     ws, rank, local = dist_setup(args.gpus)
@@ -391,7 +406,7 @@ def main():
                                 "value": cells_r * args.steps / (dev_ms_r * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": dev_ms_r / args.steps}
         dec.close()
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if ws > 1:
         import torch.distributed as dist
         dist.barrier()

@@ -5,6 +5,7 @@
 #include <cerrno>
 #include <cstring>
 #include <fstream>
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <future>
@@ -151,57 +152,78 @@ void postprocess(const std::vector<Record> &in, std::vector<Record> &out)
 // ---------------------------------------------------------------------------------------------
 // One host thread per device, kept for the life of the engine: with kernels in the millisecond range the cost of
 // spawning and joining a thread per device and call (tens of microseconds each) would show in the multi-GPU numbers.
+// So would a condition-variable wake-up per device and call (30-60 us on a sleeping thread): a thread that has just
+// finished a job keeps polling for the next one for half a millisecond before it goes to sleep, the caller's own thread
+// drives device 0, and the caller polls briefly for the others before it blocks.
 class DevicePool {
 public:
-    explicit DevicePool(int n) : jobs_((size_t)n), state_((size_t)n, 0)
+    explicit DevicePool(int n) : n_(n)
     {
-        for (int d = 0; d < n; ++d) th_.emplace_back([this, d] { loop(d); });
+        for (int d = 1; d < n; ++d) th_.emplace_back([this, d] { loop(d); });
     }
     ~DevicePool()
     {
-        { std::lock_guard<std::mutex> l(mu_); stop_ = true; }
+        stop_.store(true);
+        { std::lock_guard<std::mutex> l(mu_); }
         cv_.notify_all();
         for (auto &t : th_) t.join();
     }
-    // runs fn(d) for every device d on that device's thread and waits for all of them
+    // runs fn(d) for every device d (device 0 on the calling thread, the others on their own) and waits for all of them
     void run(const std::function<void(int)> &fn)
     {
-        {
-            std::lock_guard<std::mutex> l(mu_);
-            for (size_t d = 0; d < jobs_.size(); ++d) { jobs_[d] = &fn; state_[d] = 1; }
-            pending_ = (int)jobs_.size();
-        }
+        fn_ = &fn;
+        pending_.store(n_ - 1);
+        epoch_.fetch_add(1);
+        { std::lock_guard<std::mutex> l(mu_); }          // a thread between its check and its wait holds the mutex
         cv_.notify_all();
+        fn(0);
+        for (int spin = 0; spin < (1 << 14); ++spin) { if (pending_.load() == 0) return; relax(); }
         std::unique_lock<std::mutex> l(mu_);
-        done_.wait(l, [this] { return pending_ == 0; });
+        done_.wait(l, [this] { return pending_.load() == 0; });
     }
 
 private:
+    static void relax()
+    {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#else
+        std::this_thread::yield();
+#endif
+    }
     void loop(int d)
     {
+        uint64_t seen = 0;
         for (;;) {
-            const std::function<void(int)> *fn;
-            {
-                std::unique_lock<std::mutex> l(mu_);
-                cv_.wait(l, [&] { return stop_ || state_[(size_t)d] == 1; });
-                if (stop_) return;
-                fn = jobs_[(size_t)d]; state_[(size_t)d] = 2;
+            const auto t0 = std::chrono::steady_clock::now();
+            bool got = false;
+            for (int spin = 0; !got; ++spin) {
+                if (stop_.load()) return;
+                if (epoch_.load() != seen) { got = true; break; }
+                relax();
+                if ((spin & 255) == 255 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(500)) break;
             }
-            (*fn)(d);
-            {
-                std::lock_guard<std::mutex> l(mu_);
-                state_[(size_t)d] = 0;
-                if (--pending_ == 0) done_.notify_all();
+            if (!got) {
+                std::unique_lock<std::mutex> l(mu_);
+                cv_.wait(l, [&] { return stop_.load() || epoch_.load() != seen; });
+                if (stop_.load()) return;
+            }
+            seen = epoch_.load();
+            (*fn_)(d);
+            if (pending_.fetch_sub(1) == 1) {
+                { std::lock_guard<std::mutex> l(mu_); }
+                done_.notify_all();
             }
         }
     }
+    int n_;
     std::vector<std::thread> th_;
-    std::vector<const std::function<void(int)> *> jobs_;
-    std::vector<int> state_;
+    const std::function<void(int)> *fn_ = nullptr;
+    std::atomic<uint64_t> epoch_{0};
+    std::atomic<int> pending_{0};
+    std::atomic<bool> stop_{false};
     std::mutex mu_;
     std::condition_variable cv_, done_;
-    int pending_ = 0;
-    bool stop_ = false;
 };
 
 Engine::Engine(const std::vector<std::string> &forward_monomers, const Scoring &sc, std::vector<std::unique_ptr<Backend>> devs)
