@@ -61,6 +61,25 @@ static std::string header_name(const char *a, const char *le)      // name = fir
     return std::string(a, b);
 }
 
+// Alphabet check of one line in a single branch-free pass (a table look-up OR-ed over the line): bit 0 = an N was
+// seen, bit 1 = a symbol outside ACGTN.  Only a line with bit 1 set is looked at again, for the position of the symbol.
+struct SymbolClass {
+    uint8_t t[256];
+    SymbolClass() { for (int c = 0; c < 256; ++c) t[c] = base_code((char)c) < 0 ? 2 : (c == 'N' ? 1 : 0); }
+};
+static inline unsigned classify_line(const char *p, const char *le)
+{
+    static const SymbolClass sc;
+    const uint8_t *t = sc.t;
+    const unsigned char *a = reinterpret_cast<const unsigned char *>(p), *e = reinterpret_cast<const unsigned char *>(le);
+    unsigned f0 = 0, f1 = 0, f2 = 0, f3 = 0;
+    for (; a + 8 <= e; a += 8) {
+        f0 |= t[a[0]] | t[a[4]]; f1 |= t[a[1]] | t[a[5]]; f2 |= t[a[2]] | t[a[6]]; f3 |= t[a[3]] | t[a[7]];
+    }
+    for (; a < e; ++a) f0 |= t[*a];
+    return f0 | f1 | f2 | f3;
+}
+
 // First pass over a FASTA file: names, lengths, the alphabet check and the N warning of load_fasta (main.cpp:330-344)
 // without keeping any sequence.  Returns 0, or 255 after writing the reference's error line to diag.
 struct FastaIndex { std::vector<std::string> names; std::vector<int64_t> lens; };
@@ -73,11 +92,13 @@ static int index_fasta(const std::string &path, FastaIndex &out, std::string &di
         [&](const char *a, const char *le) { out.names.push_back(header_name(a, le)); out.lens.push_back(0); },
         [&](const char *p, const char *le) {
             if (out.lens.empty()) return;                   // text before the first header belongs to no record
-            if (bad_seq < 0)
-                for (const char *c = p; c < le; ++c) {
-                    if (base_code(*c) < 0) { bad_seq = (int)out.lens.size() - 1; bad_char = *c; break; }
-                    has_n |= *c == 'N';
-                }
+            if (bad_seq < 0) {
+                const unsigned f = classify_line(p, le);
+                has_n |= (f & 1) != 0;
+                if (f & 2)
+                    for (const char *c = p; c < le; ++c)
+                        if (base_code(*c) < 0) { bad_seq = (int)out.lens.size() - 1; bad_char = *c; break; }
+            }
             out.lens.back() += le - p;
         });
     if (bad_seq >= 0) {
@@ -98,11 +119,13 @@ int load_fasta(const std::string &path, FastaSet &out, std::string &diag)
         [&](const char *a, const char *le) { out.names.push_back(header_name(a, le)); out.seqs.emplace_back(); },
         [&](const char *p, const char *le) {
             if (out.seqs.empty()) return;
-            if (bad_seq < 0)
-                for (const char *c = p; c < le; ++c) {
-                    if (base_code(*c) < 0) { bad_seq = (int)out.seqs.size() - 1; bad_char = *c; break; }
-                    has_n |= *c == 'N';
-                }
+            if (bad_seq < 0) {
+                const unsigned f = classify_line(p, le);
+                has_n |= (f & 1) != 0;
+                if (f & 2)
+                    for (const char *c = p; c < le; ++c)
+                        if (base_code(*c) < 0) { bad_seq = (int)out.seqs.size() - 1; bad_char = *c; break; }
+            }
             out.seqs.back().append(p, le);                  // lines appended raw (main.cpp:327), checked at :330-341
         });
     if (bad_seq >= 0) {
@@ -545,26 +568,11 @@ int run_files(const std::string &reads_path, const std::string &monomers_path, i
     if (mons.seqs.empty()) { error = "no monomers"; err.add("ERROR: " + error + "\n"); return 1; }
     const auto t_indexed = tnow();
 
-    if (int dst = dev_ready.get()) {                 // no usable device: fail loudly, there is no CPU path
-        error = dev_error;
-        err.add("ERROR: " + error + "\n");
-        return dst;
-    }
-    const auto t_device = tnow();
-    std::unique_ptr<Engine> eng;
-    try {
-        eng.reset(new Engine(mons.seqs, sc, std::move(devs)));
-        eng->set_ed_thr(ed_thr);          // FilterMonomersForRead (main.cpp:91-93,135-149) when ed_thr > -1
-        eng->set_plan_hint(max_seg_len, nseg_total);
-    } catch (PlanError &e) {
-        error = e.msg;
-        err.add("ERROR: " + error + "\n");
-        return 3;
-    }
-
-    // Pass 2: reader thread -> device (this thread) -> writer thread.  A chunk holds up to chunk_cols read symbols;
-    // host memory is bounded by two chunks in flight plus the read being assembled, whatever the size of the file.
-    int64_t chunk_cols = (int64_t)256 << 20;
+    // Pass 2: reader thread -> device (this thread) -> writer thread.  A chunk holds up to chunk_cols read symbols, so
+    // that the three stages overlap on anything larger than a few tens of megabases; host memory is bounded by the
+    // chunks in flight (two per hand-over) plus the read being assembled, whatever the size of the file.  The reader
+    // starts now, while the devices are still being opened: the first chunks are waiting when the context is up.
+    int64_t chunk_cols = (int64_t)32 << 20;
     if (const char *e = getenv("SD_CHUNK_BASES")) if (atoll(e) > 0) chunk_cols = atoll(e);
     Handoff<std::unique_ptr<Chunk>> to_device(2), to_writer(2);
     std::string reader_error, writer_error;
@@ -599,6 +607,27 @@ int run_files(const std::string &reads_path, const std::string &monomers_path, i
         } catch (std::exception &e) { reader_error = e.what(); }
         to_device.finish();
     });
+    struct JoinOnExit {                              // early returns below: stop the reader before its captures go away
+        Handoff<std::unique_ptr<Chunk>> &q; std::thread &t;
+        ~JoinOnExit() { if (t.joinable()) { q.close(); t.join(); } }
+    } reader_guard{to_device, reader};
+
+    if (int dst = dev_ready.get()) {                 // no usable device: fail loudly, there is no CPU path
+        error = dev_error;
+        err.add("ERROR: " + error + "\n");
+        return dst;
+    }
+    const auto t_device = tnow();
+    std::unique_ptr<Engine> eng;
+    try {
+        eng.reset(new Engine(mons.seqs, sc, std::move(devs)));
+        eng->set_ed_thr(ed_thr);          // FilterMonomersForRead (main.cpp:91-93,135-149) when ed_thr > -1
+        eng->set_plan_hint(max_seg_len, nseg_total);
+    } catch (PlanError &e) {
+        error = e.msg;
+        err.add("ERROR: " + error + "\n");
+        return 3;
+    }
 
     const int M = (int)mons.seqs.size();
     FdWriter outw(out_fd);
@@ -679,9 +708,11 @@ int run_files(const std::string &reads_path, const std::string &monomers_path, i
     if (getenv("SD_VERBOSE")) {
         const EngineStats &es = eng->stats;
         char line[512];
-        snprintf(line, sizeof line, "[sd_b200] devices=%d geometry packed=%d lat=%d C=%d T=%d NS=%d NT=%d NG=%d segments=%ld cells=%ld sweep=%.3f ms traceback=%.3f ms -> %.1f GCUPS (kernels)\n",
+        // with several waves the traceback of one wave shares the device with the sweep of the next: its time is then
+        // mostly waiting for free SMs and lies inside the sweep time, so the rates are quoted on the sweep and on the calls
+        snprintf(line, sizeof line, "[sd_b200] devices=%d geometry packed=%d lat=%d C=%d T=%d NS=%d NT=%d NG=%d segments=%ld cells=%ld sweep=%.3f ms traceback=%.3f ms -> %.1f GCUPS (sweep), %.1f GCUPS (device calls with copies, %.1f ms)\n",
                  eng->ndev(), es.g.packed, es.g.lat, es.g.C, es.g.T, es.g.NS, es.g.NT, es.g.NG, (long)es.segments, (long)es.cells, es.sweep_ms, es.traceback_ms,
-                 es.cells / ((es.sweep_ms + es.traceback_ms) * 1e6 + 1e-9));
+                 es.cells / (es.sweep_ms * 1e6 + 1e-9), es.cells / (dev_ms * 1e6 + 1e-9), dev_ms);
         err.add(line);
     }
     if (const char *pj = getenv("SD_PERF_JSON")) {
@@ -690,13 +721,13 @@ int run_files(const std::string &reads_path, const std::string &monomers_path, i
             const EngineStats &es = eng->stats;
             int64_t read_bp = 0;
             for (int64_t l : ridx.lens) read_bp += l;
-            const double kms = es.sweep_ms + es.traceback_ms, wall = tms(t_begin, t_done);
+            const double wall = tms(t_begin, t_done);
             fprintf(f, "{\"reads\": %zu, \"read_bp\": %ld, \"segments\": %ld, \"columns\": %ld, \"cells\": %ld, \"devices\": %d, "
                        "\"sweep_ms\": %.3f, \"traceback_ms\": %.3f, \"h2d_ms\": %.3f, \"device_calls_ms\": %.3f, \"wall_ms\": %.3f, "
-                       "\"wait_for_device_ms\": %.3f, \"kernel_gcups\": %.2f, \"wall_mbp_per_s\": %.3f, "
+                       "\"wait_for_device_ms\": %.3f, \"sweep_gcups\": %.2f, \"wall_mbp_per_s\": %.3f, "
                        "\"geometry\": {\"packed\": %d, \"lat\": %d, \"C\": %d, \"T\": %d, \"NS\": %d, \"NT\": %d, \"NG\": %d, \"scanw\": %d}}\n",
                     nreads, (long)read_bp, (long)es.segments, (long)es.columns, (long)es.cells, eng->ndev(), es.sweep_ms, es.traceback_ms, es.h2d_ms,
-                    dev_ms, wall, tms(t_indexed, t_device), es.cells / (kms * 1e6 + 1e-9), read_bp / (wall * 1e3 + 1e-9),
+                    dev_ms, wall, tms(t_indexed, t_device), es.cells / (es.sweep_ms * 1e6 + 1e-9), read_bp / (wall * 1e3 + 1e-9),
                     es.g.packed, es.g.lat, es.g.C, es.g.T, es.g.NS, es.g.NT, es.g.NG, es.g.scanw);
             fclose(f);
         }
