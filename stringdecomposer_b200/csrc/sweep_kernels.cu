@@ -429,6 +429,7 @@ struct WaveSlot {
     int s0 = 0, s1 = 0, nseg = 0, nmax = 0;
     bool filter_on = false, staged = false;
     size_t nb = 0, rec_guess = 0;
+    int end_idx = -1, prev_end = -1;      // this wave's and its predecessor's entry in the backend's ring of sweep-end events
     cudaEvent_t ev[7]{};            // 0 h2d begin, 1 h2d end, 2 sweep begin, 3 sweep end, 4 traceback end, 5 d2h end, 6 traceback begin
 };
 
@@ -441,7 +442,9 @@ public:
         SD_CUDA(cudaStreamCreateWithFlags(&st_in_, cudaStreamNonBlocking));
         SD_CUDA(cudaStreamCreateWithFlags(&st_out_, cudaStreamNonBlocking));
         SD_CUDA(cudaStreamCreateWithFlags(&st_tb_, cudaStreamNonBlocking));
+        SD_CUDA(cudaStreamCreateWithFlags(&st2_, cudaStreamNonBlocking));
         for (auto &w : slot_) for (auto &e : w.ev) SD_CUDA(cudaEventCreate(&e));
+        for (auto &e : endev_) SD_CUDA(cudaEventCreate(&e));
         SD_CUDA(cudaGetDeviceProperties(&prop_, dev_));
         if (prop_.major != 10) throw PlanError{"CUDA device is not sm_100 class: this library carries sm_100a code only (no PTX for other architectures)"};
         size_t fr = 0, tot = 0;
@@ -452,6 +455,8 @@ public:
     {
         DeviceScope scope_(dev_);
         for (auto &w : slot_) for (auto &e : w.ev) cudaEventDestroy(e);
+        for (auto &e : endev_) cudaEventDestroy(e);
+        cudaStreamDestroy(st2_);
         cudaStreamDestroy(st_); cudaStreamDestroy(st_in_); cudaStreamDestroy(st_out_); cudaStreamDestroy(st_tb_);
     }
     const char *name() const override { return "cuda"; }
@@ -612,7 +617,7 @@ public:
         launches += 2;
     }
 
-    void launch_single(WaveSlot &w, int seg_stride)
+    void launch_single(WaveSlot &w, int seg_stride, cudaStream_t stream)
     {
         const Geometry &g = plan_.g;
         SweepArgs a;
@@ -637,7 +642,7 @@ public:
         SD_CUDA(cudaFuncSetAttribute(kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int nctas = (int)w.lay.cta_nmax.size();
         void *args[] = {(void *)&a};
-        SD_CUDA(cudaLaunchKernel(kernel_, dim3(nctas), dim3(g.NT), args, smem, st_));
+        SD_CUDA(cudaLaunchKernel(kernel_, dim3(nctas), dim3(g.NT), args, smem, stream));
     }
 
     void launch_group(WaveSlot &w)
@@ -725,10 +730,19 @@ public:
     {
         const Geometry &g = plan_.g;
         const int seg_stride = (w.nmax + 16) / 16 * 16;
-        SD_CUDA(cudaStreamWaitEvent(st_, w.ev[1], 0));
-        SD_CUDA(cudaEventRecord(w.ev[2], st_));
-        if (g.lat) launch_lat(w, seg_stride); else if (g.NG > 1) launch_group(w); else launch_single(w, seg_stride);
-        SD_CUDA(cudaEventRecord(w.ev[3], st_));
+        // The classic sweeps of the two wave slots go to two streams: the CTAs of the next wave fill the SMs that the
+        // last CTAs of this wave leave idle (a CTA runs for milliseconds, so the tail of a wave is a sizeable part of a
+        // small wave).  The cluster and group kernels need the whole device to themselves and stay on one stream.
+        const bool own_stream = !g.lat && g.NG == 1 && &w == &slot_[1];
+        cudaStream_t ss = own_stream ? st2_ : st_;
+        SD_CUDA(cudaStreamWaitEvent(ss, w.ev[1], 0));
+        SD_CUDA(cudaEventRecord(w.ev[2], ss));
+        if (g.lat) launch_lat(w, seg_stride); else if (g.NG > 1) launch_group(w); else launch_single(w, seg_stride, ss);
+        SD_CUDA(cudaEventRecord(w.ev[3], ss));
+        w.prev_end = last_end_;
+        w.end_idx = (int)(wave_seq_++ & 3);
+        SD_CUDA(cudaEventRecord(endev_[w.end_idx], ss));
+        last_end_ = w.end_idx;
         // the traceback (a latency-bound walk, one warp per segment) and the compaction run on their own stream: the
         // sweep of the next wave starts as soon as this one's sweep is done and the two overlap
         SD_CUDA(cudaStreamWaitEvent(st_tb_, w.ev[3], 0));
@@ -799,7 +813,13 @@ public:
         for (int s = 0; s < w.nseg; ++s) { run += cnt[s]; out.rec_off.push_back(run); }
         float ms = 0;
         SD_CUDA(cudaEventElapsedTime(&ms, w.ev[0], w.ev[1])); h2d_ms += ms;
-        SD_CUDA(cudaEventElapsedTime(&ms, w.ev[2], w.ev[3])); sweep_ms += ms;
+        SD_CUDA(cudaEventElapsedTime(&ms, w.ev[2], w.ev[3]));
+        if (w.prev_end >= 0) {                  // sweeps of consecutive waves overlap: count the overlap once
+            float since_prev = 0;
+            SD_CUDA(cudaEventElapsedTime(&since_prev, endev_[w.prev_end], w.ev[3]));
+            ms = std::min(ms, std::max(since_prev, 0.0f));
+        }
+        sweep_ms += ms;
         SD_CUDA(cudaEventElapsedTime(&ms, w.ev[6], w.ev[4])); traceback_ms += ms;
         d2h_bytes += (int64_t)(rec_off + (size_t)total * sizeof(Record));
         w.staged = false;
@@ -865,6 +885,9 @@ public:
 private:
     int dev_;
     cudaStream_t st_{}, st_in_{}, st_out_{}, st_tb_{};      // sweep, copy-in, copy-out, traceback + compaction
+    cudaStream_t st2_{};                                     // classic sweeps of wave slot 1
+    cudaEvent_t endev_[4]{};                                 // sweep-end events of the last four waves (ring)
+    uint64_t wave_seq_ = 0; int last_end_ = -1;
     cudaDeviceProp prop_{};
     Plan plan_; MonomerSet ms_;
     const void *kernel_ = nullptr;

@@ -22,7 +22,7 @@ run() {  # label chunk args...
   grep "run_files\|sd_b200\] devices" /tmp/ours.err | tail -2 >> $LOG
 }
 run warmup 33554432 tests/golden/config1_read.fa tests/golden/DXZ1_star_monomers.fa 1 5000 500
-for c in 268435456 67108864 33554432 16777216 8388608; do run config3 $c /tmp/c3.fa /tmp/mons.fa 1 5000 500; done
-for c in 536870912 67108864 33554432 16777216; do run config4 $c /tmp/c4.fa /tmp/mons.fa 1 5000 500 -2 -2 -3 1; done
+for c in ${CHUNKS3:-268435456 67108864 33554432 16777216 8388608}; do run config3 $c /tmp/c3.fa /tmp/mons.fa 1 5000 500; done
+for c in ${CHUNKS4:-536870912 67108864 33554432 16777216}; do run config4 $c /tmp/c4.fa /tmp/mons.fa 1 5000 500 -2 -2 -3 1; done
 ./tools/probes/ctx_time >> $LOG 2>&1
 cat $LOG
