@@ -38,21 +38,3 @@ def has_gpu():
         return torch.cuda.is_available()
     except Exception:
         return False
-
-
-_GPU_KEEPALIVE = []
-
-
-@pytest.fixture(scope="session", autouse=True)
-def gpu_kept_initialised(request):
-    """On a box without the persistence daemon the driver tears the GPU state down whenever the last CUDA process
-    exits, and every `dp` subprocess of the suite then pays a full device initialisation (1-4 s instead of 0.25 s;
-    measured in profiles/r02_startup.txt).  The pytest process therefore keeps one context per visible device alive
-    for the whole session -- test speed only, no test depends on it."""
-    selected = request.config.getoption("-m") or ""
-    if "not gpu" in selected or not has_gpu():
-        return False
-    import torch
-    for d in range(torch.cuda.device_count()):
-        _GPU_KEEPALIVE.append(torch.zeros(1, device="cuda:%d" % d))
-    return True

@@ -39,9 +39,34 @@ def test_config1_golden_through_dp_binary(scoring, fixture):
         assert got == open(os.path.join(cases.GOLDEN, "config1_cols1-4.tsv")).read().splitlines()
 
 
-@pytest.mark.parametrize("case", cases.load_cases(), ids=lambda c: c["name"])
+def _plain_argv(case):
+    """argv that sd_run_files can be given directly (three, seven or eight integer arguments after the two paths)"""
+    if case.get("argv_raw") is not None or len(case["argv_tail"]) not in (3, 7, 8):
+        return False
+    try:
+        [int(x) for x in case["argv_tail"]]
+    except ValueError:
+        return False
+    return True
+
+
+_ALL_CASES = cases.load_cases()
+# A `dp` process pays a CUDA context per case (0.25 s on some boxes, 3 s and more on others: profiles/r02_startup.txt),
+# so the full list of reference-generated cases runs inside this process through sd_run_files -- the function dp_main.cpp
+# hands its argv to -- with stdout, stderr and status compared, and the binary itself runs every case that is about argv
+# handling plus every fifth of the rest.
+_BINARY_CASES = [c for i, c in enumerate(_ALL_CASES)
+                 if not _plain_argv(c) or i % 5 == 0 or c["name"].startswith(("argc", "ed_thr_0", "scoring_0")) or c["status"] != 0]
+
+
+@pytest.mark.parametrize("case", _BINARY_CASES, ids=lambda c: c["name"])
 def test_edge_cases_through_dp_binary(case):
     cases.check_case(cases.DP_CUDA, case)
+
+
+@pytest.mark.parametrize("case", [c for c in _ALL_CASES if _plain_argv(c)], ids=lambda c: c["name"])
+def test_edge_cases_through_sd_run_files(case):
+    cases.check_case_inproc(case, check_stderr=True)
 
 
 @pytest.mark.parametrize("geom", ["8,32,1", "16,16,1", "24,8,1", "24,8,2", "32,8,1", "48,4,2", "48,4,3", "12,16,1", "20,10,1", "20,10,2", "12,16,1", "19,10,1", "19,10,3"])
