@@ -454,7 +454,8 @@ def config3_waves(device):
     dec.close()
     cells = float(cells_of(segs, mons))
     return {"what": "config 3 sample: 600 reads x 100 kb (60 Mb), one sd_decompose call with host buffers; the sweeps of the "
-                    "waves run back to back on one stream, the traceback of a wave runs on a second stream under the next sweep",
+                    "waves alternate between two streams (the next wave fills the tail of the previous one; overlap counted once), the "
+                    "traceback of a wave runs on a third stream under the next sweep",
             "segments": len(segs), "cells": cells, "sweep_ms": st["sweep_ms"], "traceback_ms_overlapped": st["traceback_ms"],
             "e2e_ms": 1e3 * dt, "e2e_over_sweep": 1e3 * dt / st["sweep_ms"],
             "sweep_gcups_actual_cells": cells / st["sweep_ms"] / 1e6, "e2e_gcups_actual_cells": cells / dt / 1e9,
