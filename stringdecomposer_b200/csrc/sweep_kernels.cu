@@ -24,6 +24,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -382,33 +383,124 @@ static const void *kern(int packed, int C, int T, int NT, bool fast, bool multi)
 
 namespace {
 
+// Process-wide cache of released device and page-locked blocks.  Creating and destroying an engine costs some thirty
+// cudaMalloc / cudaFree / cudaHostAlloc calls; each is a round trip into the kernel driver (and cudaFree a device-wide
+// synchronisation) that takes from a fraction of a millisecond to tens of milliseconds depending on the box -- far more
+// than the kernels of a small batch.  A process that opens many handles (one per sd_run_files call, one per monomer
+// set) gets its blocks back from here instead.  Bounded (4 GiB and 512 blocks per device, no block above 1 GiB); emptied
+// and retried when an allocation fails; SD_NO_BUFFER_CACHE=1 turns it off.  Never destroyed: the driver reclaims the
+// memory at process exit, and no CUDA call has to run from a static destructor.
+class BlockCache {
+public:
+    enum Kind { Device = 0, Pinned = 1 };
+    void *take(Kind k, int dev, size_t bytes, size_t *cap)
+    {
+        if (off()) return nullptr;
+        std::lock_guard<std::mutex> l(mu_);
+        int best = -1;
+        for (size_t i = 0; i < blocks_.size(); ++i) {
+            const Block &b = blocks_[i];
+            if (b.kind != k || b.dev != dev || b.cap < bytes || b.cap > 4 * bytes + ((size_t)1 << 20)) continue;
+            if (best < 0 || b.cap < blocks_[(size_t)best].cap) best = (int)i;
+        }
+        if (best < 0) return nullptr;
+        Block b = blocks_[(size_t)best];
+        blocks_.erase(blocks_.begin() + best);
+        held_[k] -= b.cap;
+        *cap = b.cap;
+        return b.p;
+    }
+    bool give(Kind k, int dev, void *p, size_t cap)
+    {
+        if (off() || dev < 0 || cap > ((size_t)1 << 30)) return false;
+        std::lock_guard<std::mutex> l(mu_);
+        size_t n = 0, bytes = 0;
+        for (const Block &b : blocks_) if (b.kind == k && b.dev == dev) { ++n; bytes += b.cap; }
+        if (n >= 512 || bytes + cap > (k == Device ? (size_t)4 << 30 : (size_t)512 << 20)) return false;
+        blocks_.push_back(Block{p, cap, dev, k});
+        held_[k] += cap;
+        return true;
+    }
+    void flush(Kind k, int dev)                     // an allocation failed: hand everything of that kind back to the driver
+    {
+        std::vector<Block> drop;
+        {
+            std::lock_guard<std::mutex> l(mu_);
+            for (size_t i = 0; i < blocks_.size();)
+                if (blocks_[i].kind == k && blocks_[i].dev == dev) { drop.push_back(blocks_[i]); held_[k] -= blocks_[i].cap; blocks_.erase(blocks_.begin() + (long)i); }
+                else ++i;
+        }
+        for (const Block &b : drop) { if (k == Device) cudaFree(b.p); else cudaFreeHost(b.p); }
+    }
+    static BlockCache &get() { static BlockCache *c = new BlockCache; return *c; }
+
+private:
+    struct Block { void *p; size_t cap; int dev; Kind kind; };
+    static bool off() { const char *e = getenv("SD_NO_BUFFER_CACHE"); return e && *e && *e != '0'; }
+    std::mutex mu_;
+    std::vector<Block> blocks_;
+    size_t held_[2] = {0, 0};
+};
+
 struct DevBuf {
-    void *p = nullptr; size_t cap = 0;
+    void *p = nullptr; size_t cap = 0; int dev = -1;
+    void release()
+    {
+        if (!p) return;
+        if (!BlockCache::get().give(BlockCache::Device, dev, p, cap)) cudaFree(p);
+        p = nullptr; cap = 0;
+    }
     void need(size_t bytes)
     {
         if (bytes <= cap) return;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-        size_t want = bytes + bytes / 8 + 256;
-        SD_CUDA(cudaMalloc(&p, want));
-        cap = want;
+        if (p) { cudaDeviceSynchronize(); release(); }       // nothing in flight may still use the old block (cudaFree used to imply this)
+        const size_t want = bytes + bytes / 8 + 256;
+        int d = 0;
+        SD_CUDA(cudaGetDevice(&d));
+        size_t got = 0;
+        void *q = BlockCache::get().take(BlockCache::Device, d, want, &got);
+        if (!q) {
+            if (cudaMalloc(&q, want) != cudaSuccess) {
+                cudaGetLastError();
+                BlockCache::get().flush(BlockCache::Device, d);
+                SD_CUDA(cudaMalloc(&q, want));
+            }
+            got = want;
+        }
+        p = q; cap = got; dev = d;
     }
     template <class U> U *as() { return reinterpret_cast<U *>(p); }
-    ~DevBuf() { if (p) cudaFree(p); }
+    ~DevBuf() { release(); }
 };
 struct PinnedBuf {          // page-locked host memory: the result block of a wave lands here with one asynchronous copy
-    void *p = nullptr; size_t cap = 0;
+    void *p = nullptr; size_t cap = 0; int dev = -1;
+    void release()
+    {
+        if (!p) return;
+        if (!BlockCache::get().give(BlockCache::Pinned, dev, p, cap)) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+    }
     void need(size_t bytes)
     {
         if (bytes <= cap) return;
-        if (p) cudaFreeHost(p);
-        p = nullptr; cap = 0;
-        size_t want = bytes + bytes / 4 + 4096;
-        SD_CUDA(cudaHostAlloc(&p, want, cudaHostAllocDefault));
-        cap = want;
+        if (p) { cudaDeviceSynchronize(); release(); }
+        const size_t want = bytes + bytes / 4 + 4096;
+        int d = 0;
+        SD_CUDA(cudaGetDevice(&d));
+        size_t got = 0;
+        void *q = BlockCache::get().take(BlockCache::Pinned, d, want, &got);
+        if (!q) {
+            if (cudaHostAlloc(&q, want, cudaHostAllocDefault) != cudaSuccess) {
+                cudaGetLastError();
+                BlockCache::get().flush(BlockCache::Pinned, d);
+                SD_CUDA(cudaHostAlloc(&q, want, cudaHostAllocDefault));
+            }
+            got = want;
+        }
+        p = q; cap = got; dev = d;
     }
     template <class U> U *as() { return reinterpret_cast<U *>(p); }
-    ~PinnedBuf() { if (p) cudaFreeHost(p); }
+    ~PinnedBuf() { release(); }
 };
 struct MetaView { void *p = nullptr; template <class U> U *as() { return reinterpret_cast<U *>(p); } };
 
@@ -454,6 +546,7 @@ public:
     ~CudaBackend() override
     {
         DeviceScope scope_(dev_);
+        cudaDeviceSynchronize();          // the blocks of this backend go back to the process-wide cache: nothing may still use them
         for (auto &w : slot_) for (auto &e : w.ev) cudaEventDestroy(e);
         for (auto &e : endev_) cudaEventDestroy(e);
         cudaStreamDestroy(st2_);
