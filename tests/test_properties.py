@@ -10,6 +10,10 @@ import sd_oracle
 from stringdecomposer_b200 import Decomposer
 
 
+# SD_HYP_SCALE=<k> multiplies the number of examples of every property test (soak runs; 1 in the regular suites)
+SCALE = max(1, int(os.environ.get("SD_HYP_SCALE", "1") or 1))
+
+
 def seq(alphabet, lo, hi):
     return st.text(alphabet=alphabet, min_size=lo, max_size=hi)
 
@@ -59,14 +63,14 @@ def run(flavour, problem):
         assert got == want, (monomers, s, scoring, geom, group, lat)
 
 
-@settings(max_examples=120, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
+@settings(max_examples=120 * SCALE, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
 @given(problems())
 def test_emulated_kernels_match_oracle(problem):
     run(cases.EMU_LIB, problem)
 
 
 @pytest.mark.gpu
-@settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
+@settings(max_examples=60 * SCALE, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
 @given(problems())
 def test_cuda_kernels_match_oracle(problem):
     run("cuda", problem)
@@ -104,7 +108,7 @@ def run_rescoring(flavour, problem, tmp):
         assert open(out).read() == want and open(out[:-4] + "_alt.tsv").read() == want_alt, (problem, fn.__name__)
 
 
-@settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large,
+@settings(max_examples=60 * SCALE, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large,
                                                                  HealthCheck.function_scoped_fixture])
 @given(rescoring_problems())
 def test_emulated_rescoring_matches_oracle(tmp_path, problem):
@@ -112,7 +116,7 @@ def test_emulated_rescoring_matches_oracle(tmp_path, problem):
 
 
 @pytest.mark.gpu
-@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large,
+@settings(max_examples=40 * SCALE, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large,
                                                                  HealthCheck.function_scoped_fixture])
 @given(rescoring_problems())
 def test_cuda_rescoring_matches_oracle(tmp_path, problem):
