@@ -18,7 +18,7 @@ from stringdecomposer_b200 import synth  # noqa: E402
 REF = os.path.join(ROOT, "oracle", "_ref", "dp")
 EMU = os.path.join(ROOT, "tests", "emu", "_build", "dp_emu")
 SCORINGS = [(-1, -1, -1, 1), (-2, -2, -3, 1), (-3, -2, -4, 2), (0, -1, -1, 1), (-1, 0, -1, 1), (-1, -1, -1, 5), (-6, -6, -6, 1), (-1, -2, 0, 0)]
-GEOMS = ["", "", "8,32,1", "12,16,2", "19,10,1", "24,8,3", "16,4,2", "48,2,1", "20,10,2"]
+GEOMS = ["", "", "8,32,1", "12,16,2", "19,10,1", "24,8,3", "16,4,2", "48,2,1", "20,10,2", "24,8,1", "48,4,2", "32,8,1"]
 LATS = ["", "", "0", "6,32,4", "6,32,1", "12,16,2", "24,8,1", "12,32,1"]
 
 
@@ -33,11 +33,27 @@ def fasta(names, seqs, width):
     return "".join(out)
 
 
-def one(rng, seed):
-    alphabet = rng.choice(["A", "AC", "ACG", "ACGT", "ACGT", "ACGTN"])
-    rn, rr, mn, mm = synth.random_case(seed, alphabet=alphabet, n_monomers=(1, 8), mono_len=(1, 90), n_reads=(1, 4), read_len=(1, 1500))
-    part = rng.choice([50, 137, 300, 700, 1000])
-    overlap = rng.choice([0, 10, 40, part // 3, part - 1])
+def realistic(rng, seed):
+    """alpha-satellite-like input: a subset of the DXZ1 monomers, reads cut from a noisy higher-order-repeat array"""
+    mn, mm = synth.load_dxz1()
+    keep = sorted(rng.sample(range(len(mm)), rng.randint(2, len(mm))))
+    mn, mm = [mn[i] for i in keep], [mm[i] for i in keep]
+    arr = synth.hor_array(mm, rng.randint(3000, 14000), rng.choice([0.0, 0.02, 0.1, 0.25]), seed)
+    cuts = sorted(rng.sample(range(1, len(arr)), rng.randint(0, 2)))
+    rr = [arr[a:b] for a, b in zip([0] + cuts, cuts + [len(arr)])]
+    return ["read%d" % i for i in range(len(rr))], rr, mn, mm
+
+
+def one(rng, seed, real=False):
+    if real:
+        rn, rr, mn, mm = realistic(rng, seed)
+        part = rng.choice([5000, 5000, 2000, 1000])
+        overlap = rng.choice([500, 500, 300, 0])
+    else:
+        alphabet = rng.choice(["A", "AC", "ACG", "ACGT", "ACGT", "ACGTN"])
+        rn, rr, mn, mm = synth.random_case(seed, alphabet=alphabet, n_monomers=(1, 8), mono_len=(1, 90), n_reads=(1, 4), read_len=(1, 1500))
+        part = rng.choice([50, 137, 300, 700, 1000])
+        overlap = rng.choice([0, 10, 40, part // 3, part - 1])
     tail = [str(rng.randint(1, 4)), str(part), str(overlap)]
     mode = rng.random()
     if mode < 0.35:
@@ -90,11 +106,12 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--cases", type=int, default=200)
+    ap.add_argument("--realistic", action="store_true", help="DXZ1 monomers and noisy HOR arrays instead of small random strings")
     args = ap.parse_args()
     rng = random.Random(args.seed)
     bad = rows = 0
     for i in range(args.cases):
-        ok, n = one(rng, args.seed * 100000 + i)
+        ok, n = one(rng, args.seed * 100000 + i, args.realistic)
         bad += not ok
         rows += n
         if (i + 1) % 100 == 0:
