@@ -54,9 +54,9 @@ _ALL_CASES = cases.load_cases()
 # A `dp` process pays a CUDA context per case (0.25 s on some boxes, 3 s and more on others: profiles/r02_startup.txt),
 # so the full list of reference-generated cases runs inside this process through sd_run_files -- the function dp_main.cpp
 # hands its argv to -- with stdout, stderr and status compared, and the binary itself runs every case that is about argv
-# handling plus every fifth of the rest.
+# handling, every failing case and every tenth of the rest.
 _BINARY_CASES = [c for i, c in enumerate(_ALL_CASES)
-                 if not _plain_argv(c) or i % 5 == 0 or c["name"].startswith(("argc", "ed_thr_0", "scoring_0")) or c["status"] != 0]
+                 if not _plain_argv(c) or i % 10 == 0 or c["name"].startswith(("argc", "ed_thr_0", "scoring_0")) or c["status"] != 0]
 
 
 @pytest.mark.parametrize("case", _BINARY_CASES, ids=lambda c: c["name"])
