@@ -310,14 +310,11 @@ def main():
     os.dup2(2, 1)
     if args.geom:
         os.environ["SD_GEOM"] = args.geom
-    ws, rank, local = dist_setup(args.gpus)
     if args.impl == "reference":
-        run_reference_arm(args, ws, rank)
-        if ws > 1:
-            import torch.distributed as dist
-            dist.barrier()
-            dist.destroy_process_group()
+        # CPU only: rank 0 of a torchrun launch runs it, the other ranks exit at once (no process group, no GPU touched)
+        run_reference_arm(args, int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")))
         return
+    ws, rank, local = dist_setup(args.gpus)
 
     import torch
     from stringdecomposer_b200 import Decomposer, int_peak
