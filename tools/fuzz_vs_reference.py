@@ -16,7 +16,7 @@ sys.path.insert(0, ROOT)
 from stringdecomposer_b200 import synth  # noqa: E402
 
 REF = os.path.join(ROOT, "oracle", "_ref", "dp")
-EMU = os.path.join(ROOT, "tests", "emu", "_build", "dp_emu")
+EMU = os.environ.get("SD_FUZZ_BINARY") or os.path.join(ROOT, "tests", "emu", "_build", "dp_emu")     # e.g. a sanitizer build of dp_emu
 SCORINGS = [(-1, -1, -1, 1), (-2, -2, -3, 1), (-3, -2, -4, 2), (0, -1, -1, 1), (-1, 0, -1, 1), (-1, -1, -1, 5), (-6, -6, -6, 1), (-1, -2, 0, 0)]
 GEOMS = ["", "", "8,32,1", "12,16,2", "19,10,1", "24,8,3", "16,4,2", "48,2,1", "20,10,2", "24,8,1", "48,4,2", "32,8,1"]
 LATS = ["", "", "0", "6,32,4", "6,32,1", "12,16,2", "24,8,1", "12,32,1"]
@@ -90,6 +90,8 @@ def one(rng, seed, real=False):
         a = subprocess.run([REF, rp, mp] + tail, stdout=subprocess.PIPE, stderr=subprocess.PIPE, cwd=td)
         b = subprocess.run([EMU, rp, mp] + tail, stdout=subprocess.PIPE, stderr=subprocess.PIPE, cwd=td, env=env)
         berr = b"".join(ln for ln in b.stderr.splitlines(True) if not ln.startswith(b"[sd_b200]"))
+        if b"Sanitizer" in b.stderr or b"runtime error" in b.stderr:
+            print("SANITIZER REPORT seed=%d\n%s" % (seed, b.stderr.decode(errors="replace")[:3000]), flush=True)
         same = a.returncode == b.returncode and a.stdout == b.stdout and a.stderr == berr
         if not same:
             keep = tempfile.mkdtemp(prefix="fuzz_fail_%d_" % seed)
