@@ -8,8 +8,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 GOLDEN = os.path.join(HERE, "golden")
 DP_CUDA = os.path.join(ROOT, "stringdecomposer_b200", "build", "bin", "dp")
-DP_EMU = os.path.join(HERE, "emu", "_build", "dp_emu")
-EMU_LIB = os.path.join(HERE, "emu", "_build", "libsd_emu.so")
+EMU_DIR = os.environ.get("SD_EMU_DIR") or os.path.join(HERE, "emu", "_build")     # override: a sanitizer build of the emulator
+DP_EMU = os.path.join(EMU_DIR, "dp_emu")
+EMU_LIB = os.path.join(EMU_DIR, "libsd_emu.so")
 DP_ORACLE = os.path.join(ROOT, "oracle", "_build", "oracle_dp")
 DP_REF = os.path.join(ROOT, "oracle", "_ref", "dp")
 
