@@ -8,6 +8,7 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <exception>
 #include <future>
 #include <mutex>
 #include <stdexcept>
@@ -199,10 +200,15 @@ public:
         epoch_.fetch_add(1);
         { std::lock_guard<std::mutex> l(mu_); }          // a thread between its check and its wait holds the mutex
         cv_.notify_all();
-        fn(0);
-        for (int spin = 0; spin < (1 << 14); ++spin) { if (pending_.load() == 0) return; relax(); }
-        std::unique_lock<std::mutex> l(mu_);
-        done_.wait(l, [this] { return pending_.load() == 0; });
+        std::exception_ptr thrown;                      // the workers hold references into the caller's frame: always wait for them
+        try { fn(0); } catch (...) { thrown = std::current_exception(); }
+        bool all_done = false;
+        for (int spin = 0; spin < (1 << 14) && !all_done; ++spin) { all_done = pending_.load() == 0; if (!all_done) relax(); }
+        if (!all_done) {
+            std::unique_lock<std::mutex> l(mu_);
+            done_.wait(l, [this] { return pending_.load() == 0; });
+        }
+        if (thrown) std::rethrow_exception(thrown);
     }
 
 private:
