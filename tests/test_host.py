@@ -223,3 +223,10 @@ def test_pinned_host_buffer_gives_the_same_records():
     b = dec.decompose((buf, off))
     assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
     dec.close()
+
+
+def test_block_cache_policy():
+    # csrc/block_cache.h (best fit within 4x, bounds per device and kind, flush, the off switch) on opaque pointers
+    import subprocess
+    p = subprocess.run([os.path.join(cases.HERE, "emu", "_build", "block_cache_test")], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert p.returncode == 0, p.stderr.decode()
