@@ -51,7 +51,8 @@ def one(rng, seed, real=False):
         overlap = rng.choice([500, 500, 300, 0])
     else:
         alphabet = rng.choice(["A", "AC", "ACG", "ACGT", "ACGT", "ACGTN"])
-        rn, rr, mn, mm = synth.random_case(seed, alphabet=alphabet, n_monomers=(1, 8), mono_len=(1, 90), n_reads=(1, 4), read_len=(1, 1500))
+        nmon = (1, 8) if rng.random() < 0.8 else (20, 70)            # now and then a large set: many slots, slot groups
+        rn, rr, mn, mm = synth.random_case(seed, alphabet=alphabet, n_monomers=nmon, mono_len=(1, 90), n_reads=(1, 4), read_len=(1, 1500))
         part = rng.choice([50, 137, 300, 700, 1000])
         overlap = rng.choice([0, 10, 40, part // 3, part - 1])
     tail = [str(rng.randint(1, 4)), str(part), str(overlap)]
@@ -65,11 +66,11 @@ def one(rng, seed, real=False):
     lmax = max(len(m) for m in mm)
     if geom:
         c, t, _ = map(int, geom.split(","))
-        if c * t < lmax:
+        if c * t < lmax or len(mm) > 12:         # a forced geometry that cannot hold the set is a loud error, not a case
             geom = ""
     if "," in lat:
         c, t, w = lat.split(",")
-        if int(c) * int(t) >= lmax:
+        if int(c) * int(t) >= lmax and len(mm) <= 12:            # a forced cluster shape must be able to hold the set (else: loud error)
             env.update({"SD_LAT": "1", "SD_GEOM": "%s,%s,1" % (c, t), "SD_LAT_WARPS": w})
     else:
         if geom:
@@ -82,7 +83,9 @@ def one(rng, seed, real=False):
         env["SD_DEVICES"] = str(rng.choice([2, 3, 4]))
     if rng.random() < 0.3:
         env["SD_FORCE_S32"] = "1"
-    knobs = {k: env[k] for k in ("SD_GEOM", "SD_LAT", "SD_LAT_WARPS", "SD_CHUNK_BASES", "SD_DEVICES", "SD_FORCE_S32") if k in env}
+    if rng.random() < 0.25 and "SD_LAT_WARPS" not in env:
+        env["SD_GROUP_SLOTS"] = rng.choice(["1", "2", "4"])           # group sweep: a segment's slots spread over several CTAs
+    knobs = {k: env[k] for k in ("SD_GEOM", "SD_LAT", "SD_LAT_WARPS", "SD_CHUNK_BASES", "SD_DEVICES", "SD_FORCE_S32", "SD_GROUP_SLOTS") if k in env}
     with tempfile.TemporaryDirectory() as td:
         rp, mp = os.path.join(td, "reads.fa"), os.path.join(td, "monomers.fa")
         open(rp, "w").write(fasta(rn, rr, rng.choice([0, 0, 60, 7])))
