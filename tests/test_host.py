@@ -230,3 +230,26 @@ def test_block_cache_policy():
     import subprocess
     p = subprocess.run([os.path.join(cases.HERE, "emu", "_build", "block_cache_test")], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert p.returncode == 0, p.stderr.decode()
+
+
+@pytest.mark.parametrize("N", [1, 5, 13, 32, 33, 100, 256, 1000, 2047])
+def test_planner_covers_monomer_set_shapes(N):
+    # from one row of one symbol to 2047 monomers and rows of 1536 bp: the planner must find a geometry (single CTA,
+    # cluster or slot groups, s16x2 or s32) and the emulated kernels must reproduce the oracle through it
+    import numpy as np
+    rng = np.random.default_rng(N)
+    al = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+    def rs(n):
+        return al[rng.integers(0, 4, n)].tobytes().decode()
+    for L in (1, 7, 48, 171, 340, 700, 1536):
+        if N * L > 200000:
+            continue
+        mons = [rs(int(rng.integers(max(1, L // 2), L + 1))) for _ in range(N)]
+        mons[0] = rs(L)
+        seg = rs(40)
+        d = Decomposer(mons, flavour=cases.EMU_LIB)
+        recs, off = d.decompose([seg])
+        d.close()
+        got = [(int(r["row"]), int(r["start"]), int(r["end"]), float(r["score"])) for r in recs]
+        assert got == sd_oracle.align_segment(seg, mons, (-1, -1, -1, 1)), (N, L)
